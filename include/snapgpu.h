@@ -1,0 +1,171 @@
+/*
+ * snapgpu.h -- C ABI of libsnapgpu, the B200 (sm_100a) drop-in for the one data-parallel
+ * hot path of Ubuntu's `snappy` package manager: per-file SHA-512 for hashes.yaml and the
+ * byte-wise file compare.  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Every entry point below names the reference interface it replaces (paths relative to the
+ * reference tree).  INTEGRATION.md shows the cgo binding for each.
+ *
+ * Conventions
+ *   - int-returning functions: 0 on success, negative on failure (SNAPGPU_E*); the text of
+ *     the failure is in snapgpu_last_error() (thread-local, owned by the library).
+ *   - there is NO CPU fallback: without a usable CUDA device every compute call fails.
+ *   - every call is synchronous on return (the caller's buffers may be reused or freed, as
+ *     cgo requires), except the *_device calls, which enqueue on the stream they are given.
+ *   - thread-safe: calls may come from any OS thread; per-device work is serialised inside.
+ */
+#ifndef SNAPGPU_H
+#define SNAPGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNAPGPU_OK        0
+#define SNAPGPU_ECUDA    -1   /* CUDA runtime/driver failure (no device, OOM, launch error) */
+#define SNAPGPU_EINVAL   -2   /* bad argument */
+#define SNAPGPU_EIO      -3   /* host file I/O failed; errno text in last_error */
+#define SNAPGPU_EMODE    -4   /* "Unknown file mode" (snappy/hashes.go:44) */
+#define SNAPGPU_ENAME    -5   /* file name outside what the YAML writer supports */
+#define SNAPGPU_ENOINIT  -6   /* snapgpu_init not called / failed */
+
+/* ---- lifetime ---------------------------------------------------------------------- */
+
+/* Bind the library to `ndev` CUDA devices (ordinals in `devices`; NULL = 0..ndev-1;
+ * ndev <= 0 = every visible device).  Creates per-device streams and staging buffers.
+ * Idempotent; a second call with a different device list re-initialises. */
+int snapgpu_init(const int *devices, int ndev);
+void snapgpu_shutdown(void);
+int snapgpu_num_devices(void);                 /* devices bound by snapgpu_init */
+const char *snapgpu_last_error(void);
+const char *snapgpu_version(void);
+
+/* Tunables (all optional).  Known keys: "staging_bytes" (per-device H2D chunk, default
+ * 256 MiB), "sha_warps_per_sm" (0 = auto), "sha_variant" (0 = auto). */
+int snapgpu_set_option(const char *key, long long value);
+
+/* C-owned pinned host memory for the Go side to pack file contents into
+ * (cgo: C must not keep Go pointers; pinned memory makes the H2D copy DMA-direct). */
+void *snapgpu_alloc_pinned(size_t bytes);
+void snapgpu_free_pinned(void *p);
+
+/* ---- batch kernels, host buffers (the end-to-end path) -------------------------------
+ *
+ * Replaces the arithmetic of helpers.Sha512sum (helpers/helpers.go:188-201; Go stdlib
+ * crypto/sha512 behind it) for `nfiles` files at once.  File i is
+ * data[offsets[i] .. offsets[i]+lengths[i]).  digests receives nfiles*64 bytes: the
+ * big-endian H0..H7 of FIPS 180-4, i.e. exactly hasher.Sum(nil).  Fast path when every
+ * offset is a multiple of 16 (and `data` is 16-byte aligned); any alignment is accepted.
+ * With several devices bound the file list is sharded across them; no collective.
+ */
+int snapgpu_sha512_batch(const uint8_t *data, const uint64_t *offsets, const uint64_t *lengths,
+                         size_t nfiles, uint8_t *digests);
+
+/* Streaming form for one long message, the shape of Go's hash.Hash Write/Sum that
+ * helpers.Sha512sum drives through io.Copy (helpers/helpers.go:195-200): `state` is 64
+ * caller-owned bytes carrying the chaining value between calls.  first != 0 starts from
+ * the SHA-512 IV; every call but the final one must pass a multiple of 128 bytes;
+ * prefix_bytes = bytes already hashed; final != 0 pads and leaves the digest in `state`. */
+int snapgpu_sha512_stream(uint8_t state[64], int first, const uint8_t *data, uint64_t len,
+                          uint64_t prefix_bytes, int final);
+
+/* Replaces streamsEqual / bytes.Equal (helpers/cmp.go:61-86) for `npairs` pairs whose sizes
+ * were already found equal on the host (helpers/cmp.go:54).  Pair i is a[off..off+len) vs
+ * b[off..off+len).  equal[i] = 1 if identical, else 0. */
+int snapgpu_cmp_batch(const uint8_t *a, const uint8_t *b, const uint64_t *offsets,
+                      const uint64_t *lengths, size_t npairs, uint8_t *equal);
+
+/* ---- batch kernels, device-resident data (kernel-only path) --------------------------
+ *
+ * Same contracts, but `d_data`/`d_a`/`d_b`/`d_digests`/`d_equal` are device pointers on
+ * bound device number `dev` (index into the snapgpu_init list) and the work is enqueued on
+ * `stream` (a cudaStream_t passed as void*; NULL = the legacy default stream).  offsets and
+ * lengths stay host arrays (they come from stat(2)).  The allocation behind d_data must
+ * extend to the next 16-byte boundary past the last file.  Returns after enqueueing.
+ */
+int snapgpu_sha512_batch_device(int dev, const void *d_data, const uint64_t *offsets,
+                                const uint64_t *lengths, size_t nfiles, void *d_digests,
+                                void *stream);
+int snapgpu_cmp_batch_device(int dev, const void *d_a, const void *d_b, const uint64_t *offsets,
+                             const uint64_t *lengths, size_t npairs, void *d_equal, void *stream);
+
+/* ---- whole-function drop-ins (host side in C++, same semantics as the Go functions) --- */
+
+/* helpers.Sha512sum (helpers/helpers.go:188): lowercase hex digest of one file.
+ * SNAPGPU_EIO mirrors the os.Open / io.Copy error return. */
+int snapgpu_sha512sum_file(const char *infile, char hexdigest[129]);
+
+/* writeHashes (snappy/build.go:216-270): hash data_tar, walk build_dir in filepath.Walk
+ * order, skip "/DEBIAN*", emit DEBIAN/hashes.yaml byte-identical to yaml.v2's output. */
+int snapgpu_write_hashes(const char *build_dir, const char *data_tar);
+
+/* Same walk, but returns the YAML in a malloc'd buffer (*out, *out_len; free with
+ * snapgpu_free) instead of only writing the file; used by tests and the Go shim's
+ * verification mode. */
+int snapgpu_hashes_yaml(const char *build_dir, const char *data_tar, char **out, size_t *out_len);
+
+/* helpers.FilesAreEqual (helpers/cmp.go:31): 1 equal, 0 not equal OR any error. */
+int snapgpu_files_are_equal(const char *a, const char *b);
+
+/* helpers.DirUpdated (helpers/cmp.go:97): names (pfx+basename) of files present in both
+ * directories whose contents differ.  *names is a malloc'd block of NUL-terminated strings
+ * laid end to end (sorted), *count their number; free with snapgpu_free.  All pairs of one
+ * call are compared in a single batched launch. */
+int snapgpu_dir_updated(const char *dir_a, const char *dir_b, const char *pfx, char **names,
+                        size_t *count);
+
+/* policy.AppArmorDelta (policy/policy.go:162): DirUpdated over policygroups and templates. */
+int snapgpu_apparmor_delta(const char *old_path, const char *new_path, const char *prefix,
+                           char **policies, size_t *npolicies, char **templates,
+                           size_t *ntemplates);
+
+void snapgpu_free(void *p);
+
+/* ---- synthetic inputs and instrumentation (bench/test support, not product API) ------ */
+
+/* Fill device memory with the deterministic benchmark content of SURVEY.md section 8(d):
+ * little-endian u64 word j of file i = splitmix64(seed + i*0x9E3779B97F4A7C15 + j). */
+int snapgpu_synth_fill_device(int dev, void *d_data, const uint64_t *offsets,
+                              const uint64_t *lengths, size_t nfiles, uint64_t first_index,
+                              uint64_t seed, void *stream);
+
+/* Counters since init (or the last reset): kernel launches made by this library, and the
+ * device time of the last sha512/cmp launch group as measured with CUDA events. */
+typedef struct snapgpu_stats {
+    uint64_t kernel_launches;
+    uint64_t sha512_launches;
+    uint64_t cmp_launches;
+    uint64_t h2d_bytes;
+    uint64_t d2h_bytes;
+    double last_sha512_kernel_ms;   /* CUDA-event time of the most recent launch */
+    double last_cmp_kernel_ms;
+    double sha512_kernel_ms_sum;    /* summed over the launches timed since the last reset */
+    uint64_t sha512_kernel_timed;
+    double cmp_kernel_ms_sum;
+    uint64_t cmp_kernel_timed;
+} snapgpu_stats;
+int snapgpu_get_stats(snapgpu_stats *out);
+void snapgpu_reset_stats(void);
+
+/* Integer-pipe micro-benchmark that defines the measured SHA-512 roofline: runs a
+ * register-only loop of the named instruction mix on device `dev` and returns warp
+ * instructions per clock per SM.  kind: 0 IADD3, 1 LOP3, 2 SHF, 3 IMAD, 4 IMAD.WIDE,
+ * 5 ALU+IMAD interleaved, 6 ALU+IMAD.WIDE interleaved. */
+int snapgpu_pipe_microbench(int dev, int kind, int warps_per_sm, double *inst_per_clk_per_sm,
+                            double *elapsed_ms, double *sm_clock_mhz);
+
+/* ---- test hooks: host logic only, usable without a GPU (see tests/) -------------------- */
+int snapgpu_test_yaml_from_digests(const char *build_dir, const uint8_t *digests, size_t ndigests,
+                                   char **out, size_t *out_len);
+int snapgpu_test_plan_order(const uint64_t *lengths, size_t n, uint32_t *order);
+int snapgpu_test_shard(const uint64_t *weights, size_t n, int ndev, int *device_of);
+long long snapgpu_test_chunks(const uint64_t *offsets, const uint64_t *lengths, size_t n,
+                              uint64_t cap, int is_sha, uint64_t *rows, size_t max_rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNAPGPU_H */

@@ -1,0 +1,36 @@
+"""Mirror of the hashes writer of the reference's ``snappy`` package.
+
+* ``writeHashes``   /root/reference/snappy/build.go:216-270
+* ``hashes_yaml``   the same walk, returning the document instead of writing it
+
+The tree walk, the batching of every regular file into one GPU call and the yaml.v2-exact
+emitter all live in libsnapgpu (csrc/host_path.cpp); this module is the binding.
+"""
+from __future__ import annotations
+
+import ctypes
+
+from . import _native as N
+
+
+class UnknownFileMode(Exception):
+    """yamlFileMode.MarshalYAML's "Unknown file mode" (snappy/hashes.go:44)."""
+
+
+def _raise(rc: int):
+    if rc == N.EIO:
+        raise OSError(N.last_error())
+    if rc == N.EMODE:
+        raise UnknownFileMode(N.last_error())
+    N.check(rc)
+
+
+def writeHashes(buildDir: str, dataTar: str) -> None:
+    """Write ``<buildDir>/DEBIAN/hashes.yaml``; the first error aborts, as in the reference."""
+    _raise(N.lib().snapgpu_write_hashes(N.fs(buildDir), N.fs(dataTar)))
+
+
+def hashes_yaml(buildDir: str, dataTar: str) -> bytes:
+    ptr, length = ctypes.c_void_p(), ctypes.c_size_t()
+    _raise(N.lib().snapgpu_hashes_yaml(N.fs(buildDir), N.fs(dataTar), ctypes.byref(ptr), ctypes.byref(length)))
+    return N.take_string(ptr, length.value)

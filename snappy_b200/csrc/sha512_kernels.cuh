@@ -1,0 +1,180 @@
+// sha512_kernels.cuh -- batched multi-message SHA-512 over a packed buffer of files.
+//
+// Device side of snapgpu_sha512_batch[_device]; replaces the per-file loop
+//   snappy/build.go:240-247  ->  helpers.Sha512sum (helpers/helpers.go:188-201).
+//
+// Work layout
+//   * the host sorts the segment descriptors by 128-byte block count, longest first
+//     (length binning: the 32 lanes of a warp get neighbours of the sorted list, so they
+//     run the same number of blocks and stay converged);
+//   * a "unit" is 32 consecutive descriptors = one warp's worth of files;
+//   * the kernel is persistent: one CTA of 4 warps per (SM x kCtasPerSm), every warp pulls
+//     the next unit from a global counter (longest-processing-time-first list scheduling,
+//     which is what bounds the makespan when a few files are much longer than the rest);
+//   * each lane walks its own file: 8 x 128-bit loads per block straight into registers,
+//     issued one block ahead of the compression that consumes them.
+//
+// A descriptor is a *segment* of a message so that a file larger than the staging buffer
+// can be hashed in pieces: kSegContinue takes the chaining value from the output slot,
+// kSegNoFinal stores the chaining value instead of padding and finishing.
+#pragma once
+#include "sha512_core.cuh"
+
+namespace snapgpu {
+
+struct SegDesc {
+    u64 off;      // byte offset of the segment in the packed buffer
+    u64 len;      // bytes in this segment (multiple of 128 unless it is the final one)
+    u64 prefix;   // message bytes that came before this segment
+    u32 out_idx;  // digest slot
+    u32 flags;
+};
+enum : u32 { kSegContinue = 1u, kSegNoFinal = 2u };
+
+__host__ __device__ inline u64 seg_blocks(u64 len, u32 flags) {
+    return (flags & kSegNoFinal) ? (len >> 7) : ((len + 144) >> 7);   // (L+144)/128
+}
+
+constexpr int kShaWarpsPerCta = 4;
+constexpr int kShaThreads = kShaWarpsPerCta * 32;
+
+__device__ __forceinline__ uint4 ldg_nc_v4(const void *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ u32 ldg_nc_u32(const void *p) {
+    u32 v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// Raw 128 bytes of one block as 32 little-endian words, loads predicated on the bytes that
+// exist (rem = bytes of the segment left at this block; <= 0 means none).
+template <bool kAligned16>
+__device__ __forceinline__ void load_block(const uint8_t *p, long long rem, u32 (&raw)[32]) {
+    if (kAligned16) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if ((long long)(16 * i) < rem) v = ldg_nc_v4(p + 16 * i);
+            raw[4 * i + 0] = v.x; raw[4 * i + 1] = v.y; raw[4 * i + 2] = v.z; raw[4 * i + 3] = v.w;
+        }
+    } else {
+        // any alignment: 33 aligned words, realigned with a funnel shift by the byte phase
+        const uintptr_t addr = (uintptr_t)p;
+        const int phase = (int)(addr & 3);
+        const uint8_t *base = p - phase;
+        u32 prev = 0;
+        if ((long long)(-phase) < rem) prev = ldg_nc_u32(base);
+#pragma unroll
+        for (int k = 0; k < 32; k++) {
+            u32 next = 0;
+            if ((long long)(4 * (k + 1) - phase) < rem) next = ldg_nc_u32(base + 4 * (k + 1));
+            raw[k] = __funnelshift_r(prev, next, 8 * phase);
+            prev = next;
+        }
+    }
+}
+
+// Turn the raw words of a block into big-endian message words and apply the FIPS 180-4
+// 5.1.2 padding when the block holds fewer than 128 message bytes.
+__device__ __forceinline__ void pad_block(u64 (&w)[16], long long rem, bool last_block, u64 total_len) {
+    if (rem >= 128) return;
+    const int r = rem > 0 ? (int)rem : 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        int nb = r - 8 * j;                       // message bytes in word j
+        nb = nb < 0 ? 0 : (nb > 8 ? 8 : nb);
+        u64 mask = nb == 0 ? 0ULL : (~0ULL << (64 - 8 * nb));
+        u64 v = w[j] & mask;
+        if (rem >= 0 && (r >> 3) == j) v |= 0x80ULL << (56 - 8 * (r & 7));
+        w[j] = v;
+    }
+    if (last_block) {
+        w[14] = total_len >> 61;
+        w[15] = total_len << 3;
+    }
+}
+
+template <int kRoundFma, int kSchedFma, bool kAligned16, int kCtasPerSm>
+__global__ void __launch_bounds__(kShaThreads, kCtasPerSm)
+sha512_segments_kernel(const uint8_t *__restrict__ data, const SegDesc *__restrict__ descs, u32 nsegs,
+                       uint8_t *__restrict__ digests, u32 *__restrict__ unit_counter, u32 one) {
+    const u32 lane = threadIdx.x & 31;
+    const u32 warp = threadIdx.x >> 5;
+    const u32 nunits = (nsegs + 31) >> 5;
+    const u32 total_warps = gridDim.x * kShaWarpsPerCta;
+    // first unit: consecutive (long) units land on different CTAs, hence different SMs
+    u32 unit = warp * gridDim.x + blockIdx.x;
+
+    while (unit < nunits) {
+        const u32 idx = unit * 32 + lane;
+        const bool have = idx < nsegs;
+        SegDesc sd;
+        sd.off = 0; sd.len = 0; sd.prefix = 0; sd.out_idx = 0; sd.flags = kSegNoFinal;
+        if (have) {
+            const uint4 *q = reinterpret_cast<const uint4 *>(descs + idx);
+            uint4 q0 = q[0], q1 = q[1];
+            sd.off = pack64(q0.x, q0.y); sd.len = pack64(q0.z, q0.w);
+            sd.prefix = pack64(q1.x, q1.y); sd.out_idx = q1.z; sd.flags = q1.w;
+        }
+        const u32 nblk = have ? (u32)seg_blocks(sd.len, sd.flags) : 0u;
+        const u32 nblk_max = __reduce_max_sync(0xffffffffu, nblk);
+        const bool final_seg = !(sd.flags & kSegNoFinal);
+        const u64 total_len = sd.prefix + sd.len;
+        uint8_t *out = digests + (size_t)sd.out_idx * 64;
+
+        u64 st[8];
+        if (have && (sd.flags & kSegContinue)) {
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(out);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint4 v = s4[i];
+                st[2 * i] = be64_from_le_words(v.x, v.y);
+                st[2 * i + 1] = be64_from_le_words(v.z, v.w);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) st[i] = kIV512[i];
+        }
+
+        const uint8_t *p = data + sd.off;
+        long long rem = (long long)sd.len;
+        u32 raw[32];
+        load_block<kAligned16>(p, rem, raw);
+
+        for (u32 blk = 0; blk < nblk_max; blk++) {
+            u64 w[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) w[j] = be64_from_le_words(raw[2 * j], raw[2 * j + 1]);
+            const bool active = blk < nblk;
+            const long long rem_now = rem;
+            // next block's bytes are requested before this block's 80 rounds
+            p += 128;
+            rem -= 128;
+            load_block<kAligned16>(p, rem, raw);
+            if (__any_sync(0xffffffffu, active && rem_now < 128))
+                pad_block(w, rem_now, final_seg && (blk + 1 == nblk), total_len);
+            sha512_compress<kRoundFma, kSchedFma>(st, w, active, one);
+        }
+
+        if (have) {
+            uint4 *o4 = reinterpret_cast<uint4 *>(out);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                u32 a_lo, a_hi, b_lo, b_hi;
+                unpack64(st[2 * i], a_lo, a_hi);
+                unpack64(st[2 * i + 1], b_lo, b_hi);
+                o4[i] = make_uint4(bswap32(a_hi), bswap32(a_lo), bswap32(b_hi), bswap32(b_lo));
+            }
+        }
+
+        u32 next = 0;
+        if (lane == 0) next = atomicAdd(unit_counter, 1u) + total_warps;
+        unit = __shfl_sync(0xffffffffu, next, 0);
+    }
+}
+
+}  // namespace snapgpu

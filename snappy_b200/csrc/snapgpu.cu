@@ -1,0 +1,1070 @@
+// snapgpu.cu -- CUDA runtime layer of libsnapgpu: device contexts, length-binned launch
+// plans, the double-buffered host->device pipeline, the file-list sharder for 1/2/4/8 GPUs,
+// and the extern "C" batch entry points declared in include/snapgpu.h.
+//
+// There is deliberately no CPU implementation of either hot op in this library: if CUDA is
+// unavailable every compute entry point returns SNAPGPU_ECUDA / SNAPGPU_ENOINIT.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <thread>
+
+#include "cmp_kernels.cuh"
+#include "pipe_microbench.cuh"
+#include "runtime.hpp"
+#include "sha512_kernels.cuh"
+
+namespace snapgpu {
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+
+static thread_local std::string g_last_error;
+
+void set_error(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define SG_CUDA(call)                                                                         \
+    do {                                                                                      \
+        cudaError_t sg_e_ = (call);                                                           \
+        if (sg_e_ != cudaSuccess)                                                             \
+            return fail(SNAPGPU_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(sg_e_), \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+std::string hex_lower(const uint8_t *p, size_t n) {
+    static const char d[] = "0123456789abcdef";
+    std::string s(2 * n, '0');
+    for (size_t i = 0; i < n; i++) {
+        s[2 * i] = d[p[i] >> 4];
+        s[2 * i + 1] = d[p[i] & 15];
+    }
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------
+// device context
+// ------------------------------------------------------------------------------------------
+
+constexpr int kPlanSlots = 4;
+constexpr size_t kMaxChunkItems = 1u << 20;
+constexpr uint64_t kMaxSegBytes = 1ULL << 39;   // block counts stay below 2^32
+constexpr size_t kStageSlack = 256;
+
+struct PlanSlot {
+    void *h_buf = nullptr;    // pinned
+    void *d_buf = nullptr;
+    size_t cap = 0;           // bytes
+    u32 *d_counter = nullptr;
+    cudaEvent_t done = nullptr;
+    bool in_flight = false;
+};
+
+struct TimedLaunch {
+    cudaEvent_t beg = nullptr, end = nullptr;
+    bool pending = false;
+};
+
+struct Device {
+    int ordinal = -1;
+    int sm_count = 0;
+    std::mutex mu;
+    cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+    PlanSlot slots[kPlanSlots];
+    int next_slot = 0;
+    // host-buffer pipeline (allocated on first use)
+    uint8_t *d_stage[2] = {nullptr, nullptr};
+    size_t stage_cap = 0;
+    uint8_t *d_out[2] = {nullptr, nullptr};
+    uint8_t *h_out[2] = {nullptr, nullptr};
+    size_t out_cap = 0;       // bytes
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    // kernel timing ring (events on the launching stream)
+    TimedLaunch sha_t[8], cmp_t[8];
+    int sha_ti = 0, cmp_ti = 0;
+    double sha_ms_sum = 0, cmp_ms_sum = 0, sha_ms_last = 0, cmp_ms_last = 0;
+    uint64_t sha_ms_n = 0, cmp_ms_n = 0;
+};
+
+struct Options {
+    std::atomic<long long> staging_bytes{256ll << 20};
+    std::atomic<long long> sha_warps_per_sm{0};
+    std::atomic<long long> sha_variant{0};
+    std::atomic<long long> cmp_ctas_per_sm{0};
+    std::atomic<long long> time_kernels{1};
+};
+
+struct Runtime {
+    std::mutex mu;
+    std::vector<std::unique_ptr<Device>> devs;
+    Options opt;
+    std::atomic<uint64_t> kernel_launches{0}, sha_launches{0}, cmp_launches{0}, h2d_bytes{0}, d2h_bytes{0};
+};
+
+static Runtime &rt() {
+    static Runtime r;
+    return r;
+}
+
+bool runtime_ready() { return !rt().devs.empty(); }
+size_t staging_bytes() { return (size_t)rt().opt.staging_bytes.load(); }
+
+static void destroy_device(Device &D) {
+    if (D.ordinal < 0) return;
+    cudaSetDevice(D.ordinal);
+    cudaDeviceSynchronize();
+    for (auto &s : D.slots) {
+        if (s.h_buf) cudaFreeHost(s.h_buf);
+        if (s.d_buf) cudaFree(s.d_buf);
+        if (s.d_counter) cudaFree(s.d_counter);
+        if (s.done) cudaEventDestroy(s.done);
+    }
+    for (int b = 0; b < 2; b++) {
+        if (D.d_stage[b]) cudaFree(D.d_stage[b]);
+        if (D.d_out[b]) cudaFree(D.d_out[b]);
+        if (D.h_out[b]) cudaFreeHost(D.h_out[b]);
+        if (D.ev_copied[b]) cudaEventDestroy(D.ev_copied[b]);
+        if (D.ev_done[b]) cudaEventDestroy(D.ev_done[b]);
+    }
+    for (auto &t : D.sha_t) { if (t.beg) cudaEventDestroy(t.beg); if (t.end) cudaEventDestroy(t.end); }
+    for (auto &t : D.cmp_t) { if (t.beg) cudaEventDestroy(t.beg); if (t.end) cudaEventDestroy(t.end); }
+    if (D.copy_stream) cudaStreamDestroy(D.copy_stream);
+    if (D.compute_stream) cudaStreamDestroy(D.compute_stream);
+    D.ordinal = -1;
+}
+
+static int init_device(Device &D, int ordinal) {
+    D.ordinal = ordinal;
+    SG_CUDA(cudaSetDevice(ordinal));
+    cudaDeviceProp prop;
+    SG_CUDA(cudaGetDeviceProperties(&prop, ordinal));
+    D.sm_count = prop.multiProcessorCount;
+    if (prop.major < 10)
+        return fail(SNAPGPU_ECUDA, "device %d is sm_%d%d; libsnapgpu is built for sm_100a only", ordinal,
+                    prop.major, prop.minor);
+    SG_CUDA(cudaStreamCreateWithFlags(&D.copy_stream, cudaStreamNonBlocking));
+    SG_CUDA(cudaStreamCreateWithFlags(&D.compute_stream, cudaStreamNonBlocking));
+    for (auto &s : D.slots) {
+        SG_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        SG_CUDA(cudaMalloc(&s.d_counter, 256));
+    }
+    for (int b = 0; b < 2; b++) {
+        SG_CUDA(cudaEventCreateWithFlags(&D.ev_copied[b], cudaEventDisableTiming));
+        SG_CUDA(cudaEventCreateWithFlags(&D.ev_done[b], cudaEventDisableTiming));
+    }
+    for (auto &t : D.sha_t) { SG_CUDA(cudaEventCreate(&t.beg)); SG_CUDA(cudaEventCreate(&t.end)); }
+    for (auto &t : D.cmp_t) { SG_CUDA(cudaEventCreate(&t.beg)); SG_CUDA(cudaEventCreate(&t.end)); }
+    return 0;
+}
+
+static int get_device(int dev, Device **out) {
+    auto &R = rt();
+    if (R.devs.empty()) return fail(SNAPGPU_ENOINIT, "snapgpu_init has not been called (or failed)");
+    if (dev < 0 || (size_t)dev >= R.devs.size()) return fail(SNAPGPU_EINVAL, "device index %d out of range", dev);
+    *out = R.devs[(size_t)dev].get();
+    return 0;
+}
+
+int ensure_init() {
+    if (runtime_ready()) return 0;
+    return snapgpu_init(nullptr, 0);
+}
+
+// Reserve a plan slot of at least `bytes`: waits for the launch that used it last.
+static int acquire_slot(Device &D, size_t bytes, PlanSlot **out) {
+    PlanSlot &s = D.slots[D.next_slot];
+    D.next_slot = (D.next_slot + 1) % kPlanSlots;
+    if (s.in_flight) {
+        SG_CUDA(cudaEventSynchronize(s.done));
+        s.in_flight = false;
+    }
+    if (s.cap < bytes) {
+        if (s.h_buf) cudaFreeHost(s.h_buf);
+        if (s.d_buf) cudaFree(s.d_buf);
+        s.h_buf = s.d_buf = nullptr;
+        s.cap = 0;
+        size_t want = std::max<size_t>(bytes + bytes / 4, 1u << 16);
+        SG_CUDA(cudaHostAlloc(&s.h_buf, want, cudaHostAllocPortable));
+        SG_CUDA(cudaMalloc(&s.d_buf, want));
+        s.cap = want;
+    }
+    *out = &s;
+    return 0;
+}
+
+static void harvest_timings(TimedLaunch *ring, int n, double &sum, uint64_t &cnt, double &last, bool wait) {
+    for (int i = 0; i < n; i++) {
+        TimedLaunch &t = ring[i];
+        if (!t.pending) continue;
+        if (wait) cudaEventSynchronize(t.end);
+        else if (cudaEventQuery(t.end) != cudaSuccess) continue;
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, t.beg, t.end) == cudaSuccess) {
+            sum += ms;
+            cnt++;
+            last = ms;
+        }
+        t.pending = false;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// SHA-512 launch: length binning + persistent kernel
+// ------------------------------------------------------------------------------------------
+
+typedef void (*ShaKernel)(const uint8_t *, const SegDesc *, u32, uint8_t *, u32 *, u32);
+
+constexpr int kShaCtasPerSmMax = 3;   // 168 registers per thread: no spills with the one-block-ahead prefetch
+constexpr int kShaVariants = 3;
+
+// variant 0: every 64-bit add on the FMA pipe; 1: every add on the ALU pipe (plain IADD3);
+// variant 2: round adds on FMA, schedule adds on ALU.
+static ShaKernel sha_kernel_for(int variant, bool aligned) {
+    switch (variant) {
+    case 1:
+        return aligned ? sha512_segments_kernel<0x00, 0x0, true, kShaCtasPerSmMax>
+                       : sha512_segments_kernel<0x00, 0x0, false, kShaCtasPerSmMax>;
+    case 2:
+        return aligned ? sha512_segments_kernel<0x7f, 0x0, true, kShaCtasPerSmMax>
+                       : sha512_segments_kernel<0x7f, 0x0, false, kShaCtasPerSmMax>;
+    default:
+        return aligned ? sha512_segments_kernel<0x7f, 0x7, true, kShaCtasPerSmMax>
+                       : sha512_segments_kernel<0x7f, 0x7, false, kShaCtasPerSmMax>;
+    }
+}
+
+// Sort `n` descriptors by block count, longest first, into `dst` (pinned).  Counting sort on
+// min(blocks, 65535); the (few) longer ones are ordered exactly with std::sort.
+static void bin_by_length(const SegDesc *src, size_t n, SegDesc *dst, uint64_t *total_blocks,
+                          uint64_t *max_blocks) {
+    constexpr uint32_t kCap = 65535;
+    std::vector<uint32_t> count(kCap + 2, 0);
+    uint64_t total = 0, mx = 0;
+    for (size_t i = 0; i < n; i++) {
+        uint64_t nb = seg_blocks(src[i].len, src[i].flags);
+        total += nb;
+        mx = std::max(mx, nb);
+        count[(size_t)std::min<uint64_t>(nb, kCap)]++;
+    }
+    // descending: start position of bucket k = number of items in buckets > k
+    std::vector<size_t> start(kCap + 2, 0);
+    size_t run = 0;
+    for (int64_t k = kCap; k >= 0; k--) {
+        start[(size_t)k] = run;
+        run += count[(size_t)k];
+    }
+    for (size_t i = 0; i < n; i++) {
+        uint64_t nb = seg_blocks(src[i].len, src[i].flags);
+        dst[start[(size_t)std::min<uint64_t>(nb, kCap)]++] = src[i];
+    }
+    if (count[kCap] > 1)
+        std::sort(dst, dst + count[kCap], [](const SegDesc &a, const SegDesc &b) {
+            return seg_blocks(a.len, a.flags) > seg_blocks(b.len, b.flags);
+        });
+    *total_blocks = total;
+    *max_blocks = mx;
+}
+
+// Enqueue the hashing of `n` segments of `d_data` on `stream`.  Caller holds D.mu.
+static int launch_sha512(Device &D, cudaStream_t stream, const uint8_t *d_data, const SegDesc *segs, size_t n,
+                         uint8_t *d_digests) {
+    if (n == 0) return 0;
+    if (n > 0xfffffff0ull) return fail(SNAPGPU_EINVAL, "too many files in one launch (%zu)", n);
+    auto &R = rt();
+    bool aligned = ((uintptr_t)d_data & 15) == 0;
+    for (size_t i = 0; i < n; i++) {
+        if (segs[i].len >= kMaxSegBytes) return fail(SNAPGPU_EINVAL, "file %zu too large (%llu bytes)", i,
+                                                     (unsigned long long)segs[i].len);
+        if ((segs[i].flags & kSegNoFinal) && (segs[i].len & 127))
+            return fail(SNAPGPU_EINVAL, "non-final segment %zu is not a multiple of 128 bytes", i);
+        aligned = aligned && ((segs[i].off & 15) == 0);
+    }
+    PlanSlot *slot;
+    int rc = acquire_slot(D, n * sizeof(SegDesc), &slot);
+    if (rc) return rc;
+    uint64_t total_blocks = 0, max_blocks = 0;
+    bin_by_length(segs, n, static_cast<SegDesc *>(slot->h_buf), &total_blocks, &max_blocks);
+
+    SG_CUDA(cudaMemcpyAsync(slot->d_buf, slot->h_buf, n * sizeof(SegDesc), cudaMemcpyHostToDevice, stream));
+    SG_CUDA(cudaMemsetAsync(slot->d_counter, 0, sizeof(u32), stream));
+
+    // warps per SM sub-partition: more hides latency better, fewer shortens the makespan when
+    // one file is a large share of a lane's work (see DESIGN.md "makespan").
+    int per_sm = (int)R.opt.sha_warps_per_sm.load();
+    if (per_sm <= 0) {
+        const uint64_t lanes = (uint64_t)D.sm_count * kShaThreads;
+        const uint64_t depth = max_blocks ? total_blocks / (lanes * max_blocks) : 1;
+        per_sm = (int)std::min<uint64_t>(std::max<uint64_t>(depth, 1), 3);
+    }
+    per_sm = std::min(per_sm, kShaCtasPerSmMax);
+    const u32 nunits = (u32)((n + 31) / 32);
+    const u32 want_ctas = (nunits + kShaWarpsPerCta - 1) / kShaWarpsPerCta;
+    const u32 grid = std::max<u32>(1, std::min<u32>((u32)(D.sm_count * per_sm), want_ctas));
+
+    ShaKernel k = sha_kernel_for((int)R.opt.sha_variant.load(), aligned);
+    TimedLaunch *tl = nullptr;
+    if (R.opt.time_kernels.load()) {
+        harvest_timings(D.sha_t, 8, D.sha_ms_sum, D.sha_ms_n, D.sha_ms_last, false);
+        tl = &D.sha_t[D.sha_ti];
+        D.sha_ti = (D.sha_ti + 1) % 8;
+        if (tl->pending) harvest_timings(tl, 1, D.sha_ms_sum, D.sha_ms_n, D.sha_ms_last, true);
+        SG_CUDA(cudaEventRecord(tl->beg, stream));
+    }
+    k<<<grid, kShaThreads, 0, stream>>>(d_data, static_cast<const SegDesc *>(slot->d_buf), (u32)n, d_digests,
+                                         slot->d_counter, 1u);
+    SG_CUDA(cudaGetLastError());
+    if (tl) {
+        SG_CUDA(cudaEventRecord(tl->end, stream));
+        tl->pending = true;
+    }
+    SG_CUDA(cudaEventRecord(slot->done, stream));
+    slot->in_flight = true;
+    R.kernel_launches++;
+    R.sha_launches++;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// cmp launch
+// ------------------------------------------------------------------------------------------
+
+struct CmpItem {
+    uint64_t off, len;
+};
+
+static int launch_cmp(Device &D, cudaStream_t stream, const uint8_t *d_a, const uint8_t *d_b, const CmpItem *items,
+                      size_t n, uint8_t *d_equal) {
+    if (n == 0) return 0;
+    if (n > 0xfffffff0ull) return fail(SNAPGPU_EINVAL, "too many pairs in one launch (%zu)", n);
+    auto &R = rt();
+    PlanSlot *slot;
+    int rc = acquire_slot(D, (n + 1) * sizeof(CmpPair), &slot);
+    if (rc) return rc;
+    CmpPair *hp = static_cast<CmpPair *>(slot->h_buf);
+    bool aligned = (((uintptr_t)d_a | (uintptr_t)d_b) & 15) == 0;
+    uint64_t tiles = 0;
+    for (size_t i = 0; i < n; i++) {
+        hp[i].off = items[i].off;
+        hp[i].len = items[i].len;
+        hp[i].first_tile = tiles;
+        tiles += (items[i].len + kCmpTileBytes - 1) / kCmpTileBytes;
+        aligned = aligned && ((items[i].off & 15) == 0);
+    }
+    hp[n].off = 0;
+    hp[n].len = 0;
+    hp[n].first_tile = tiles;
+    SG_CUDA(cudaMemsetAsync(d_equal, 1, n, stream));
+    if (tiles == 0) return 0;
+    SG_CUDA(cudaMemcpyAsync(slot->d_buf, slot->h_buf, (n + 1) * sizeof(CmpPair), cudaMemcpyHostToDevice, stream));
+    int per_sm = (int)R.opt.cmp_ctas_per_sm.load();
+    if (per_sm <= 0) per_sm = 8;
+    const uint64_t grid64 = std::min<uint64_t>((uint64_t)D.sm_count * per_sm, tiles);
+    const u32 grid = (u32)std::max<uint64_t>(1, grid64);
+    TimedLaunch *tl = nullptr;
+    if (R.opt.time_kernels.load()) {
+        harvest_timings(D.cmp_t, 8, D.cmp_ms_sum, D.cmp_ms_n, D.cmp_ms_last, false);
+        tl = &D.cmp_t[D.cmp_ti];
+        D.cmp_ti = (D.cmp_ti + 1) % 8;
+        if (tl->pending) harvest_timings(tl, 1, D.cmp_ms_sum, D.cmp_ms_n, D.cmp_ms_last, true);
+        SG_CUDA(cudaEventRecord(tl->beg, stream));
+    }
+    if (aligned)
+        cmp_pairs_kernel<true><<<grid, kCmpThreads, 0, stream>>>(d_a, d_b, static_cast<const CmpPair *>(slot->d_buf),
+                                                                 (u32)n, tiles, d_equal);
+    else
+        cmp_pairs_kernel<false><<<grid, kCmpThreads, 0, stream>>>(d_a, d_b, static_cast<const CmpPair *>(slot->d_buf),
+                                                                  (u32)n, tiles, d_equal);
+    SG_CUDA(cudaGetLastError());
+    if (tl) {
+        SG_CUDA(cudaEventRecord(tl->end, stream));
+        tl->pending = true;
+    }
+    SG_CUDA(cudaEventRecord(slot->done, stream));
+    slot->in_flight = true;
+    R.kernel_launches++;
+    R.cmp_launches++;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-buffer pipeline: pack spans -> H2D -> kernel -> D2H, double buffered
+// ------------------------------------------------------------------------------------------
+
+static int ensure_staging(Device &D, size_t stage_bytes, size_t out_bytes) {
+    if (D.stage_cap < stage_bytes) {
+        for (int b = 0; b < 2; b++) {
+            if (D.d_stage[b]) cudaFree(D.d_stage[b]);
+            D.d_stage[b] = nullptr;
+        }
+        D.stage_cap = 0;
+        for (int b = 0; b < 2; b++) SG_CUDA(cudaMalloc(&D.d_stage[b], stage_bytes + kStageSlack));
+        D.stage_cap = stage_bytes;
+    }
+    if (D.out_cap < out_bytes) {
+        for (int b = 0; b < 2; b++) {
+            if (D.d_out[b]) cudaFree(D.d_out[b]);
+            if (D.h_out[b]) cudaFreeHost(D.h_out[b]);
+            D.d_out[b] = D.h_out[b] = nullptr;
+        }
+        D.out_cap = 0;
+        size_t want = std::max<size_t>(out_bytes + out_bytes / 2, 1u << 16);
+        for (int b = 0; b < 2; b++) {
+            SG_CUDA(cudaMalloc(&D.d_out[b], want));
+            SG_CUDA(cudaHostAlloc(&D.h_out[b], want, cudaHostAllocPortable));
+        }
+        D.out_cap = want;
+    }
+    return 0;
+}
+
+// A unit of pipelined work: a run of items whose bytes form one dense span of the host buffer.
+struct WorkItem {
+    size_t user_index;     // digest slot / pair index in the caller's arrays
+    uint64_t off, len;     // host offsets
+    uint64_t prefix;
+    uint32_t flags;
+};
+struct Chunk {
+    size_t first, count;   // range in the item list
+    uint64_t span_begin, span_end;   // host byte range to copy (span_begin is 16-aligned)
+    bool needs_state_in;
+};
+
+// Cut the shard's item list into chunks that fit `cap` bytes of staging.  Items longer than
+// the staging buffer are split into continuation segments (SHA) or sub-ranges (cmp).
+static void build_chunks(const std::vector<WorkItem> &in, size_t cap, bool is_sha, std::vector<WorkItem> &items,
+                         std::vector<Chunk> &chunks) {
+    const uint64_t usable = (cap - 64) & ~(uint64_t)127;
+    items.clear();
+    chunks.clear();
+    Chunk cur{0, 0, 0, 0, false};
+    auto close = [&]() {
+        if (cur.count) chunks.push_back(cur);
+        cur = Chunk{items.size(), 0, 0, 0, false};
+    };
+    for (const WorkItem &w : in) {
+        if (w.len + 16 > usable) {
+            close();
+            uint64_t done = 0;
+            while (done < w.len || (w.len == 0 && done == 0)) {
+                uint64_t piece = std::min<uint64_t>(w.len - done, usable - 128);
+                piece = (done + piece < w.len) ? (piece & ~(uint64_t)127) : piece;
+                WorkItem s = w;
+                s.off = w.off + done;
+                s.len = piece;
+                s.prefix = w.prefix + done;
+                if (is_sha) {
+                    s.flags = w.flags;
+                    if (done > 0) s.flags |= kSegContinue;
+                    if (done + piece < w.len) s.flags |= kSegNoFinal;
+                }
+                items.push_back(s);
+                const uint64_t begin = s.off & ~(uint64_t)15;
+                chunks.push_back(Chunk{items.size() - 1, 1, begin, s.off + s.len, (s.flags & kSegContinue) != 0});
+                done += piece;
+                if (w.len == 0) break;
+            }
+            cur = Chunk{items.size(), 0, 0, 0, false};
+            continue;
+        }
+        const uint64_t begin = w.off & ~(uint64_t)15;
+        const uint64_t end = w.off + w.len;
+        bool fits = cur.count > 0 && cur.count < kMaxChunkItems && begin >= cur.span_begin &&
+                    end - cur.span_begin <= usable && (w.off <= cur.span_end + (1u << 20));
+        if (!fits) {
+            close();
+            cur.span_begin = begin;
+            cur.span_end = end;
+        }
+        cur.span_end = std::max(cur.span_end, end);
+        cur.count++;
+        cur.needs_state_in = cur.needs_state_in || (is_sha && (w.flags & kSegContinue));
+        items.push_back(w);
+    }
+    close();
+}
+
+// Runs one device's shard of a host-buffer SHA-512 batch.  digests: caller's n*64 array.
+static int sha512_shard(Device &D, const uint8_t *data, const std::vector<WorkItem> &shard, uint8_t *digests) {
+    if (shard.empty()) return 0;
+    std::lock_guard<std::mutex> lock(D.mu);
+    SG_CUDA(cudaSetDevice(D.ordinal));
+    auto &R = rt();
+    const size_t cap = staging_bytes();
+    std::vector<WorkItem> items;
+    std::vector<Chunk> chunks;
+    build_chunks(shard, cap, true, items, chunks);
+    size_t max_items = 0;
+    for (auto &c : chunks) max_items = std::max(max_items, c.count);
+    int rc = ensure_staging(D, cap, max_items * 64);
+    if (rc) return rc;
+
+    const size_t phase = (uintptr_t)data & 15;   // keep (data + off) mod 16 on the device
+    std::vector<SegDesc> descs;
+    int scatter_pending[2] = {-1, -1};            // chunk index whose digests wait in h_out[b]
+    auto scatter = [&](int b) -> int {
+        if (scatter_pending[b] < 0) return 0;
+        SG_CUDA(cudaEventSynchronize(D.ev_done[b]));
+        const Chunk &c = chunks[(size_t)scatter_pending[b]];
+        for (size_t i = 0; i < c.count; i++)
+            memcpy(digests + 64 * items[c.first + i].user_index, D.h_out[b] + 64 * i, 64);
+        scatter_pending[b] = -1;
+        return 0;
+    };
+
+    for (size_t ci = 0; ci < chunks.size(); ci++) {
+        const Chunk &c = chunks[ci];
+        const int b = (int)(ci & 1);
+        if ((rc = scatter(b))) return rc;        // buffer b (stage, out) is free again
+        const size_t span = (size_t)(c.span_end - c.span_begin);
+        if (span) {
+            SG_CUDA(cudaMemcpyAsync(D.d_stage[b] + phase, data + c.span_begin, span, cudaMemcpyHostToDevice,
+                                    D.copy_stream));
+            R.h2d_bytes += span;
+        }
+        SG_CUDA(cudaEventRecord(D.ev_copied[b], D.copy_stream));
+        if (c.needs_state_in) {
+            // chaining values come from the previous chunk: finish it first
+            if ((rc = scatter(b ^ 1))) return rc;
+            for (size_t i = 0; i < c.count; i++)
+                memcpy(D.h_out[b] + 64 * i, digests + 64 * items[c.first + i].user_index, 64);
+            SG_CUDA(cudaMemcpyAsync(D.d_out[b], D.h_out[b], c.count * 64, cudaMemcpyHostToDevice, D.compute_stream));
+            R.h2d_bytes += c.count * 64;
+        }
+        descs.resize(c.count);
+        for (size_t i = 0; i < c.count; i++) {
+            const WorkItem &w = items[c.first + i];
+            descs[i].off = phase + (w.off - c.span_begin);
+            descs[i].len = w.len;
+            descs[i].prefix = w.prefix;
+            descs[i].out_idx = (u32)i;
+            descs[i].flags = w.flags;
+        }
+        SG_CUDA(cudaStreamWaitEvent(D.compute_stream, D.ev_copied[b], 0));
+        if ((rc = launch_sha512(D, D.compute_stream, D.d_stage[b], descs.data(), c.count, D.d_out[b]))) return rc;
+        SG_CUDA(cudaMemcpyAsync(D.h_out[b], D.d_out[b], c.count * 64, cudaMemcpyDeviceToHost, D.compute_stream));
+        R.d2h_bytes += c.count * 64;
+        SG_CUDA(cudaEventRecord(D.ev_done[b], D.compute_stream));
+        scatter_pending[b] = (int)ci;   // scatter(b) syncs on ev_done[b] before buffer b is reused
+    }
+    if ((rc = scatter(0))) return rc;
+    if ((rc = scatter(1))) return rc;
+    return 0;
+}
+
+static int cmp_shard(Device &D, const uint8_t *a, const uint8_t *b_host, const std::vector<WorkItem> &shard,
+                     uint8_t *equal) {
+    if (shard.empty()) return 0;
+    std::lock_guard<std::mutex> lock(D.mu);
+    SG_CUDA(cudaSetDevice(D.ordinal));
+    auto &R = rt();
+    const size_t cap = staging_bytes();
+    const size_t half = (cap / 2) & ~(size_t)255;
+    std::vector<WorkItem> items;
+    std::vector<Chunk> chunks;
+    build_chunks(shard, half, false, items, chunks);
+    size_t max_items = 0;
+    for (auto &c : chunks) max_items = std::max(max_items, c.count);
+    int rc = ensure_staging(D, cap, max_items);
+    if (rc) return rc;
+    // the two streams may sit at different phases mod 16; the kernel then takes the byte path
+    const size_t pa = (uintptr_t)a & 15, pb = (uintptr_t)b_host & 15;
+    std::vector<CmpItem> ci_items;
+    int pending[2] = {-1, -1};
+    auto gather = [&](int b) -> int {
+        if (pending[b] < 0) return 0;
+        SG_CUDA(cudaEventSynchronize(D.ev_done[b]));
+        const Chunk &c = chunks[(size_t)pending[b]];
+        for (size_t i = 0; i < c.count; i++)
+            if (D.h_out[b][i] == 0) equal[items[c.first + i].user_index] = 0;
+        pending[b] = -1;
+        return 0;
+    };
+    for (size_t ci = 0; ci < chunks.size(); ci++) {
+        const Chunk &c = chunks[ci];
+        const int b = (int)(ci & 1);
+        if ((rc = gather(b))) return rc;
+        // host-side early-out: a pair already known to differ is not copied again
+        if (c.count == 1 && equal[items[c.first].user_index] == 0) continue;
+        const size_t span = (size_t)(c.span_end - c.span_begin);
+        uint8_t *da = D.d_stage[b] + pa, *db = D.d_stage[b] + half + 128 + pb;
+        if (span) {
+            SG_CUDA(cudaMemcpyAsync(da, a + c.span_begin, span, cudaMemcpyHostToDevice, D.copy_stream));
+            SG_CUDA(cudaMemcpyAsync(db, b_host + c.span_begin, span, cudaMemcpyHostToDevice, D.copy_stream));
+            R.h2d_bytes += 2 * span;
+        }
+        SG_CUDA(cudaEventRecord(D.ev_copied[b], D.copy_stream));
+        ci_items.resize(c.count);
+        for (size_t i = 0; i < c.count; i++) {
+            ci_items[i].off = items[c.first + i].off - c.span_begin;
+            ci_items[i].len = items[c.first + i].len;
+        }
+        SG_CUDA(cudaStreamWaitEvent(D.compute_stream, D.ev_copied[b], 0));
+        // offsets are relative to da/db, whose phases differ only if the host pointers' do
+        if ((rc = launch_cmp(D, D.compute_stream, da, db, ci_items.data(), c.count, D.d_out[b]))) return rc;
+        SG_CUDA(cudaMemcpyAsync(D.h_out[b], D.d_out[b], c.count, cudaMemcpyDeviceToHost, D.compute_stream));
+        R.d2h_bytes += c.count;
+        SG_CUDA(cudaEventRecord(D.ev_done[b], D.compute_stream));
+        pending[b] = (int)ci;
+    }
+    if ((rc = gather(0))) return rc;
+    if ((rc = gather(1))) return rc;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// sharding across devices: no collective, results gathered by index on the host
+// ------------------------------------------------------------------------------------------
+
+// Items heavier than 1/(4*ndev) of the job are placed longest-first on the least loaded
+// device; the rest are dealt out as contiguous runs (keeps each device's H2D spans dense).
+static void shard_items(const std::vector<WorkItem> &all, const std::vector<uint64_t> &weight, int ndev,
+                        std::vector<std::vector<WorkItem>> &out) {
+    out.assign((size_t)ndev, {});
+    if (ndev == 1) {
+        out[0] = all;
+        return;
+    }
+    uint64_t total = 0;
+    for (uint64_t w : weight) total += w;
+    const uint64_t big = std::max<uint64_t>(total / (4 * (uint64_t)ndev), 1);
+    std::vector<uint64_t> load((size_t)ndev, 0);
+    std::vector<size_t> bigs;
+    for (size_t i = 0; i < all.size(); i++)
+        if (weight[i] > big) bigs.push_back(i);
+    std::sort(bigs.begin(), bigs.end(), [&](size_t x, size_t y) { return weight[x] > weight[y]; });
+    std::vector<char> placed(all.size(), 0);
+    for (size_t i : bigs) {
+        size_t d = (size_t)(std::min_element(load.begin(), load.end()) - load.begin());
+        out[d].push_back(all[i]);
+        load[d] += weight[i];
+        placed[i] = 1;
+    }
+    const uint64_t target = (total + ndev - 1) / ndev;
+    size_t d = 0;
+    for (size_t i = 0; i < all.size(); i++) {
+        if (placed[i]) continue;
+        while (d + 1 < (size_t)ndev && load[d] >= target) d++;
+        out[d].push_back(all[i]);
+        load[d] += weight[i];
+    }
+}
+
+static int run_on_devices(const std::vector<std::vector<WorkItem>> &shards,
+                          const std::function<int(Device &, const std::vector<WorkItem> &)> &fn) {
+    auto &R = rt();
+    const size_t ndev = R.devs.size();
+    if (ndev == 1) return fn(*R.devs[0], shards[0]);
+    std::vector<int> rcs(ndev, 0);
+    std::vector<std::string> errs(ndev);
+    std::vector<std::thread> threads;
+    for (size_t d = 0; d < ndev; d++)
+        threads.emplace_back([&, d]() {
+            rcs[d] = fn(*R.devs[d], shards[d]);
+            if (rcs[d]) errs[d] = g_last_error;
+        });
+    for (auto &t : threads) t.join();
+    for (size_t d = 0; d < ndev; d++)
+        if (rcs[d]) return fail(rcs[d], "device %zu: %s", d, errs[d].c_str());
+    return 0;
+}
+
+int sha512_host_segments(const uint8_t *data, const HostSeg *segs, size_t n, uint8_t *digests) {
+    if (!runtime_ready()) return fail(SNAPGPU_ENOINIT, "snapgpu_init has not been called (or failed)");
+    if (n == 0) return 0;
+    if (!segs || !digests || (!data && n)) return fail(SNAPGPU_EINVAL, "null argument");
+    std::vector<WorkItem> all(n);
+    std::vector<uint64_t> weight(n);
+    for (size_t i = 0; i < n; i++) {
+        if (segs[i].len >= kMaxSegBytes) return fail(SNAPGPU_EINVAL, "file %zu too large", i);
+        u32 f = 0;
+        if (segs[i].flags & kHostSegContinue) f |= kSegContinue;
+        if (segs[i].flags & kHostSegNoFinal) f |= kSegNoFinal;
+        if ((f & kSegNoFinal) && (segs[i].len & 127))
+            return fail(SNAPGPU_EINVAL, "non-final segment %zu is not a multiple of 128 bytes", i);
+        all[i] = WorkItem{i, segs[i].off, segs[i].len, segs[i].prefix, f};
+        weight[i] = seg_blocks(segs[i].len, f) + 1;
+    }
+    std::vector<std::vector<WorkItem>> shards;
+    shard_items(all, weight, (int)rt().devs.size(), shards);
+    return run_on_devices(shards, [&](Device &D, const std::vector<WorkItem> &s) {
+        return sha512_shard(D, data, s, digests);
+    });
+}
+
+}  // namespace snapgpu
+
+// ==========================================================================================
+// extern "C"
+// ==========================================================================================
+
+using namespace snapgpu;
+
+extern "C" {
+
+const char *snapgpu_last_error(void) { return g_last_error.c_str(); }
+const char *snapgpu_version(void) { return "snapgpu 0.1 (sm_100a)"; }
+
+int snapgpu_init(const int *devices, int ndev) {
+    auto &R = rt();
+    std::lock_guard<std::mutex> lock(R.mu);
+    int visible = 0;
+    cudaError_t e = cudaGetDeviceCount(&visible);
+    if (e != cudaSuccess || visible == 0)
+        return fail(SNAPGPU_ECUDA, "no CUDA device: %s (libsnapgpu has no CPU fallback)",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    std::vector<int> want;
+    if (ndev <= 0) {
+        for (int i = 0; i < visible; i++) want.push_back(i);
+    } else {
+        for (int i = 0; i < ndev; i++) want.push_back(devices ? devices[i] : i);
+    }
+    for (int o : want)
+        if (o < 0 || o >= visible) return fail(SNAPGPU_EINVAL, "device ordinal %d not visible (%d devices)", o, visible);
+    bool same = R.devs.size() == want.size();
+    for (size_t i = 0; same && i < want.size(); i++) same = R.devs[i]->ordinal == want[i];
+    if (same) return 0;
+    for (auto &d : R.devs) destroy_device(*d);
+    R.devs.clear();
+    for (int o : want) {
+        std::unique_ptr<Device> d(new Device());
+        int rc = init_device(*d, o);
+        if (rc) {
+            destroy_device(*d);
+            for (auto &x : R.devs) destroy_device(*x);
+            R.devs.clear();
+            return rc;
+        }
+        R.devs.push_back(std::move(d));
+    }
+    return 0;
+}
+
+void snapgpu_shutdown(void) {
+    auto &R = rt();
+    std::lock_guard<std::mutex> lock(R.mu);
+    for (auto &d : R.devs) destroy_device(*d);
+    R.devs.clear();
+}
+
+int snapgpu_num_devices(void) { return (int)rt().devs.size(); }
+
+int snapgpu_set_option(const char *key, long long value) {
+    if (!key) return fail(SNAPGPU_EINVAL, "null key");
+    auto &o = rt().opt;
+    std::string k(key);
+    if (k == "staging_bytes") {
+        if (value < (1ll << 20)) return fail(SNAPGPU_EINVAL, "staging_bytes must be >= 1 MiB");
+        o.staging_bytes = value & ~255ll;
+    } else if (k == "sha_warps_per_sm") {
+        if (value < 0 || value > kShaCtasPerSmMax) return fail(SNAPGPU_EINVAL, "sha_warps_per_sm out of range");
+        o.sha_warps_per_sm = value;
+    } else if (k == "sha_variant") {
+        if (value < 0 || value >= kShaVariants) return fail(SNAPGPU_EINVAL, "sha_variant out of range");
+        o.sha_variant = value;
+    } else if (k == "cmp_ctas_per_sm") {
+        if (value < 0 || value > 32) return fail(SNAPGPU_EINVAL, "cmp_ctas_per_sm out of range");
+        o.cmp_ctas_per_sm = value;
+    } else if (k == "time_kernels") {
+        o.time_kernels = value ? 1 : 0;
+    } else {
+        return fail(SNAPGPU_EINVAL, "unknown option %s", key);
+    }
+    return 0;
+}
+
+void *snapgpu_alloc_pinned(size_t bytes) {
+    void *p = nullptr;
+    if (!runtime_ready()) {
+        set_error("snapgpu_init has not been called (or failed)");
+        return nullptr;
+    }
+    cudaSetDevice(rt().devs[0]->ordinal);
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        set_error("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        return nullptr;
+    }
+    return p;
+}
+
+void snapgpu_free_pinned(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+void snapgpu_free(void *p) { free(p); }
+
+int snapgpu_sha512_batch(const uint8_t *data, const uint64_t *offsets, const uint64_t *lengths, size_t nfiles,
+                         uint8_t *digests) {
+    if (nfiles == 0) return runtime_ready() ? 0 : fail(SNAPGPU_ENOINIT, "snapgpu_init has not been called (or failed)");
+    if (!offsets || !lengths || !digests) return fail(SNAPGPU_EINVAL, "null argument");
+    std::vector<HostSeg> segs(nfiles);
+    for (size_t i = 0; i < nfiles; i++) segs[i] = HostSeg{offsets[i], lengths[i], 0, 0};
+    return sha512_host_segments(data, segs.data(), nfiles, digests);
+}
+
+int snapgpu_sha512_stream(uint8_t state[64], int first, const uint8_t *data, uint64_t len, uint64_t prefix_bytes,
+                          int final) {
+    if (!state) return fail(SNAPGPU_EINVAL, "null state");
+    HostSeg s{0, len, prefix_bytes, 0};
+    if (!first) s.flags |= kHostSegContinue;
+    if (!final) s.flags |= kHostSegNoFinal;
+    static const uint8_t dummy[16] = {0};
+    return sha512_host_segments(data ? data : dummy, &s, 1, state);
+}
+
+int snapgpu_cmp_batch(const uint8_t *a, const uint8_t *b, const uint64_t *offsets, const uint64_t *lengths,
+                      size_t npairs, uint8_t *equal) {
+    if (!runtime_ready()) return fail(SNAPGPU_ENOINIT, "snapgpu_init has not been called (or failed)");
+    if (npairs == 0) return 0;
+    if (!a || !b || !offsets || !lengths || !equal) return fail(SNAPGPU_EINVAL, "null argument");
+    std::vector<WorkItem> all(npairs);
+    std::vector<uint64_t> weight(npairs);
+    for (size_t i = 0; i < npairs; i++) {
+        all[i] = WorkItem{i, offsets[i], lengths[i], 0, 0};
+        weight[i] = lengths[i] + 64;
+        equal[i] = 1;
+    }
+    std::vector<std::vector<WorkItem>> shards;
+    shard_items(all, weight, (int)rt().devs.size(), shards);
+    return run_on_devices(shards, [&](Device &D, const std::vector<WorkItem> &s) { return cmp_shard(D, a, b, s, equal); });
+}
+
+int snapgpu_sha512_batch_device(int dev, const void *d_data, const uint64_t *offsets, const uint64_t *lengths,
+                                size_t nfiles, void *d_digests, void *stream) {
+    Device *D;
+    int rc = get_device(dev, &D);
+    if (rc) return rc;
+    if (nfiles == 0) return 0;
+    if (!d_data || !offsets || !lengths || !d_digests) return fail(SNAPGPU_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lock(D->mu);
+    SG_CUDA(cudaSetDevice(D->ordinal));
+    std::vector<SegDesc> segs(nfiles);
+    for (size_t i = 0; i < nfiles; i++) {
+        segs[i].off = offsets[i];
+        segs[i].len = lengths[i];
+        segs[i].prefix = 0;
+        segs[i].out_idx = (u32)i;
+        segs[i].flags = 0;
+    }
+    return launch_sha512(*D, (cudaStream_t)stream, static_cast<const uint8_t *>(d_data), segs.data(), nfiles,
+                         static_cast<uint8_t *>(d_digests));
+}
+
+int snapgpu_cmp_batch_device(int dev, const void *d_a, const void *d_b, const uint64_t *offsets,
+                             const uint64_t *lengths, size_t npairs, void *d_equal, void *stream) {
+    Device *D;
+    int rc = get_device(dev, &D);
+    if (rc) return rc;
+    if (npairs == 0) return 0;
+    if (!d_a || !d_b || !offsets || !lengths || !d_equal) return fail(SNAPGPU_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lock(D->mu);
+    SG_CUDA(cudaSetDevice(D->ordinal));
+    std::vector<CmpItem> items(npairs);
+    for (size_t i = 0; i < npairs; i++) items[i] = CmpItem{offsets[i], lengths[i]};
+    return launch_cmp(*D, (cudaStream_t)stream, static_cast<const uint8_t *>(d_a), static_cast<const uint8_t *>(d_b),
+                      items.data(), npairs, static_cast<uint8_t *>(d_equal));
+}
+
+int snapgpu_synth_fill_device(int dev, void *d_data, const uint64_t *offsets, const uint64_t *lengths, size_t nfiles,
+                              uint64_t first_index, uint64_t seed, void *stream) {
+    Device *D;
+    int rc = get_device(dev, &D);
+    if (rc) return rc;
+    if (nfiles == 0) return 0;
+    if (!d_data || !offsets || !lengths) return fail(SNAPGPU_EINVAL, "null argument");
+    if (nfiles > 0xfffffff0ull) return fail(SNAPGPU_EINVAL, "too many files");
+    std::lock_guard<std::mutex> lock(D->mu);
+    SG_CUDA(cudaSetDevice(D->ordinal));
+    PlanSlot *slot;
+    if ((rc = acquire_slot(*D, nfiles * sizeof(SynthFile), &slot))) return rc;
+    SynthFile *h = static_cast<SynthFile *>(slot->h_buf);
+    for (size_t i = 0; i < nfiles; i++) h[i] = SynthFile{offsets[i], lengths[i]};
+    cudaStream_t s = (cudaStream_t)stream;
+    SG_CUDA(cudaMemcpyAsync(slot->d_buf, h, nfiles * sizeof(SynthFile), cudaMemcpyHostToDevice, s));
+    const u32 grid = (u32)std::min<size_t>(nfiles, (size_t)D->sm_count * 16);
+    synth_fill_kernel<<<grid, 256, 0, s>>>(static_cast<uint8_t *>(d_data), static_cast<const SynthFile *>(slot->d_buf),
+                                           (u32)nfiles, first_index, seed);
+    SG_CUDA(cudaGetLastError());
+    SG_CUDA(cudaEventRecord(slot->done, s));
+    slot->in_flight = true;
+    rt().kernel_launches++;
+    return 0;
+}
+
+int snapgpu_get_stats(snapgpu_stats *out) {
+    if (!out) return fail(SNAPGPU_EINVAL, "null argument");
+    auto &R = rt();
+    memset(out, 0, sizeof *out);
+    out->kernel_launches = R.kernel_launches;
+    out->sha512_launches = R.sha_launches;
+    out->cmp_launches = R.cmp_launches;
+    out->h2d_bytes = R.h2d_bytes;
+    out->d2h_bytes = R.d2h_bytes;
+    double sha_sum = 0, cmp_sum = 0;
+    uint64_t sha_n = 0, cmp_n = 0;
+    for (auto &dp : R.devs) {
+        Device &D = *dp;
+        std::lock_guard<std::mutex> lock(D.mu);
+        cudaSetDevice(D.ordinal);
+        harvest_timings(D.sha_t, 8, D.sha_ms_sum, D.sha_ms_n, D.sha_ms_last, true);
+        harvest_timings(D.cmp_t, 8, D.cmp_ms_sum, D.cmp_ms_n, D.cmp_ms_last, true);
+        sha_sum += D.sha_ms_sum;
+        sha_n += D.sha_ms_n;
+        cmp_sum += D.cmp_ms_sum;
+        cmp_n += D.cmp_ms_n;
+        out->last_sha512_kernel_ms = D.sha_ms_last;
+        out->last_cmp_kernel_ms = D.cmp_ms_last;
+    }
+    out->sha512_kernel_ms_sum = sha_sum;
+    out->sha512_kernel_timed = sha_n;
+    out->cmp_kernel_ms_sum = cmp_sum;
+    out->cmp_kernel_timed = cmp_n;
+    return 0;
+}
+
+void snapgpu_reset_stats(void) {
+    auto &R = rt();
+    R.kernel_launches = 0;
+    R.sha_launches = 0;
+    R.cmp_launches = 0;
+    R.h2d_bytes = 0;
+    R.d2h_bytes = 0;
+    for (auto &dp : R.devs) {
+        Device &D = *dp;
+        std::lock_guard<std::mutex> lock(D.mu);
+        cudaSetDevice(D.ordinal);
+        harvest_timings(D.sha_t, 8, D.sha_ms_sum, D.sha_ms_n, D.sha_ms_last, true);
+        harvest_timings(D.cmp_t, 8, D.cmp_ms_sum, D.cmp_ms_n, D.cmp_ms_last, true);
+        D.sha_ms_sum = D.cmp_ms_sum = 0;
+        D.sha_ms_n = D.cmp_ms_n = 0;
+    }
+}
+
+// ---- test hooks: host logic only, callable without a GPU ---------------------------------
+
+// Launch order the length binning produces: order[k] = index of the k-th file of the plan.
+int snapgpu_test_plan_order(const uint64_t *lengths, size_t n, uint32_t *order) {
+    if (!lengths || !order) return fail(SNAPGPU_EINVAL, "null argument");
+    std::vector<SegDesc> src(n), dst(n);
+    for (size_t i = 0; i < n; i++) src[i] = SegDesc{0, lengths[i], 0, (u32)i, 0};
+    uint64_t total = 0, mx = 0;
+    bin_by_length(src.data(), n, dst.data(), &total, &mx);
+    for (size_t i = 0; i < n; i++) order[i] = dst[i].out_idx;
+    return 0;
+}
+
+// Device each item of a batch is sharded to (weights as used by the sharder).
+int snapgpu_test_shard(const uint64_t *weights, size_t n, int ndev, int *device_of) {
+    if (!weights || !device_of || ndev < 1) return fail(SNAPGPU_EINVAL, "bad argument");
+    std::vector<WorkItem> all(n);
+    std::vector<uint64_t> w(weights, weights + n);
+    for (size_t i = 0; i < n; i++) all[i] = WorkItem{i, 0, 0, 0, 0};
+    std::vector<std::vector<WorkItem>> shards;
+    shard_items(all, w, ndev, shards);
+    for (int d = 0; d < ndev; d++)
+        for (const WorkItem &it : shards[(size_t)d]) device_of[it.user_index] = d;
+    return 0;
+}
+
+// Chunking of a host batch for a staging buffer of `cap` bytes.  Writes one row of six u64
+// per produced item: user index, off, len, prefix, flags, chunk number.  Returns the number
+// of rows (or a negative error); rows beyond max_rows are counted but not written.
+long long snapgpu_test_chunks(const uint64_t *offsets, const uint64_t *lengths, size_t n, uint64_t cap, int is_sha,
+                              uint64_t *rows, size_t max_rows) {
+    if (!offsets || !lengths || cap < 4096) return fail(SNAPGPU_EINVAL, "bad argument");
+    std::vector<WorkItem> in(n), items;
+    std::vector<Chunk> chunks;
+    for (size_t i = 0; i < n; i++) in[i] = WorkItem{i, offsets[i], lengths[i], 0, 0};
+    build_chunks(in, (size_t)cap, is_sha != 0, items, chunks);
+    size_t row = 0;
+    for (size_t c = 0; c < chunks.size(); c++)
+        for (size_t i = 0; i < chunks[c].count; i++, row++) {
+            if (!rows || row >= max_rows) continue;
+            const WorkItem &w = items[chunks[c].first + i];
+            uint64_t *r = rows + 6 * row;
+            r[0] = w.user_index; r[1] = w.off; r[2] = w.len; r[3] = w.prefix; r[4] = w.flags; r[5] = c;
+        }
+    return (long long)row;
+}
+
+typedef void (*ProbeKernel)(uint32_t *, int, uint32_t, uint32_t, unsigned long long *);
+
+int snapgpu_pipe_microbench(int dev, int kind, int warps_per_sm, double *inst_per_clk_per_sm, double *elapsed_ms,
+                            double *sm_clock_mhz) {
+    Device *D;
+    int rc = get_device(dev, &D);
+    if (rc) return rc;
+    static const ProbeKernel table[kProbeCount] = {
+        pipe_probe_kernel<0>, pipe_probe_kernel<1>, pipe_probe_kernel<2>, pipe_probe_kernel<3>,
+        pipe_probe_kernel<4>, pipe_probe_kernel<5>, pipe_probe_kernel<6>, pipe_probe_kernel<7>,
+    };
+    if (kind < 0 || kind >= kProbeCount) return fail(SNAPGPU_EINVAL, "unknown probe kind %d", kind);
+    if (warps_per_sm < 4 || warps_per_sm > 64 || warps_per_sm % 4) return fail(SNAPGPU_EINVAL, "warps_per_sm must be 4..64, multiple of 4");
+    std::lock_guard<std::mutex> lock(D->mu);
+    SG_CUDA(cudaSetDevice(D->ordinal));
+    const int ctas_per_sm = warps_per_sm / (kProbeThreads / 32);
+    const int grid = D->sm_count * ctas_per_sm;
+    const int iters = 4096;
+    uint32_t *d_out = nullptr;
+    unsigned long long *d_clk = nullptr;
+    SG_CUDA(cudaMalloc(&d_out, (size_t)grid * kProbeThreads * sizeof(uint32_t)));
+    SG_CUDA(cudaMalloc(&d_clk, 2 * sizeof(unsigned long long)));
+    cudaEvent_t e0, e1;
+    SG_CUDA(cudaEventCreate(&e0));
+    SG_CUDA(cudaEventCreate(&e1));
+    cudaStream_t s = D->compute_stream;
+    float best = 1e30f;
+    unsigned long long clk[2] = {0, 0};
+    for (int rep = 0; rep < 4; rep++) {   // first repetition is the warm-up
+        SG_CUDA(cudaEventRecord(e0, s));
+        table[kind]<<<grid, kProbeThreads, 0, s>>>(d_out, iters, 1u, 0x9e3779b9u, d_clk);
+        SG_CUDA(cudaGetLastError());
+        SG_CUDA(cudaEventRecord(e1, s));
+        SG_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        SG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) {
+            best = ms;
+            SG_CUDA(cudaMemcpy(clk, d_clk, sizeof clk, cudaMemcpyDeviceToHost));
+        }
+    }
+    rt().kernel_launches += 4;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    cudaFree(d_clk);
+    const double mhz = clk[1] ? (double)clk[0] / (double)clk[1] * 1e3 : 0.0;
+    const double warp_insts = (double)iters * probe_ops_per_iter(kind) * warps_per_sm;   // per SM
+    const double cycles = clk[0] ? (double)clk[0] : best * 1e-3 * mhz * 1e6;
+    if (inst_per_clk_per_sm) *inst_per_clk_per_sm = cycles > 0 ? warp_insts / cycles : 0.0;
+    if (elapsed_ms) *elapsed_ms = best;
+    if (sm_clock_mhz) *sm_clock_mhz = mhz;
+    return 0;
+}
+
+}  // extern "C"

