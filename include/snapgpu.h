@@ -44,7 +44,8 @@ const char *snapgpu_last_error(void);
 const char *snapgpu_version(void);
 
 /* Tunables (all optional).  Known keys: "staging_bytes" (per-device H2D chunk, default
- * 256 MiB), "sha_warps_per_sm" (0 = auto), "sha_variant" (0 = auto). */
+ * 1 GiB, two buffers), "sha_warps_per_sm" (0 = auto), "sha_variant" (0 = default kernel),
+ * "cmp_ctas_per_sm", "time_kernels". */
 int snapgpu_set_option(const char *key, long long value);
 
 /* C-owned pinned host memory for the Go side to pack file contents into

@@ -22,7 +22,11 @@ enum ProbeKind : int {
     kProbeAluImad = 5,   // IADD3 / IMAD alternating, 1:1
     kProbeAluWide = 6,   // LOP3 / IMAD.WIDE alternating, 1:1
     kProbeShaMix = 7,    // 10 ALU : 3 IMAD : 3 IMAD.WIDE, the mix of the FMA-add SHA-512 kernel
-    kProbeCount = 8
+    kProbeImadHi = 8,    // IMAD.HI.U32 (FMA pipe; the ">> n" half of a multiply-based rotate)
+    kProbeAluImadHi = 9, // LOP3 / IMAD.HI alternating, 1:1
+    kProbeRotMix = 10,   // SHF : IMAD : IMAD.HI = 2 : 1 : 1 (half of the rotates done by multiplies)
+    kProbeAddX = 11,     // 64-bit add as IADD3 (carry out) + IMAD.X (carry in)
+    kProbeCount = 12
 };
 
 // warp instructions of the probed classes issued per thread and outer iteration
@@ -36,6 +40,7 @@ pipe_probe_kernel(uint32_t *out, int iters, uint32_t m_in, uint32_t y_in, unsign
     // per-thread copies, so that the operands are plain registers (not constant-bank reads)
     const uint32_t m = m_in + (threadIdx.x >> 10);
     const uint32_t y = y_in ^ threadIdx.x;
+    const uint32_t m2 = (m_in << 19) | (threadIdx.x >> 10);   // 2^19: a rotate-by-13 multiplier
     uint32_t x[kProbeChains];
     uint64_t acc[kProbeChains];
 #pragma unroll
@@ -80,6 +85,19 @@ pipe_probe_kernel(uint32_t *out, int iters, uint32_t m_in, uint32_t y_in, unsign
                         x[c] = __funnelshift_r(x[c], y, 13);
                     } else if (kKind == kProbeImad || (kKind == kProbeAluImad && alt)) {
                         asm("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[c]) : "r"(m), "r"(y));
+                    } else if (kKind == kProbeImadHi || (kKind == kProbeAluImadHi && alt)) {
+                        asm("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[c]) : "r"(m2), "r"(y));
+                    } else if (kKind == kProbeAluImadHi) {
+                        asm("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(y), "r"(m));
+                    } else if (kKind == kProbeRotMix) {
+                        if ((c & 3) < 2) x[c] = __funnelshift_r(x[c], y, 13);
+                        else if ((c & 3) == 2) asm("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[c]) : "r"(m), "r"(y));
+                        else asm("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[c]) : "r"(m2), "r"(y));
+                    } else if (kKind == kProbeAddX) {
+                        // (x[c], x[c^1]) as a 64-bit accumulator for even c; odd c is its high half
+                        if (!alt)
+                            asm("{add.cc.u32 %0, %0, %2;\n\tmadc.lo.u32 %1, %1, %3, %4;}"
+                                : "+r"(x[c]), "+r"(x[c + 1]) : "r"(y), "r"(m), "r"(m2));
                     } else {   // IMAD.WIDE.U32 with a register-pair addend
                         uint64_t p;
                         asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"((uint32_t)acc[c]), "r"(m));

@@ -185,6 +185,101 @@ __device__ __forceinline__ void sha512_compress(u64 (&st)[8], u64 (&w)[16], bool
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Compact form: 4 x (16 rounds + 16 schedule words) in a loop, then 16 rounds.  ~20 KB of code
+// instead of ~65 KB, so the loop stays in the SM's instruction cache (ncu: "no instruction"
+// was the top stall reason of the fully unrolled form).  Round constants come from constant
+// memory through the uniform datapath.
+// ------------------------------------------------------------------------------------------
+
+__constant__ u64 c_K512[80] = {
+    0x428a2f98d728ae22ULL, 0x7137449123ef65cdULL, 0xb5c0fbcfec4d3b2fULL, 0xe9b5dba58189dbbcULL,
+    0x3956c25bf348b538ULL, 0x59f111f1b605d019ULL, 0x923f82a4af194f9bULL, 0xab1c5ed5da6d8118ULL,
+    0xd807aa98a3030242ULL, 0x12835b0145706fbeULL, 0x243185be4ee4b28cULL, 0x550c7dc3d5ffb4e2ULL,
+    0x72be5d74f27b896fULL, 0x80deb1fe3b1696b1ULL, 0x9bdc06a725c71235ULL, 0xc19bf174cf692694ULL,
+    0xe49b69c19ef14ad2ULL, 0xefbe4786384f25e3ULL, 0x0fc19dc68b8cd5b5ULL, 0x240ca1cc77ac9c65ULL,
+    0x2de92c6f592b0275ULL, 0x4a7484aa6ea6e483ULL, 0x5cb0a9dcbd41fbd4ULL, 0x76f988da831153b5ULL,
+    0x983e5152ee66dfabULL, 0xa831c66d2db43210ULL, 0xb00327c898fb213fULL, 0xbf597fc7beef0ee4ULL,
+    0xc6e00bf33da88fc2ULL, 0xd5a79147930aa725ULL, 0x06ca6351e003826fULL, 0x142929670a0e6e70ULL,
+    0x27b70a8546d22ffcULL, 0x2e1b21385c26c926ULL, 0x4d2c6dfc5ac42aedULL, 0x53380d139d95b3dfULL,
+    0x650a73548baf63deULL, 0x766a0abb3c77b2a8ULL, 0x81c2c92e47edaee6ULL, 0x92722c851482353bULL,
+    0xa2bfe8a14cf10364ULL, 0xa81a664bbc423001ULL, 0xc24b8b70d0f89791ULL, 0xc76c51a30654be30ULL,
+    0xd192e819d6ef5218ULL, 0xd69906245565a910ULL, 0xf40e35855771202aULL, 0x106aa07032bbd1b8ULL,
+    0x19a4c116b8d2d0c8ULL, 0x1e376c085141ab53ULL, 0x2748774cdf8eeb99ULL, 0x34b0bcb5e19b48a8ULL,
+    0x391c0cb3c5c95a63ULL, 0x4ed8aa4ae3418acbULL, 0x5b9cca4f7763e373ULL, 0x682e6ff3d6b2b8a3ULL,
+    0x748f82ee5defb2fcULL, 0x78a5636f43172f60ULL, 0x84c87814a1f0ab72ULL, 0x8cc702081a6439ecULL,
+    0x90befffa23631e28ULL, 0xa4506cebde82bde9ULL, 0xbef9a3f7b2c67915ULL, 0xc67178f2e372532bULL,
+    0xca273eceea26619cULL, 0xd186b8c721c0c207ULL, 0xeada7dd6cde0eb1eULL, 0xf57d4f7fee6ed178ULL,
+    0x06f067aa72176fbaULL, 0x0a637dc5a2c898a6ULL, 0x113f9804bef90daeULL, 0x1b710b35131c471bULL,
+    0x28db77f523047d84ULL, 0x32caab7b40c72493ULL, 0x3c9ebe0a15c9bebcULL, 0x431d67c49c100d4cULL,
+    0x4cc5d4becb3e42b6ULL, 0x597f299cfc657e2aULL, 0x5fcb6fab3ad6faecULL, 0x6c44198c4a475817ULL,
+};
+
+// 64-bit add with the low half on the ALU pipe (IADD3, carry out) and the high half on the
+// FMA pipe (IMAD.X: a.hi * one + b.hi + carry).
+__device__ __forceinline__ u64 add64_split(u64 a, u64 b, u32 one) {
+    u32 al, ah, bl, bh, lo, hi;
+    unpack64(a, al, ah);
+    unpack64(b, bl, bh);
+    asm("{add.cc.u32 %0, %2, %3;\n\tmadc.lo.u32 %1, %4, %6, %5;}"
+        : "=r"(lo), "=r"(hi) : "r"(al), "r"(bl), "r"(ah), "r"(bh), "r"(one));
+    return pack64(lo, hi);
+}
+
+// kAddMode 0: plain 64-bit adds (ptxas pairs them into 3-input IADD3 / IADD3.X)
+// kAddMode 1: every add split ALU(lo) / FMA(hi)
+template <int kAddMode>
+__device__ __forceinline__ u64 addm(u64 a, u64 b, u32 one) {
+    if constexpr (kAddMode == 1) return add64_split(a, b, one);
+    else return a + b;
+}
+
+template <int kAddMode>
+__device__ __forceinline__ void sha512_round(u64 a, u64 b, u64 c, u64 &d, u64 e, u64 f, u64 g, u64 &h, u64 kw, u32 one) {
+    u64 t1 = addm<kAddMode>(addm<kAddMode>(h, kw, one), addm<kAddMode>(big_sigma1(e), ch64(e, f, g), one), one);
+    u64 t2 = addm<kAddMode>(big_sigma0(a), maj64(a, b, c), one);
+    d = addm<kAddMode>(d, t1, one);
+    h = addm<kAddMode>(t1, t2, one);
+}
+
+#define SNAPGPU_R8(W, KB, I)                                                                        \
+    sha512_round<kAddMode>(a, b, c, d, e, f, g, h, addm<kAddMode>(W[I + 0], KB[I + 0], one), one);  \
+    sha512_round<kAddMode>(h, a, b, c, d, e, f, g, addm<kAddMode>(W[I + 1], KB[I + 1], one), one);  \
+    sha512_round<kAddMode>(g, h, a, b, c, d, e, f, addm<kAddMode>(W[I + 2], KB[I + 2], one), one);  \
+    sha512_round<kAddMode>(f, g, h, a, b, c, d, e, addm<kAddMode>(W[I + 3], KB[I + 3], one), one);  \
+    sha512_round<kAddMode>(e, f, g, h, a, b, c, d, addm<kAddMode>(W[I + 4], KB[I + 4], one), one);  \
+    sha512_round<kAddMode>(d, e, f, g, h, a, b, c, addm<kAddMode>(W[I + 5], KB[I + 5], one), one);  \
+    sha512_round<kAddMode>(c, d, e, f, g, h, a, b, addm<kAddMode>(W[I + 6], KB[I + 6], one), one);  \
+    sha512_round<kAddMode>(b, c, d, e, f, g, h, a, addm<kAddMode>(W[I + 7], KB[I + 7], one), one);
+
+template <int kAddMode>
+__device__ __forceinline__ void sha512_compress_compact(u64 (&st)[8], u64 (&w)[16], bool commit, u32 one) {
+    u64 a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll 1
+    for (int grp = 0; grp < 4; grp++) {
+        const u64 *kb = c_K512 + 16 * grp;
+        SNAPGPU_R8(w, kb, 0)
+        SNAPGPU_R8(w, kb, 8)
+        // schedule for the next 16 rounds, in place: W[t+16] = s1(W[t+14]) + W[t+9] + s0(W[t+1]) + W[t]
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            u64 x = addm<kAddMode>(small_sigma0(w[(i + 1) & 15]), w[i], one);
+            u64 y = addm<kAddMode>(small_sigma1(w[(i + 14) & 15]), w[(i + 9) & 15], one);
+            w[i] = addm<kAddMode>(x, y, one);
+        }
+    }
+    {
+        const u64 *kb = c_K512 + 64;
+        SNAPGPU_R8(w, kb, 0)
+        SNAPGPU_R8(w, kb, 8)
+    }
+    if (commit) {
+        st[0] += a; st[1] += b; st[2] += c; st[3] += d;
+        st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+    }
+}
+
 __device__ __forceinline__ u32 bswap32(u32 x) { return __byte_perm(x, 0, 0x0123); }
 
 // Two little-endian 32-bit loads (memory order lo, hi) -> the big-endian 64-bit word.

@@ -177,4 +177,139 @@ sha512_segments_kernel(const uint8_t *__restrict__ data, const SegDesc *__restri
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// v2: message bytes staged through shared memory with cp.async (LDGSTS), two stages per warp.
+//
+// Each lane copies the 128 bytes of its own next block as 8 x 16 B asynchronous copies, one
+// block ahead of the compression that consumes them; the copies of a tail block carry a
+// src-size so that bytes past the end of the file are zero-filled, never read.  The stage is
+// laid out [chunk][lane] (16 B units), so both the LDGSTS writes and the LDS.128 reads of a
+// warp touch 32 consecutive 16-byte words: no bank conflicts.  A lane only ever reads what it
+// copied itself, so cp.async.wait_group is all the synchronisation there is.
+// Compared with loading into registers this keeps 32 registers free and leaves ptxas no way
+// to pull a load's first use forward (ncu showed exactly that: a 16 % long-scoreboard stall).
+// ------------------------------------------------------------------------------------------
+
+constexpr int kStageBytesPerWarp = 8 * 32 * 16;   // 4 KiB: one 128-byte block per lane
+
+__device__ __forceinline__ void cp_async_16(u32 smem_addr, const void *gptr, u32 src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gptr), "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void cp_async_16_full(u32 smem_addr, const void *gptr) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+
+// queue the copies of the block at p (rem = bytes of the segment left there)
+__device__ __forceinline__ void stage_block(u32 stage_addr, u32 lane, const uint8_t *p, long long rem,
+                                            const uint8_t *safe) {
+    const u32 dst = stage_addr + lane * 16u;
+    if (rem >= 128) {                       // whole block: no per-chunk arithmetic
+#pragma unroll
+        for (int j = 0; j < 8; j++) cp_async_16_full(dst + (u32)j * 512u, p + 16 * j);
+    } else {                                // tail (or nothing): zero-fill past the end
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            long long left = rem - 16 * j;
+            u32 nbytes = left <= 0 ? 0u : (left >= 16 ? 16u : (u32)left);
+            const uint8_t *src = nbytes ? p + 16 * j : safe;
+            cp_async_16(dst + (u32)j * 512u, src, nbytes);
+        }
+    }
+    cp_async_commit();
+}
+
+template <int kAddMode, int kCtasPerSm>
+__global__ void __launch_bounds__(kShaThreads, kCtasPerSm)
+sha512_segments_kernel_v2(const uint8_t *__restrict__ data, const SegDesc *__restrict__ descs, u32 nsegs,
+                          uint8_t *__restrict__ digests, u32 *__restrict__ unit_counter, u32 one) {
+    __shared__ __align__(16) uint8_t stages[kShaWarpsPerCta][2][kStageBytesPerWarp];
+    const u32 lane = threadIdx.x & 31;
+    const u32 warp = threadIdx.x >> 5;
+    const u32 nunits = (nsegs + 31) >> 5;
+    const u32 total_warps = gridDim.x * kShaWarpsPerCta;
+    const u32 stage0 = (u32)__cvta_generic_to_shared(&stages[warp][0][0]);
+    u32 unit = warp * gridDim.x + blockIdx.x;
+
+    while (unit < nunits) {
+        const u32 idx = unit * 32 + lane;
+        const bool have = idx < nsegs;
+        SegDesc sd;
+        sd.off = 0; sd.len = 0; sd.prefix = 0; sd.out_idx = 0; sd.flags = kSegNoFinal;
+        if (have) {
+            const uint4 *q = reinterpret_cast<const uint4 *>(descs + idx);
+            uint4 q0 = q[0], q1 = q[1];
+            sd.off = pack64(q0.x, q0.y); sd.len = pack64(q0.z, q0.w);
+            sd.prefix = pack64(q1.x, q1.y); sd.out_idx = q1.z; sd.flags = q1.w;
+        }
+        const u32 nblk = have ? (u32)seg_blocks(sd.len, sd.flags) : 0u;
+        const u32 nblk_max = __reduce_max_sync(0xffffffffu, nblk);
+        const bool final_seg = !(sd.flags & kSegNoFinal);
+        const u64 total_len = sd.prefix + sd.len;
+        uint8_t *out = digests + (size_t)sd.out_idx * 64;
+
+        u64 st[8];
+        if (have && (sd.flags & kSegContinue)) {
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(out);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint4 v = s4[i];
+                st[2 * i] = be64_from_le_words(v.x, v.y);
+                st[2 * i + 1] = be64_from_le_words(v.z, v.w);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) st[i] = kIV512[i];
+        }
+
+        const uint8_t *p = data + sd.off;
+        long long rem = (long long)sd.len;
+        stage_block(stage0, lane, p, rem, data);
+
+        for (u32 blk = 0; blk < nblk_max; blk++) {
+            const u32 cur = stage0 + (blk & 1) * kStageBytesPerWarp;
+            const u32 nxt = stage0 + ((blk + 1) & 1) * kStageBytesPerWarp;
+            const bool active = blk < nblk;
+            const long long rem_now = rem;
+            p += 128;
+            rem -= 128;
+            stage_block(nxt, lane, p, rem, data);        // block blk+1 starts moving ...
+            cp_async_wait<1>();                          // ... block blk has landed
+            u64 w[16];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                uint4 v;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(cur + lane * 16u + (u32)j * 512u));
+                w[2 * j] = be64_from_le_words(v.x, v.y);
+                w[2 * j + 1] = be64_from_le_words(v.z, v.w);
+            }
+            if (__any_sync(0xffffffffu, active && rem_now < 128))
+                pad_block(w, rem_now, final_seg && (blk + 1 == nblk), total_len);
+            sha512_compress_compact<kAddMode>(st, w, active, one);
+        }
+        cp_async_wait<0>();
+
+        if (have) {
+            uint4 *o4 = reinterpret_cast<uint4 *>(out);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                u32 a_lo, a_hi, b_lo, b_hi;
+                unpack64(st[2 * i], a_lo, a_hi);
+                unpack64(st[2 * i + 1], b_lo, b_hi);
+                o4[i] = make_uint4(bswap32(a_hi), bswap32(a_lo), bswap32(b_hi), bswap32(b_lo));
+            }
+        }
+
+        u32 next = 0;
+        if (lane == 0) next = atomicAdd(unit_counter, 1u) + total_warps;
+        unit = __shfl_sync(0xffffffffu, next, 0);
+    }
+}
+
 }  // namespace snapgpu

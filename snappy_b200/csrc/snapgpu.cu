@@ -15,6 +15,7 @@
 #include <memory>
 #include <mutex>
 #include <thread>
+#include <time.h>
 
 #include "cmp_kernels.cuh"
 #include "pipe_microbench.cuh"
@@ -81,6 +82,7 @@ struct PlanSlot {
     size_t cap = 0;           // bytes
     u32 *d_counter = nullptr;
     cudaEvent_t done = nullptr;
+    cudaEvent_t uploaded = nullptr;
     bool in_flight = false;
 };
 
@@ -111,7 +113,7 @@ struct Device {
 };
 
 struct Options {
-    std::atomic<long long> staging_bytes{256ll << 20};
+    std::atomic<long long> staging_bytes{1024ll << 20};   // fewer, larger H2D copies: 55 vs 47 GB/s measured
     std::atomic<long long> sha_warps_per_sm{0};
     std::atomic<long long> sha_variant{0};
     std::atomic<long long> cmp_ctas_per_sm{0};
@@ -142,6 +144,7 @@ static void destroy_device(Device &D) {
         if (s.d_buf) cudaFree(s.d_buf);
         if (s.d_counter) cudaFree(s.d_counter);
         if (s.done) cudaEventDestroy(s.done);
+        if (s.uploaded) cudaEventDestroy(s.uploaded);
     }
     for (int b = 0; b < 2; b++) {
         if (D.d_stage[b]) cudaFree(D.d_stage[b]);
@@ -170,6 +173,7 @@ static int init_device(Device &D, int ordinal) {
     SG_CUDA(cudaStreamCreateWithFlags(&D.compute_stream, cudaStreamNonBlocking));
     for (auto &s : D.slots) {
         SG_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        SG_CUDA(cudaEventCreateWithFlags(&s.uploaded, cudaEventDisableTiming));
         SG_CUDA(cudaMalloc(&s.d_counter, 256));
     }
     for (int b = 0; b < 2; b++) {
@@ -239,78 +243,123 @@ static void harvest_timings(TimedLaunch *ring, int n, double &sum, uint64_t &cnt
 typedef void (*ShaKernel)(const uint8_t *, const SegDesc *, u32, uint8_t *, u32 *, u32);
 
 constexpr int kShaCtasPerSmMax = 3;   // 168 registers per thread: no spills with the one-block-ahead prefetch
-constexpr int kShaVariants = 3;
+constexpr int kShaVariants = 5;
 
-// variant 0: every 64-bit add on the FMA pipe; 1: every add on the ALU pipe (plain IADD3);
-// variant 2: round adds on FMA, schedule adds on ALU.
+// variant 0 (default): compact 16-round loop, cp.async staging through shared memory, plain
+//            64-bit adds (ptxas pairs them into 3-input IADD3 / IADD3.X)
+// variant 1: same, every add split IADD3 (low half, ALU) / IMAD.X (high half, FMA)
+// variant 2: 80 rounds fully unrolled, register prefetch, ALU adds          (round-1 first cut)
+// variant 3: fully unrolled, every add as IMAD.WIDE + IMAD on the FMA pipe  (measured slower)
+// variant 4: fully unrolled, round adds on FMA, schedule adds on ALU
+// Input that is not 16-byte aligned always takes the register-load kernel (any alignment).
 static ShaKernel sha_kernel_for(int variant, bool aligned) {
+    if (!aligned) return sha512_segments_kernel<0x00, 0x0, false, kShaCtasPerSmMax>;
     switch (variant) {
-    case 1:
-        return aligned ? sha512_segments_kernel<0x00, 0x0, true, kShaCtasPerSmMax>
-                       : sha512_segments_kernel<0x00, 0x0, false, kShaCtasPerSmMax>;
-    case 2:
-        return aligned ? sha512_segments_kernel<0x7f, 0x0, true, kShaCtasPerSmMax>
-                       : sha512_segments_kernel<0x7f, 0x0, false, kShaCtasPerSmMax>;
-    default:
-        return aligned ? sha512_segments_kernel<0x7f, 0x7, true, kShaCtasPerSmMax>
-                       : sha512_segments_kernel<0x7f, 0x7, false, kShaCtasPerSmMax>;
+    case 1: return sha512_segments_kernel_v2<1, kShaCtasPerSmMax>;
+    case 2: return sha512_segments_kernel<0x00, 0x0, true, kShaCtasPerSmMax>;
+    case 3: return sha512_segments_kernel<0x7f, 0x7, true, kShaCtasPerSmMax>;
+    case 4: return sha512_segments_kernel<0x7f, 0x0, true, kShaCtasPerSmMax>;
+    default: return sha512_segments_kernel_v2<0, kShaCtasPerSmMax>;
     }
 }
 
-// Sort `n` descriptors by block count, longest first, into `dst` (pinned).  Counting sort on
-// min(blocks, 65535); the (few) longer ones are ordered exactly with std::sort.
-static void bin_by_length(const SegDesc *src, size_t n, SegDesc *dst, uint64_t *total_blocks,
-                          uint64_t *max_blocks) {
+// Length binning: write the `n` descriptors produced by get(i) into `dst` (pinned memory)
+// sorted by block count, longest first.  Counting sort on min(blocks, 65535); the (few)
+// longer ones are ordered exactly with std::sort.  Large batches are binned by several host
+// threads (per-thread histograms, then a stable scatter).
+struct PlanInfo {
+    uint64_t total_blocks = 0, max_blocks = 0;
+    bool aligned = true;
+    int bad = 0;            // 1: too large, 2: non-final segment not a multiple of 128
+    size_t bad_index = 0;
+};
+
+template <typename Get>
+static void bin_by_length(Get get, size_t n, SegDesc *dst, PlanInfo *info) {
     constexpr uint32_t kCap = 65535;
-    std::vector<uint32_t> count(kCap + 2, 0);
-    uint64_t total = 0, mx = 0;
-    for (size_t i = 0; i < n; i++) {
-        uint64_t nb = seg_blocks(src[i].len, src[i].flags);
-        total += nb;
-        mx = std::max(mx, nb);
-        count[(size_t)std::min<uint64_t>(nb, kCap)]++;
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t nthreads = n < (1u << 16) ? 1 : std::min<size_t>({(size_t)hw, (size_t)8, n >> 15});
+    std::vector<std::vector<uint32_t>> count(nthreads, std::vector<uint32_t>(kCap + 1, 0));
+    std::vector<PlanInfo> part(nthreads);
+    auto range = [&](size_t t) { return std::make_pair(n * t / nthreads, n * (t + 1) / nthreads); };
+    auto pass1 = [&](size_t t) {
+        PlanInfo &pi = part[t];
+        auto [lo, hi] = range(t);
+        uint32_t *cnt = count[t].data();
+        for (size_t i = lo; i < hi; i++) {
+            const SegDesc d = get(i);
+            if (d.len >= kMaxSegBytes && !pi.bad) { pi.bad = 1; pi.bad_index = i; }
+            if ((d.flags & kSegNoFinal) && (d.len & 127) && !pi.bad) { pi.bad = 2; pi.bad_index = i; }
+            pi.aligned = pi.aligned && ((d.off & 15) == 0);
+            const uint64_t nb = seg_blocks(d.len, d.flags);
+            pi.total_blocks += nb;
+            pi.max_blocks = std::max(pi.max_blocks, nb);
+            cnt[(size_t)std::min<uint64_t>(nb, kCap)]++;
+        }
+    };
+    auto run_all = [&](auto fn) {
+        if (nthreads == 1) { fn((size_t)0); return; }
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < nthreads; t++) th.emplace_back(fn, t);
+        fn((size_t)0);
+        for (auto &x : th) x.join();
+    };
+    run_all(pass1);
+    for (const PlanInfo &pi : part) {
+        info->total_blocks += pi.total_blocks;
+        info->max_blocks = std::max(info->max_blocks, pi.max_blocks);
+        info->aligned = info->aligned && pi.aligned;
+        if (pi.bad && !info->bad) { info->bad = pi.bad; info->bad_index = pi.bad_index; }
     }
-    // descending: start position of bucket k = number of items in buckets > k
-    std::vector<size_t> start(kCap + 2, 0);
-    size_t run = 0;
-    for (int64_t k = kCap; k >= 0; k--) {
-        start[(size_t)k] = run;
-        run += count[(size_t)k];
-    }
-    for (size_t i = 0; i < n; i++) {
-        uint64_t nb = seg_blocks(src[i].len, src[i].flags);
-        dst[start[(size_t)std::min<uint64_t>(nb, kCap)]++] = src[i];
-    }
-    if (count[kCap] > 1)
-        std::sort(dst, dst + count[kCap], [](const SegDesc &a, const SegDesc &b) {
+    if (info->bad) return;
+    // descending buckets; inside a bucket thread 0's items first (keeps the sort stable)
+    std::vector<std::vector<size_t>> start(nthreads, std::vector<size_t>(kCap + 1, 0));
+    size_t run = 0, n_long = 0;
+    for (int64_t k = kCap; k >= 0; k--)
+        for (size_t t = 0; t < nthreads; t++) {
+            start[t][(size_t)k] = run;
+            run += count[t][(size_t)k];
+            if (k == kCap) n_long += count[t][(size_t)k];
+        }
+    auto pass2 = [&](size_t t) {
+        auto [lo, hi] = range(t);
+        size_t *st = start[t].data();
+        for (size_t i = lo; i < hi; i++) {
+            const SegDesc d = get(i);
+            dst[st[(size_t)std::min<uint64_t>(seg_blocks(d.len, d.flags), kCap)]++] = d;
+        }
+    };
+    run_all(pass2);
+    if (n_long > 1)
+        std::sort(dst, dst + n_long, [](const SegDesc &a, const SegDesc &b) {
             return seg_blocks(a.len, a.flags) > seg_blocks(b.len, b.flags);
         });
-    *total_blocks = total;
-    *max_blocks = mx;
 }
 
-// Enqueue the hashing of `n` segments of `d_data` on `stream`.  Caller holds D.mu.
-static int launch_sha512(Device &D, cudaStream_t stream, const uint8_t *d_data, const SegDesc *segs, size_t n,
+// Enqueue the hashing of `n` segments (get(i) -> SegDesc) of `d_data` on `stream`.
+// Caller holds D.mu.  The plan goes up on the copy stream so that it overlaps whatever the
+// caller's stream is still running.
+template <typename Get>
+static int launch_sha512(Device &D, cudaStream_t stream, const uint8_t *d_data, Get get, size_t n,
                          uint8_t *d_digests) {
     if (n == 0) return 0;
     if (n > 0xfffffff0ull) return fail(SNAPGPU_EINVAL, "too many files in one launch (%zu)", n);
     auto &R = rt();
-    bool aligned = ((uintptr_t)d_data & 15) == 0;
-    for (size_t i = 0; i < n; i++) {
-        if (segs[i].len >= kMaxSegBytes) return fail(SNAPGPU_EINVAL, "file %zu too large (%llu bytes)", i,
-                                                     (unsigned long long)segs[i].len);
-        if ((segs[i].flags & kSegNoFinal) && (segs[i].len & 127))
-            return fail(SNAPGPU_EINVAL, "non-final segment %zu is not a multiple of 128 bytes", i);
-        aligned = aligned && ((segs[i].off & 15) == 0);
-    }
     PlanSlot *slot;
     int rc = acquire_slot(D, n * sizeof(SegDesc), &slot);
     if (rc) return rc;
-    uint64_t total_blocks = 0, max_blocks = 0;
-    bin_by_length(segs, n, static_cast<SegDesc *>(slot->h_buf), &total_blocks, &max_blocks);
+    PlanInfo info;
+    bin_by_length(get, n, static_cast<SegDesc *>(slot->h_buf), &info);
+    if (info.bad == 1) return fail(SNAPGPU_EINVAL, "file %zu too large", info.bad_index);
+    if (info.bad == 2)
+        return fail(SNAPGPU_EINVAL, "non-final segment %zu is not a multiple of 128 bytes", info.bad_index);
+    const bool aligned = info.aligned && ((uintptr_t)d_data & 15) == 0;
+    const uint64_t total_blocks = info.total_blocks, max_blocks = info.max_blocks;
 
-    SG_CUDA(cudaMemcpyAsync(slot->d_buf, slot->h_buf, n * sizeof(SegDesc), cudaMemcpyHostToDevice, stream));
-    SG_CUDA(cudaMemsetAsync(slot->d_counter, 0, sizeof(u32), stream));
+    SG_CUDA(cudaMemcpyAsync(slot->d_buf, slot->h_buf, n * sizeof(SegDesc), cudaMemcpyHostToDevice, D.copy_stream));
+    SG_CUDA(cudaMemsetAsync(slot->d_counter, 0, sizeof(u32), D.copy_stream));
+    SG_CUDA(cudaEventRecord(slot->uploaded, D.copy_stream));
+    SG_CUDA(cudaStreamWaitEvent(stream, slot->uploaded, 0));
 
     // warps per SM sub-partition: more hides latency better, fewer shortens the makespan when
     // one file is a large share of a lane's work (see DESIGN.md "makespan").
@@ -449,28 +498,39 @@ struct WorkItem {
     uint32_t flags;
 };
 struct Chunk {
-    size_t first, count;   // range in the item list
+    size_t first, count;   // range in the shard's item list, or in the split-piece list
+    bool in_pieces;        // true: `first` indexes the pieces of an item that was split
     uint64_t span_begin, span_end;   // host byte range to copy (span_begin is 16-aligned)
     bool needs_state_in;
+    bool dense_out;        // user_index runs first..first+count-1: results move with one memcpy
+};
+
+struct ChunkPlan {
+    std::vector<Chunk> chunks;
+    std::vector<WorkItem> pieces;   // continuation segments (SHA) / sub-ranges (cmp) of oversized items
+    const WorkItem *base = nullptr;
+    const WorkItem &item(const Chunk &c, size_t i) const { return (c.in_pieces ? pieces.data() : base)[c.first + i]; }
 };
 
 // Cut the shard's item list into chunks that fit `cap` bytes of staging.  Items longer than
-// the staging buffer are split into continuation segments (SHA) or sub-ranges (cmp).
-static void build_chunks(const std::vector<WorkItem> &in, size_t cap, bool is_sha, std::vector<WorkItem> &items,
-                         std::vector<Chunk> &chunks) {
+// the staging buffer are split into continuation segments (SHA) or sub-ranges (cmp).  Items
+// that fit are referenced in place (no copy).
+static void build_chunks(const std::vector<WorkItem> &in, size_t cap, bool is_sha, ChunkPlan &plan) {
     const uint64_t usable = (cap - 64) & ~(uint64_t)127;
-    items.clear();
-    chunks.clear();
-    Chunk cur{0, 0, 0, 0, false};
-    auto close = [&]() {
-        if (cur.count) chunks.push_back(cur);
-        cur = Chunk{items.size(), 0, 0, 0, false};
+    plan.chunks.clear();
+    plan.pieces.clear();
+    plan.base = in.data();
+    Chunk cur{0, 0, false, 0, 0, false, true};
+    auto close = [&](size_t next_first) {
+        if (cur.count) plan.chunks.push_back(cur);
+        cur = Chunk{next_first, 0, false, 0, 0, false, true};
     };
-    for (const WorkItem &w : in) {
+    for (size_t k = 0; k < in.size(); k++) {
+        const WorkItem &w = in[k];
         if (w.len + 16 > usable) {
-            close();
+            close(k + 1);
             uint64_t done = 0;
-            while (done < w.len || (w.len == 0 && done == 0)) {
+            while (done < w.len) {
                 uint64_t piece = std::min<uint64_t>(w.len - done, usable - 128);
                 piece = (done + piece < w.len) ? (piece & ~(uint64_t)127) : piece;
                 WorkItem s = w;
@@ -482,56 +542,74 @@ static void build_chunks(const std::vector<WorkItem> &in, size_t cap, bool is_sh
                     if (done > 0) s.flags |= kSegContinue;
                     if (done + piece < w.len) s.flags |= kSegNoFinal;
                 }
-                items.push_back(s);
+                plan.pieces.push_back(s);
                 const uint64_t begin = s.off & ~(uint64_t)15;
-                chunks.push_back(Chunk{items.size() - 1, 1, begin, s.off + s.len, (s.flags & kSegContinue) != 0});
+                plan.chunks.push_back(Chunk{plan.pieces.size() - 1, 1, true, begin, s.off + s.len,
+                                            (s.flags & kSegContinue) != 0, true});
                 done += piece;
-                if (w.len == 0) break;
             }
-            cur = Chunk{items.size(), 0, 0, 0, false};
             continue;
         }
         const uint64_t begin = w.off & ~(uint64_t)15;
         const uint64_t end = w.off + w.len;
-        bool fits = cur.count > 0 && cur.count < kMaxChunkItems && begin >= cur.span_begin &&
-                    end - cur.span_begin <= usable && (w.off <= cur.span_end + (1u << 20));
+        const bool fits = cur.count > 0 && cur.count < kMaxChunkItems && begin >= cur.span_begin &&
+                          end - cur.span_begin <= usable && (w.off <= cur.span_end + (1u << 20));
         if (!fits) {
-            close();
+            close(k);
             cur.span_begin = begin;
             cur.span_end = end;
+        } else if (w.user_index != in[k - 1].user_index + 1) {
+            cur.dense_out = false;
         }
         cur.span_end = std::max(cur.span_end, end);
         cur.count++;
         cur.needs_state_in = cur.needs_state_in || (is_sha && (w.flags & kSegContinue));
-        items.push_back(w);
     }
-    close();
+    close(in.size());
 }
 
 // Runs one device's shard of a host-buffer SHA-512 batch.  digests: caller's n*64 array.
+static double now_ms() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+static bool trace_on() {
+    static const bool on = getenv("SNAPGPU_TRACE") != nullptr;
+    return on;
+}
+
 static int sha512_shard(Device &D, const uint8_t *data, const std::vector<WorkItem> &shard, uint8_t *digests) {
     if (shard.empty()) return 0;
     std::lock_guard<std::mutex> lock(D.mu);
     SG_CUDA(cudaSetDevice(D.ordinal));
     auto &R = rt();
+    const double t_begin = now_ms();
     const size_t cap = staging_bytes();
-    std::vector<WorkItem> items;
-    std::vector<Chunk> chunks;
-    build_chunks(shard, cap, true, items, chunks);
+    ChunkPlan plan;
+    build_chunks(shard, cap, true, plan);
+    const std::vector<Chunk> &chunks = plan.chunks;
     size_t max_items = 0;
     for (auto &c : chunks) max_items = std::max(max_items, c.count);
     int rc = ensure_staging(D, cap, max_items * 64);
     if (rc) return rc;
+    if (trace_on())
+        fprintf(stderr, "[snapgpu] dev %d: %zu items -> %zu chunks, chunking %.2f ms\n", D.ordinal, shard.size(),
+                chunks.size(), now_ms() - t_begin);
 
     const size_t phase = (uintptr_t)data & 15;   // keep (data + off) mod 16 on the device
-    std::vector<SegDesc> descs;
     int scatter_pending[2] = {-1, -1};            // chunk index whose digests wait in h_out[b]
     auto scatter = [&](int b) -> int {
         if (scatter_pending[b] < 0) return 0;
         SG_CUDA(cudaEventSynchronize(D.ev_done[b]));
         const Chunk &c = chunks[(size_t)scatter_pending[b]];
-        for (size_t i = 0; i < c.count; i++)
-            memcpy(digests + 64 * items[c.first + i].user_index, D.h_out[b] + 64 * i, 64);
+        if (c.dense_out) {
+            memcpy(digests + 64 * plan.item(c, 0).user_index, D.h_out[b], 64 * c.count);
+        } else {
+            for (size_t i = 0; i < c.count; i++)
+                memcpy(digests + 64 * plan.item(c, i).user_index, D.h_out[b] + 64 * i, 64);
+        }
         scatter_pending[b] = -1;
         return 0;
     };
@@ -539,7 +617,9 @@ static int sha512_shard(Device &D, const uint8_t *data, const std::vector<WorkIt
     for (size_t ci = 0; ci < chunks.size(); ci++) {
         const Chunk &c = chunks[ci];
         const int b = (int)(ci & 1);
+        const double t_chunk = now_ms();
         if ((rc = scatter(b))) return rc;        // buffer b (stage, out) is free again
+        const double t_free = now_ms();
         const size_t span = (size_t)(c.span_end - c.span_begin);
         if (span) {
             SG_CUDA(cudaMemcpyAsync(D.d_stage[b] + phase, data + c.span_begin, span, cudaMemcpyHostToDevice,
@@ -551,28 +631,30 @@ static int sha512_shard(Device &D, const uint8_t *data, const std::vector<WorkIt
             // chaining values come from the previous chunk: finish it first
             if ((rc = scatter(b ^ 1))) return rc;
             for (size_t i = 0; i < c.count; i++)
-                memcpy(D.h_out[b] + 64 * i, digests + 64 * items[c.first + i].user_index, 64);
+                memcpy(D.h_out[b] + 64 * i, digests + 64 * plan.item(c, i).user_index, 64);
             SG_CUDA(cudaMemcpyAsync(D.d_out[b], D.h_out[b], c.count * 64, cudaMemcpyHostToDevice, D.compute_stream));
             R.h2d_bytes += c.count * 64;
         }
-        descs.resize(c.count);
-        for (size_t i = 0; i < c.count; i++) {
-            const WorkItem &w = items[c.first + i];
-            descs[i].off = phase + (w.off - c.span_begin);
-            descs[i].len = w.len;
-            descs[i].prefix = w.prefix;
-            descs[i].out_idx = (u32)i;
-            descs[i].flags = w.flags;
-        }
         SG_CUDA(cudaStreamWaitEvent(D.compute_stream, D.ev_copied[b], 0));
-        if ((rc = launch_sha512(D, D.compute_stream, D.d_stage[b], descs.data(), c.count, D.d_out[b]))) return rc;
+        {
+            const WorkItem *wp = &plan.item(c, 0);
+            const uint64_t rebase = phase - c.span_begin;       // host offset -> staging offset
+            auto get = [wp, rebase](size_t i) {
+                return SegDesc{wp[i].off + rebase, wp[i].len, wp[i].prefix, (u32)i, wp[i].flags};
+            };
+            if ((rc = launch_sha512(D, D.compute_stream, D.d_stage[b], get, c.count, D.d_out[b]))) return rc;
+        }
         SG_CUDA(cudaMemcpyAsync(D.h_out[b], D.d_out[b], c.count * 64, cudaMemcpyDeviceToHost, D.compute_stream));
         R.d2h_bytes += c.count * 64;
         SG_CUDA(cudaEventRecord(D.ev_done[b], D.compute_stream));
         scatter_pending[b] = (int)ci;   // scatter(b) syncs on ev_done[b] before buffer b is reused
+        if (trace_on())
+            fprintf(stderr, "[snapgpu] chunk %zu: %zu items, span %.1f MiB, waited %.2f ms for the buffer, enqueue %.2f ms\n",
+                    ci, c.count, (double)(c.span_end - c.span_begin) / (1 << 20), t_free - t_chunk, now_ms() - t_free);
     }
     if ((rc = scatter(0))) return rc;
     if ((rc = scatter(1))) return rc;
+    if (trace_on()) fprintf(stderr, "[snapgpu] dev %d: shard done in %.2f ms\n", D.ordinal, now_ms() - t_begin);
     return 0;
 }
 
@@ -584,9 +666,9 @@ static int cmp_shard(Device &D, const uint8_t *a, const uint8_t *b_host, const s
     auto &R = rt();
     const size_t cap = staging_bytes();
     const size_t half = (cap / 2) & ~(size_t)255;
-    std::vector<WorkItem> items;
-    std::vector<Chunk> chunks;
-    build_chunks(shard, half, false, items, chunks);
+    ChunkPlan plan;
+    build_chunks(shard, half, false, plan);
+    const std::vector<Chunk> &chunks = plan.chunks;
     size_t max_items = 0;
     for (auto &c : chunks) max_items = std::max(max_items, c.count);
     int rc = ensure_staging(D, cap, max_items);
@@ -600,7 +682,7 @@ static int cmp_shard(Device &D, const uint8_t *a, const uint8_t *b_host, const s
         SG_CUDA(cudaEventSynchronize(D.ev_done[b]));
         const Chunk &c = chunks[(size_t)pending[b]];
         for (size_t i = 0; i < c.count; i++)
-            if (D.h_out[b][i] == 0) equal[items[c.first + i].user_index] = 0;
+            if (D.h_out[b][i] == 0) equal[plan.item(c, i).user_index] = 0;
         pending[b] = -1;
         return 0;
     };
@@ -609,7 +691,7 @@ static int cmp_shard(Device &D, const uint8_t *a, const uint8_t *b_host, const s
         const int b = (int)(ci & 1);
         if ((rc = gather(b))) return rc;
         // host-side early-out: a pair already known to differ is not copied again
-        if (c.count == 1 && equal[items[c.first].user_index] == 0) continue;
+        if (c.count == 1 && equal[plan.item(c, 0).user_index] == 0) continue;
         const size_t span = (size_t)(c.span_end - c.span_begin);
         uint8_t *da = D.d_stage[b] + pa, *db = D.d_stage[b] + half + 128 + pb;
         if (span) {
@@ -620,8 +702,8 @@ static int cmp_shard(Device &D, const uint8_t *a, const uint8_t *b_host, const s
         SG_CUDA(cudaEventRecord(D.ev_copied[b], D.copy_stream));
         ci_items.resize(c.count);
         for (size_t i = 0; i < c.count; i++) {
-            ci_items[i].off = items[c.first + i].off - c.span_begin;
-            ci_items[i].len = items[c.first + i].len;
+            ci_items[i].off = plan.item(c, i).off - c.span_begin;
+            ci_items[i].len = plan.item(c, i).len;
         }
         SG_CUDA(cudaStreamWaitEvent(D.compute_stream, D.ev_copied[b], 0));
         // offsets are relative to da/db, whose phases differ only if the host pointers' do
@@ -649,6 +731,7 @@ static void shard_items(const std::vector<WorkItem> &all, const std::vector<uint
         out[0] = all;
         return;
     }
+    for (auto &o : out) o.reserve(all.size() / (size_t)ndev + 16);
     uint64_t total = 0;
     for (uint64_t w : weight) total += w;
     const uint64_t big = std::max<uint64_t>(total / (4 * (uint64_t)ndev), 1);
@@ -693,12 +776,13 @@ static int run_on_devices(const std::vector<std::vector<WorkItem>> &shards,
     return 0;
 }
 
+static int sha512_host_items(const uint8_t *data, const std::vector<WorkItem> &all, uint8_t *digests);
+
 int sha512_host_segments(const uint8_t *data, const HostSeg *segs, size_t n, uint8_t *digests) {
     if (!runtime_ready()) return fail(SNAPGPU_ENOINIT, "snapgpu_init has not been called (or failed)");
     if (n == 0) return 0;
     if (!segs || !digests || (!data && n)) return fail(SNAPGPU_EINVAL, "null argument");
     std::vector<WorkItem> all(n);
-    std::vector<uint64_t> weight(n);
     for (size_t i = 0; i < n; i++) {
         if (segs[i].len >= kMaxSegBytes) return fail(SNAPGPU_EINVAL, "file %zu too large", i);
         u32 f = 0;
@@ -707,10 +791,18 @@ int sha512_host_segments(const uint8_t *data, const HostSeg *segs, size_t n, uin
         if ((f & kSegNoFinal) && (segs[i].len & 127))
             return fail(SNAPGPU_EINVAL, "non-final segment %zu is not a multiple of 128 bytes", i);
         all[i] = WorkItem{i, segs[i].off, segs[i].len, segs[i].prefix, f};
-        weight[i] = seg_blocks(segs[i].len, f) + 1;
     }
+    return sha512_host_items(data, all, digests);
+}
+
+// `all` carries user_index = position; one device: the list is used in place.
+static int sha512_host_items(const uint8_t *data, const std::vector<WorkItem> &all, uint8_t *digests) {
+    auto &R = rt();
+    if (R.devs.size() == 1) return sha512_shard(*R.devs[0], data, all, digests);
+    std::vector<uint64_t> weight(all.size());
+    for (size_t i = 0; i < all.size(); i++) weight[i] = seg_blocks(all[i].len, all[i].flags) + 1;
     std::vector<std::vector<WorkItem>> shards;
-    shard_items(all, weight, (int)rt().devs.size(), shards);
+    shard_items(all, weight, (int)R.devs.size(), shards);
     return run_on_devices(shards, [&](Device &D, const std::vector<WorkItem> &s) {
         return sha512_shard(D, data, s, digests);
     });
@@ -821,10 +913,14 @@ void snapgpu_free(void *p) { free(p); }
 int snapgpu_sha512_batch(const uint8_t *data, const uint64_t *offsets, const uint64_t *lengths, size_t nfiles,
                          uint8_t *digests) {
     if (nfiles == 0) return runtime_ready() ? 0 : fail(SNAPGPU_ENOINIT, "snapgpu_init has not been called (or failed)");
-    if (!offsets || !lengths || !digests) return fail(SNAPGPU_EINVAL, "null argument");
-    std::vector<HostSeg> segs(nfiles);
-    for (size_t i = 0; i < nfiles; i++) segs[i] = HostSeg{offsets[i], lengths[i], 0, 0};
-    return sha512_host_segments(data, segs.data(), nfiles, digests);
+    if (!data || !offsets || !lengths || !digests) return fail(SNAPGPU_EINVAL, "null argument");
+    if (!runtime_ready()) return fail(SNAPGPU_ENOINIT, "snapgpu_init has not been called (or failed)");
+    std::vector<WorkItem> all(nfiles);
+    for (size_t i = 0; i < nfiles; i++) {
+        if (lengths[i] >= kMaxSegBytes) return fail(SNAPGPU_EINVAL, "file %zu too large", i);
+        all[i] = WorkItem{i, offsets[i], lengths[i], 0, 0};
+    }
+    return sha512_host_items(data, all, digests);
 }
 
 int snapgpu_sha512_stream(uint8_t state[64], int first, const uint8_t *data, uint64_t len, uint64_t prefix_bytes,
@@ -863,15 +959,9 @@ int snapgpu_sha512_batch_device(int dev, const void *d_data, const uint64_t *off
     if (!d_data || !offsets || !lengths || !d_digests) return fail(SNAPGPU_EINVAL, "null argument");
     std::lock_guard<std::mutex> lock(D->mu);
     SG_CUDA(cudaSetDevice(D->ordinal));
-    std::vector<SegDesc> segs(nfiles);
-    for (size_t i = 0; i < nfiles; i++) {
-        segs[i].off = offsets[i];
-        segs[i].len = lengths[i];
-        segs[i].prefix = 0;
-        segs[i].out_idx = (u32)i;
-        segs[i].flags = 0;
-    }
-    return launch_sha512(*D, (cudaStream_t)stream, static_cast<const uint8_t *>(d_data), segs.data(), nfiles,
+    if (nfiles > 0xfffffff0ull) return fail(SNAPGPU_EINVAL, "too many files in one launch (%zu)", nfiles);
+    auto get = [offsets, lengths](size_t i) { return SegDesc{offsets[i], lengths[i], 0, (u32)i, 0}; };
+    return launch_sha512(*D, (cudaStream_t)stream, static_cast<const uint8_t *>(d_data), get, nfiles,
                          static_cast<uint8_t *>(d_digests));
 }
 
@@ -970,10 +1060,10 @@ void snapgpu_reset_stats(void) {
 // Launch order the length binning produces: order[k] = index of the k-th file of the plan.
 int snapgpu_test_plan_order(const uint64_t *lengths, size_t n, uint32_t *order) {
     if (!lengths || !order) return fail(SNAPGPU_EINVAL, "null argument");
-    std::vector<SegDesc> src(n), dst(n);
-    for (size_t i = 0; i < n; i++) src[i] = SegDesc{0, lengths[i], 0, (u32)i, 0};
-    uint64_t total = 0, mx = 0;
-    bin_by_length(src.data(), n, dst.data(), &total, &mx);
+    std::vector<SegDesc> dst(n);
+    PlanInfo info;
+    bin_by_length([lengths](size_t i) { return SegDesc{0, std::min<uint64_t>(lengths[i], kMaxSegBytes - 1), 0, (u32)i, 0}; },
+                  n, dst.data(), &info);
     for (size_t i = 0; i < n; i++) order[i] = dst[i].out_idx;
     return 0;
 }
@@ -997,15 +1087,16 @@ int snapgpu_test_shard(const uint64_t *weights, size_t n, int ndev, int *device_
 long long snapgpu_test_chunks(const uint64_t *offsets, const uint64_t *lengths, size_t n, uint64_t cap, int is_sha,
                               uint64_t *rows, size_t max_rows) {
     if (!offsets || !lengths || cap < 4096) return fail(SNAPGPU_EINVAL, "bad argument");
-    std::vector<WorkItem> in(n), items;
-    std::vector<Chunk> chunks;
+    std::vector<WorkItem> in(n);
+    ChunkPlan plan;
     for (size_t i = 0; i < n; i++) in[i] = WorkItem{i, offsets[i], lengths[i], 0, 0};
-    build_chunks(in, (size_t)cap, is_sha != 0, items, chunks);
+    build_chunks(in, (size_t)cap, is_sha != 0, plan);
+    const std::vector<Chunk> &chunks = plan.chunks;
     size_t row = 0;
     for (size_t c = 0; c < chunks.size(); c++)
         for (size_t i = 0; i < chunks[c].count; i++, row++) {
             if (!rows || row >= max_rows) continue;
-            const WorkItem &w = items[chunks[c].first + i];
+            const WorkItem &w = plan.item(chunks[c], i);
             uint64_t *r = rows + 6 * row;
             r[0] = w.user_index; r[1] = w.off; r[2] = w.len; r[3] = w.prefix; r[4] = w.flags; r[5] = c;
         }
@@ -1022,6 +1113,7 @@ int snapgpu_pipe_microbench(int dev, int kind, int warps_per_sm, double *inst_pe
     static const ProbeKernel table[kProbeCount] = {
         pipe_probe_kernel<0>, pipe_probe_kernel<1>, pipe_probe_kernel<2>, pipe_probe_kernel<3>,
         pipe_probe_kernel<4>, pipe_probe_kernel<5>, pipe_probe_kernel<6>, pipe_probe_kernel<7>,
+        pipe_probe_kernel<8>, pipe_probe_kernel<9>, pipe_probe_kernel<10>, pipe_probe_kernel<11>,
     };
     if (kind < 0 || kind >= kProbeCount) return fail(SNAPGPU_EINVAL, "unknown probe kind %d", kind);
     if (warps_per_sm < 4 || warps_per_sm > 64 || warps_per_sm % 4) return fail(SNAPGPU_EINVAL, "warps_per_sm must be 4..64, multiple of 4");
@@ -1059,8 +1151,10 @@ int snapgpu_pipe_microbench(int dev, int kind, int warps_per_sm, double *inst_pe
     cudaFree(d_out);
     cudaFree(d_clk);
     const double mhz = clk[1] ? (double)clk[0] / (double)clk[1] * 1e3 : 0.0;
+    // Rate from the whole launch (CUDA events x measured SM clock): one CTA's own clock64 span
+    // is misleading because the warp scheduler lets the oldest CTA of an SM run ahead.
     const double warp_insts = (double)iters * probe_ops_per_iter(kind) * warps_per_sm;   // per SM
-    const double cycles = clk[0] ? (double)clk[0] : best * 1e-3 * mhz * 1e6;
+    const double cycles = best * 1e-3 * mhz * 1e6;
     if (inst_per_clk_per_sm) *inst_per_clk_per_sm = cycles > 0 ? warp_insts / cycles : 0.0;
     if (elapsed_ms) *elapsed_ms = best;
     if (sm_clock_mhz) *sm_clock_mhz = mhz;

@@ -1,0 +1,86 @@
+"""Static checks of the machine code (cuobjdump, no GPU): the instruction mix the design
+relies on is what ptxas actually emitted."""
+import re
+import shutil
+import subprocess
+from collections import Counter
+
+import pytest
+
+pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not on PATH")
+
+
+@pytest.fixture(scope="module")
+def sass(native):
+    text = subprocess.run(["cuobjdump", "-sass", str(native.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    funcs, cur = {}, None
+    for line in text.splitlines():
+        m = re.match(r"\s+Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            funcs[cur] = Counter()
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", line)
+        if m and cur:
+            funcs[cur][m.group(1)] += 1
+    return funcs
+
+
+def find(funcs, *needles):
+    hits = [f for f in funcs if all(n in f for n in needles)]
+    assert len(hits) == 1, (needles, hits)
+    return funcs[hits[0]]
+
+
+def count(c, prefix):
+    return sum(v for k, v in c.items() if k.startswith(prefix))
+
+
+def test_only_sm100a_code(native):
+    out = subprocess.run(["cuobjdump", "-lelf", str(native.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and not re.search(r"sm_[89]\d", out)
+
+
+def test_default_kernel_is_compact_and_staged(sass):
+    """Variant 0: 16-round loop (fits the instruction cache), cp.async staging, no spills."""
+    c = find(sass, "sha512_segments_kernel_v2", "ILi0E")
+    total = sum(c.values())
+    assert total < 2600                                     # ~33 KB of code, was ~65 KB fully unrolled
+    assert count(c, "LDGSTS") >= 16                         # cp.async: 8 full + 8 tail copies per block
+    assert count(c, "LDS") >= 8 and count(c, "LDG.E.128") <= 8          # LDG only for descriptors / state
+    assert count(c, "SHF.R.W") >= 16 * 12 * 2 + 16 * 10     # two round groups + one schedule group
+    assert count(c, "LDL") == 0 and count(c, "STL") == 0
+    assert count(c, "IMAD.WIDE") < 8 and count(c, "IMAD.HI") == 0   # both measured at half rate
+
+
+def test_fma_add_variant_mix(sass):
+    """Variant 3: rotates are funnel shifts, logic is LOP3, 64-bit adds sit on the FMA pipe."""
+    c = find(sass, "sha512_segments_kernel", "Li127ELi7ELb1")
+    assert count(c, "SHF.R.W") == 1600                      # 80*12 + 64*10 funnel shifts
+    assert 896 <= count(c, "LOP3") <= 1000                  # 80*8 + 64*4 (+ padding logic)
+    assert count(c, "IMAD.WIDE") >= 750                     # 7*80 + 3*64 + 8 = 760 wide accumulates
+    assert count(c, "IADD3") < 60                           # the adds really left the ALU pipe
+    assert count(c, "LDL") == 0 and count(c, "STL") == 0    # no spills
+    assert sum(v for k, v in c.items() if k.startswith("LDG") and ".128" in k) >= 8   # 128-bit message loads
+
+
+def test_alu_add_variant_mix(sass):
+    c = find(sass, "sha512_segments_kernel", "Li0ELi0ELb1")
+    assert count(c, "SHF.R.W") == 1600
+    assert count(c, "IADD3") >= 700 and count(c, "IMAD.WIDE") < 10
+    assert count(c, "LDL") == 0 and count(c, "STL") == 0
+
+
+def test_cmp_kernel_uses_128_bit_loads(sass):
+    c = find(sass, "cmp_pairs_kernel", "Lb1")
+    wide = sum(v for k, v in c.items() if k.startswith("LDG") and ".128" in k)
+    assert wide >= 8                                        # 4 rows x 2 streams, 128 bits per lane
+    assert all(".NA." in k for k in c if k.startswith("LDG") and ".128" in k)   # streamed past L1
+    assert count(c, "VOTE") >= 1
+
+
+@pytest.mark.parametrize("kind,opcode,least", [(0, "IADD3", 128), (1, "LOP3", 128), (2, "SHF.R.W", 128),
+                                               (3, "IMAD", 128), (4, "IMAD.WIDE", 128)])
+def test_probe_kernels_issue_what_they_claim(sass, kind, opcode, least):
+    c = find(sass, "pipe_probe_kernel", f"ILi{kind}E")
+    assert count(c, opcode) >= least, c.most_common(6)

@@ -32,8 +32,9 @@ props = torch.cuda.get_device_properties(dev)
 emit({"what": "device", "name": props.name, "sms": props.multi_processor_count,
       "mem_gb": props.total_memory / 1e9})
 
-names = ["IADD3", "LOP3", "SHF", "IMAD", "IMAD.WIDE", "IADD3+IMAD", "LOP3+IMAD.WIDE", "SHA-mix 10:3:3"]
-for kind in range(8):
+names = ["IADD3", "LOP3", "SHF", "IMAD", "IMAD.WIDE", "IADD3+IMAD", "LOP3+IMAD.WIDE", "SHA-mix 10:3:3",
+         "IMAD.HI", "LOP3+IMAD.HI", "SHF:IMAD:IMAD.HI 2:1:1", "IADD3+IMAD.X"]
+for kind in range(12):
     for w in (4, 8, 16, 32):
         r = device.pipe_microbench(kind, w)
         r.update(what="pipe", name=names[kind])
@@ -60,6 +61,7 @@ workloads = {
     "cfg5-shard-50k": np.full(50_000, 65536, dtype=np.uint64),
     "cfg1": np.full(1000, 4096, dtype=np.uint64),
     "4k-x-400k": np.full(400_000, 4096, dtype=np.uint64),
+    "cfg5-shard-250k": np.full(250_000, 65536, dtype=np.uint64),
 }
 for wname, lengths in workloads.items():
     off, total = synth.layout(lengths)
