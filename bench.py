@@ -23,6 +23,7 @@ from __future__ import annotations
 
 import argparse
 import ctypes
+import datetime
 import json
 import os
 import subprocess
@@ -54,46 +55,92 @@ def measured_peaks() -> dict:
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """nvidia-smi clocks and throttle reasons sampled DURING the timed regions.
+
+    nvidia-smi runs for the whole benchmark (it needs ~100 ms to produce its first row); the
+    rows are then filtered by their timestamps to the windows marked with begin()/end()."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index = index
         self.proc = None
         self.path = None
+        self.windows = []
+        self._t0 = None
 
     def start(self):
         try:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=f,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=f,
                                          stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
+    def begin(self):
+        self._t0 = datetime.datetime.now()
+
+    def end(self):
+        if self._t0 is not None:
+            self.windows.append((self._t0, datetime.datetime.now()))
+            self._t0 = None
+
     def stop(self) -> dict:
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        rows = []
+        rows, inside = [], []
         for line in Path(self.path).read_text().splitlines():
             parts = [x.strip() for x in line.split(",")]
-            if len(parts) == 7 and parts[0].replace(".", "").isdigit():
-                rows.append(parts)
+            if len(parts) != 8:
+                continue
+            try:
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f")
+                float(parts[1])
+            except ValueError:
+                continue
+            rows.append(parts)
+            pad = datetime.timedelta(milliseconds=25)      # a row describes the ~20 ms before its timestamp
+            if any(a - pad <= ts <= b + pad for a, b in self.windows):
+                inside.append(parts)
         os.unlink(self.path)
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = sorted(float(r[0]) for r in rows)
+        use = inside or rows
+        sm = sorted(float(r[1]) for r in use)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "samples": len(rows),
-                "power_w_max": max(float(r[2]) for r in rows if r[2].replace(".", "").isdigit() or True), "reasons": reasons}
+        reasons = [n for k, n in enumerate(names) if any(r[4 + k].lower().startswith("active") for r in use)]
+
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return 0.0
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": float(use[0][2]),
+                "samples": len(use), "samples_in_timed_regions": len(inside), "samples_total": len(rows),
+                "power_w_max": max(num(r[3]) for r in use), "reasons": reasons}
+
+
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the newest committed ncu --set full capture of this
+    bench command (profiles/r*_traffic.json, written by tools/ncu_traffic.py), or None."""
+    best = None
+    for p in sorted((ROOT / "profiles").glob("r*_traffic.json")):
+        try:
+            d = json.loads(p.read_text())
+        except ValueError:
+            continue
+        if kernel in d:
+            best = dict(d[kernel], source=p.name)
+    return best
 
 
 def workload(name: str, rank: int):
@@ -173,13 +220,14 @@ def run_reference(args, rank: int, world: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg5"])
     ap.add_argument("--no-cmp", action="store_true", help="skip the config 4 compare kernel figures")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-tail", action="store_true", help="skip the single-long-file latency sample")
     ap.add_argument("--variant", type=int, default=None)
     ap.add_argument("--warps", type=int, default=None)
     args = ap.parse_args()
@@ -205,6 +253,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     N.init([local_rank])
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     if args.variant is not None:
         N.set_option("sha_variant", args.variant)
     if args.warps is not None:
@@ -239,19 +290,17 @@ def main():
         device.sha512_batch_device(d_data, offsets, lengths, d_digests)
     torch.cuda.synchronize()
     N.reset_stats()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     barrier()
+    sampler.begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         device.sha512_batch_device(d_data, offsets, lengths, d_digests)
     e1.record()
     torch.cuda.synchronize()
+    sampler.end()
     barrier()
     ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
-    clocks = sampler.stop() if rank == 0 else None
     st = N.stats()
     launches = int(st.kernel_launches)
     kernel_ms = st.sha512_kernel_ms_sum / max(st.sha512_kernel_timed, 1)
@@ -271,16 +320,19 @@ def main():
         e2e_steps = max(3, min(args.steps, 10))
         N.reset_stats()
         barrier()
+        sampler.begin()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             dg = helpers.sha512_batch(host_view, offsets, lengths)
         torch.cuda.synchronize()
         dt = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+        sampler.end()
         st2 = N.stats()
         e2e = {"value": world * file_bytes / dt / 1e9, "unit": "GB/s", "ms_per_step": dt * 1e3,
                "files_per_s": world * len(lengths) / dt,
                "h2d_bytes_per_step": int(st2.h2d_bytes // e2e_steps), "d2h_bytes_per_step": int(st2.d2h_bytes // e2e_steps),
-               "bound": "PCIe host-to-device copy (pinned memory, one span per 256 MiB chunk, double buffered)",
+               "bound": "PCIe host-to-device copy (pinned host memory; chunks of 64 MiB, 256 MiB, then 1 GiB, double buffered)",
+               "timing": "host wall clock around the synchronous C-ABI call (digests are in host memory on return), max over ranks",
                "h2d_gbs_per_gpu": st2.h2d_bytes / e2e_steps / dt / 1e9}
 
     if rank != 0:
@@ -288,6 +340,7 @@ def main():
             dist.barrier()
             dist.destroy_process_group()
         return
+    clocks = sampler.stop()
 
     # ---- roofline of the dominant kernel (rank 0's launch; every rank runs the same shape) ---
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -297,7 +350,7 @@ def main():
     mix = device.pipe_microbench(7, 16)
     measured_alu_peak = alu["warp_inst_per_clk_per_sm"] * 32 * sms * alu["sm_clock_mhz"] * 1e6 / 1e12
     roofline = {
-        "bound": "int_alu", "kernel": "sha512_segments_kernel",
+        "bound": "int_alu", "kernel": "sha512_segments_kernel_v2" if not args.variant or args.variant == 1 else "sha512_segments_kernel",
         "achieved": achieved, "peak": nominal_peak, "unit": "T int32-instr/s", "frac": achieved / nominal_peak,
         "peak_source": f"{sms} SMs x {INT32_LANES_PER_SM} int32 lanes/clk x sm_max_mhz {peaks['sm_max_mhz']} ({peaks['_source']})",
         "algorithmic_instr_per_block": ALGO_INSTR_PER_BLOCK, "blocks_per_launch": nblocks,
@@ -305,7 +358,9 @@ def main():
         "measured_alu_pipe": {"warp_inst_per_clk_per_sm": alu["warp_inst_per_clk_per_sm"], "sm_clock_mhz": alu["sm_clock_mhz"],
                               "peak_T_instr_s": measured_alu_peak, "frac": achieved / measured_alu_peak if measured_alu_peak else None},
         "sha_mix_probe_warp_inst_per_clk_per_sm": mix["warp_inst_per_clk_per_sm"],
-        "traffic": None,
+        "traffic": (ncu_traffic("sha512") or {}).get("dram_bytes") if args.workload == "cfg2" else None,
+        "traffic_detail": ncu_traffic("sha512") if args.workload == "cfg2" else None,
+        "algorithmic_bytes": file_bytes + 64 * len(lengths) + 36 * len(lengths),
         "hbm": {"achieved_gbs": file_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
                 "frac": file_bytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
     }
@@ -345,9 +400,34 @@ def main():
         cmp_res = {"workload": "config 4: 10,000 pairs x 1 MiB, 1% differ by one byte", "bound": "hbm",
                    "achieved": algo_bytes / (cms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                    "frac": algo_bytes / (cms * 1e-3) / 1e9 / peaks["hbm_gbs"], "kernel_ms": cms,
-                   "step_ms": c0.elapsed_time(c1) / csteps, "algorithmic_bytes": algo_bytes, "traffic": None,
+                   "step_ms": c0.elapsed_time(c1) / csteps, "algorithmic_bytes": algo_bytes,
+                   "traffic": (ncu_traffic("cmp") or {}).get("dram_bytes"), "traffic_detail": ncu_traffic("cmp"),
                    "peak_source": peaks["_source"]}
         del da, db
+
+    # ---- tail latency: the serial chain of ONE long file (north_star: reported separately) ----
+    tail = None
+    if not args.no_tail:
+        tl = np.array([16 << 20], dtype=np.uint64)
+        to, ttotal = synth.layout(tl)
+        dt_ = torch.empty(ttotal, dtype=torch.uint8, device=dev)
+        device.synth_fill_device(dt_, to, tl)
+        dgt = torch.empty((1, 64), dtype=torch.uint8, device=dev)
+        device.sha512_batch_device(dt_, to, tl, dgt)
+        torch.cuda.synchronize()
+        N.reset_stats()
+        device.sha512_batch_device(dt_, to, tl, dgt)
+        torch.cuda.synchronize()
+        tms = N.stats().sha512_kernel_ms_sum
+        launches += 2
+        tblocks = int(synth.blocks(tl)[0])
+        tail = {"what": "one 16 MiB file alone on the GPU: a single SHA-512 chain cannot be split, so this is the "
+                        "latency floor of the longest file of a batch",
+                "file_bytes": int(tl[0]), "blocks": tblocks, "kernel_ms": tms, "us_per_block": tms * 1e3 / tblocks,
+                "mb_per_s_per_stream": int(tl[0]) / (tms * 1e-3) / 1e6,
+                "extrapolated_s_per_GiB": tms * 1e-3 * (1 << 30) / int(tl[0]),
+                "sha512_hex_prefix": dgt.cpu().numpy().tobytes().hex()[:16]}
+        del dt_
 
     # ---- CPU baseline: the oracle on this box's cores, bounded sample ------------------------
     cpu = None
@@ -388,7 +468,7 @@ def main():
                    "cache": "inputs (1.29 GB per GPU) larger than the 126 MB L2; no flush needed",
                    "sha_variant": int(args.variant or 0)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-        "roofline_cmp": cmp_res, "cpu_baseline": cpu,
+        "roofline_cmp": cmp_res, "tail_latency": tail, "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

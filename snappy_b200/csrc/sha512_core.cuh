@@ -229,29 +229,35 @@ __device__ __forceinline__ u64 add64_split(u64 a, u64 b, u32 one) {
 
 // kAddMode 0: plain 64-bit adds (ptxas pairs them into 3-input IADD3 / IADD3.X)
 // kAddMode 1: every add split ALU(lo) / FMA(hi)
-template <int kAddMode>
+// kAddMode 0x1000 | sched << 8 | round: per-add pipe choice.  A set bit sends that 64-bit add
+//   to the FMA pipe as IMAD.WIDE.U32 + IMAD (add64_fma); a clear bit leaves it on the ALU.
+//   round bits  0: W+K   1: h+(W+K)   2: Sigma1+Ch   3: T1   4: T2=Sigma0+Maj   5: e'=d+T1   6: a'=T1+T2
+//   sched bits  0: sigma0+W[t-16]   1: sigma1+W[t-7]   2: their sum
+template <int kAddMode, int kBit>
 __device__ __forceinline__ u64 addm(u64 a, u64 b, u32 one) {
     if constexpr (kAddMode == 1) return add64_split(a, b, one);
+    else if constexpr ((kAddMode & 0x1000) != 0 && ((kAddMode >> kBit) & 1) != 0) return add64_fma(a, b, one);
     else return a + b;
 }
 
 template <int kAddMode>
-__device__ __forceinline__ void sha512_round(u64 a, u64 b, u64 c, u64 &d, u64 e, u64 f, u64 g, u64 &h, u64 kw, u32 one) {
-    u64 t1 = addm<kAddMode>(addm<kAddMode>(h, kw, one), addm<kAddMode>(big_sigma1(e), ch64(e, f, g), one), one);
-    u64 t2 = addm<kAddMode>(big_sigma0(a), maj64(a, b, c), one);
-    d = addm<kAddMode>(d, t1, one);
-    h = addm<kAddMode>(t1, t2, one);
+__device__ __forceinline__ void sha512_round(u64 a, u64 b, u64 c, u64 &d, u64 e, u64 f, u64 g, u64 &h, u64 w, u64 k, u32 one) {
+    u64 kw = addm<kAddMode, 0>(w, k, one);
+    u64 t1 = addm<kAddMode, 3>(addm<kAddMode, 1>(h, kw, one), addm<kAddMode, 2>(big_sigma1(e), ch64(e, f, g), one), one);
+    u64 t2 = addm<kAddMode, 4>(big_sigma0(a), maj64(a, b, c), one);
+    d = addm<kAddMode, 5>(d, t1, one);
+    h = addm<kAddMode, 6>(t1, t2, one);
 }
 
-#define SNAPGPU_R8(W, KB, I)                                                                        \
-    sha512_round<kAddMode>(a, b, c, d, e, f, g, h, addm<kAddMode>(W[I + 0], KB[I + 0], one), one);  \
-    sha512_round<kAddMode>(h, a, b, c, d, e, f, g, addm<kAddMode>(W[I + 1], KB[I + 1], one), one);  \
-    sha512_round<kAddMode>(g, h, a, b, c, d, e, f, addm<kAddMode>(W[I + 2], KB[I + 2], one), one);  \
-    sha512_round<kAddMode>(f, g, h, a, b, c, d, e, addm<kAddMode>(W[I + 3], KB[I + 3], one), one);  \
-    sha512_round<kAddMode>(e, f, g, h, a, b, c, d, addm<kAddMode>(W[I + 4], KB[I + 4], one), one);  \
-    sha512_round<kAddMode>(d, e, f, g, h, a, b, c, addm<kAddMode>(W[I + 5], KB[I + 5], one), one);  \
-    sha512_round<kAddMode>(c, d, e, f, g, h, a, b, addm<kAddMode>(W[I + 6], KB[I + 6], one), one);  \
-    sha512_round<kAddMode>(b, c, d, e, f, g, h, a, addm<kAddMode>(W[I + 7], KB[I + 7], one), one);
+#define SNAPGPU_R8(W, KB, I)                                                            \
+    sha512_round<kAddMode>(a, b, c, d, e, f, g, h, W[I + 0], KB[I + 0], one);           \
+    sha512_round<kAddMode>(h, a, b, c, d, e, f, g, W[I + 1], KB[I + 1], one);           \
+    sha512_round<kAddMode>(g, h, a, b, c, d, e, f, W[I + 2], KB[I + 2], one);           \
+    sha512_round<kAddMode>(f, g, h, a, b, c, d, e, W[I + 3], KB[I + 3], one);           \
+    sha512_round<kAddMode>(e, f, g, h, a, b, c, d, W[I + 4], KB[I + 4], one);           \
+    sha512_round<kAddMode>(d, e, f, g, h, a, b, c, W[I + 5], KB[I + 5], one);           \
+    sha512_round<kAddMode>(c, d, e, f, g, h, a, b, W[I + 6], KB[I + 6], one);           \
+    sha512_round<kAddMode>(b, c, d, e, f, g, h, a, W[I + 7], KB[I + 7], one);
 
 template <int kAddMode>
 __device__ __forceinline__ void sha512_compress_compact(u64 (&st)[8], u64 (&w)[16], bool commit, u32 one) {
@@ -264,9 +270,9 @@ __device__ __forceinline__ void sha512_compress_compact(u64 (&st)[8], u64 (&w)[1
         // schedule for the next 16 rounds, in place: W[t+16] = s1(W[t+14]) + W[t+9] + s0(W[t+1]) + W[t]
 #pragma unroll
         for (int i = 0; i < 16; i++) {
-            u64 x = addm<kAddMode>(small_sigma0(w[(i + 1) & 15]), w[i], one);
-            u64 y = addm<kAddMode>(small_sigma1(w[(i + 14) & 15]), w[(i + 9) & 15], one);
-            w[i] = addm<kAddMode>(x, y, one);
+            u64 x = addm<kAddMode, 8>(small_sigma0(w[(i + 1) & 15]), w[i], one);
+            u64 y = addm<kAddMode, 9>(small_sigma1(w[(i + 14) & 15]), w[(i + 9) & 15], one);
+            w[i] = addm<kAddMode, 10>(x, y, one);
         }
     }
     {

@@ -4,10 +4,10 @@
 //   snappy/build.go:240-247  ->  helpers.Sha512sum (helpers/helpers.go:188-201).
 //
 // Work layout
-//   * the host sorts the segment descriptors by 128-byte block count, longest first
-//     (length binning: the 32 lanes of a warp get neighbours of the sorted list, so they
-//     run the same number of blocks and stay converged);
-//   * a "unit" is 32 consecutive descriptors = one warp's worth of files;
+//   * the host sorts the indices of the segment descriptors by 128-byte block count, longest
+//     first (length binning: the 32 lanes of a warp get neighbours of the sorted list, so
+//     they run the same number of blocks and stay converged);
+//   * a "unit" is 32 consecutive entries of that order = one warp's worth of files;
 //   * the kernel is persistent: one CTA of 4 warps per (SM x kCtasPerSm), every warp pulls
 //     the next unit from a global counter (longest-processing-time-first list scheduling,
 //     which is what bounds the makespan when a few files are much longer than the rest);
@@ -100,7 +100,8 @@ __device__ __forceinline__ void pad_block(u64 (&w)[16], long long rem, bool last
 
 template <int kRoundFma, int kSchedFma, bool kAligned16, int kCtasPerSm>
 __global__ void __launch_bounds__(kShaThreads, kCtasPerSm)
-sha512_segments_kernel(const uint8_t *__restrict__ data, const SegDesc *__restrict__ descs, u32 nsegs,
+sha512_segments_kernel(const uint8_t *__restrict__ data, const SegDesc *__restrict__ descs,
+                       const u32 *__restrict__ order, u32 nsegs,
                        uint8_t *__restrict__ digests, u32 *__restrict__ unit_counter, u32 one) {
     const u32 lane = threadIdx.x & 31;
     const u32 warp = threadIdx.x >> 5;
@@ -115,7 +116,7 @@ sha512_segments_kernel(const uint8_t *__restrict__ data, const SegDesc *__restri
         SegDesc sd;
         sd.off = 0; sd.len = 0; sd.prefix = 0; sd.out_idx = 0; sd.flags = kSegNoFinal;
         if (have) {
-            const uint4 *q = reinterpret_cast<const uint4 *>(descs + idx);
+            const uint4 *q = reinterpret_cast<const uint4 *>(descs + order[idx]);
             uint4 q0 = q[0], q1 = q[1];
             sd.off = pack64(q0.x, q0.y); sd.len = pack64(q0.z, q0.w);
             sd.prefix = pack64(q1.x, q1.y); sd.out_idx = q1.z; sd.flags = q1.w;
@@ -226,7 +227,8 @@ __device__ __forceinline__ void stage_block(u32 stage_addr, u32 lane, const uint
 
 template <int kAddMode, int kCtasPerSm>
 __global__ void __launch_bounds__(kShaThreads, kCtasPerSm)
-sha512_segments_kernel_v2(const uint8_t *__restrict__ data, const SegDesc *__restrict__ descs, u32 nsegs,
+sha512_segments_kernel_v2(const uint8_t *__restrict__ data, const SegDesc *__restrict__ descs,
+                          const u32 *__restrict__ order, u32 nsegs,
                           uint8_t *__restrict__ digests, u32 *__restrict__ unit_counter, u32 one) {
     __shared__ __align__(16) uint8_t stages[kShaWarpsPerCta][2][kStageBytesPerWarp];
     const u32 lane = threadIdx.x & 31;
@@ -242,7 +244,7 @@ sha512_segments_kernel_v2(const uint8_t *__restrict__ data, const SegDesc *__res
         SegDesc sd;
         sd.off = 0; sd.len = 0; sd.prefix = 0; sd.out_idx = 0; sd.flags = kSegNoFinal;
         if (have) {
-            const uint4 *q = reinterpret_cast<const uint4 *>(descs + idx);
+            const uint4 *q = reinterpret_cast<const uint4 *>(descs + order[idx]);
             uint4 q0 = q[0], q1 = q[1];
             sd.off = pack64(q0.x, q0.y); sd.len = pack64(q0.z, q0.w);
             sd.prefix = pack64(q1.x, q1.y); sd.out_idx = q1.z; sd.flags = q1.w;

@@ -240,10 +240,21 @@ static void harvest_timings(TimedLaunch *ring, int n, double &sum, uint64_t &cnt
 // SHA-512 launch: length binning + persistent kernel
 // ------------------------------------------------------------------------------------------
 
-typedef void (*ShaKernel)(const uint8_t *, const SegDesc *, u32, uint8_t *, u32 *, u32);
+static double now_ms() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+static bool trace_on() {
+    static const bool on = getenv("SNAPGPU_TRACE") != nullptr;
+    return on;
+}
+
+typedef void (*ShaKernel)(const uint8_t *, const SegDesc *, const u32 *, u32, uint8_t *, u32 *, u32);
 
 constexpr int kShaCtasPerSmMax = 3;   // 168 registers per thread: no spills with the one-block-ahead prefetch
-constexpr int kShaVariants = 5;
+constexpr int kShaVariants = 12;
 
 // variant 0 (default): compact 16-round loop, cp.async staging through shared memory, plain
 //            64-bit adds (ptxas pairs them into 3-input IADD3 / IADD3.X)
@@ -251,6 +262,11 @@ constexpr int kShaVariants = 5;
 // variant 2: 80 rounds fully unrolled, register prefetch, ALU adds          (round-1 first cut)
 // variant 3: fully unrolled, every add as IMAD.WIDE + IMAD on the FMA pipe  (measured slower)
 // variant 4: fully unrolled, round adds on FMA, schedule adds on ALU
+// variants 5..11: compact loop with a per-add choice of pipe (sha512_core.cuh, kAddMode 0x1000|...)
+//            5: every add on FMA         6: round adds on FMA        7: schedule adds on FMA
+//            8: off-chain round adds (W+K, h+KW, Sigma0+Maj) + schedule on FMA
+//            9: off-chain round adds on FMA      10: W+K and schedule sums on FMA
+//           11: W+K, h+KW, Sigma1+Ch, Sigma0+Maj and schedule on FMA (state adds stay on ALU)
 // Input that is not 16-byte aligned always takes the register-load kernel (any alignment).
 static ShaKernel sha_kernel_for(int variant, bool aligned) {
     if (!aligned) return sha512_segments_kernel<0x00, 0x0, false, kShaCtasPerSmMax>;
@@ -259,14 +275,24 @@ static ShaKernel sha_kernel_for(int variant, bool aligned) {
     case 2: return sha512_segments_kernel<0x00, 0x0, true, kShaCtasPerSmMax>;
     case 3: return sha512_segments_kernel<0x7f, 0x7, true, kShaCtasPerSmMax>;
     case 4: return sha512_segments_kernel<0x7f, 0x0, true, kShaCtasPerSmMax>;
+    case 5: return sha512_segments_kernel_v2<0x1000 | 0x700 | 0x7f, kShaCtasPerSmMax>;
+    case 6: return sha512_segments_kernel_v2<0x1000 | 0x000 | 0x7f, kShaCtasPerSmMax>;
+    case 7: return sha512_segments_kernel_v2<0x1000 | 0x700 | 0x00, kShaCtasPerSmMax>;
+    case 8: return sha512_segments_kernel_v2<0x1000 | 0x700 | 0x13, kShaCtasPerSmMax>;
+    case 9: return sha512_segments_kernel_v2<0x1000 | 0x000 | 0x13, kShaCtasPerSmMax>;
+    case 10: return sha512_segments_kernel_v2<0x1000 | 0x400 | 0x01, kShaCtasPerSmMax>;
+    case 11: return sha512_segments_kernel_v2<0x1000 | 0x700 | 0x17, kShaCtasPerSmMax>;
     default: return sha512_segments_kernel_v2<0, kShaCtasPerSmMax>;
     }
 }
 
-// Length binning: write the `n` descriptors produced by get(i) into `dst` (pinned memory)
-// sorted by block count, longest first.  Counting sort on min(blocks, 65535); the (few)
-// longer ones are ordered exactly with std::sort.  Large batches are binned by several host
-// threads (per-thread histograms, then a stable scatter).
+// Length binning.  The `n` descriptors produced by get(i) are written to `descs` in the
+// caller's order (a streaming write into pinned memory) and `order` receives their indices
+// sorted by block count, longest first -- the kernel walks `order`, so only 4 bytes per file
+// are scattered on the host.  Counting sort over exactly the bucket range the batch uses
+// (514 buckets for files up to 64 KiB); the few items beyond 65535 blocks are ordered exactly
+// with std::sort.  Multi-million-file shards are binned by several host threads (per-thread
+// histograms, stable scatter).
 struct PlanInfo {
     uint64_t total_blocks = 0, max_blocks = 0;
     bool aligned = true;
@@ -275,28 +301,14 @@ struct PlanInfo {
 };
 
 template <typename Get>
-static void bin_by_length(Get get, size_t n, SegDesc *dst, PlanInfo *info) {
+static void bin_by_length(Get get, size_t n, SegDesc *descs, u32 *order, PlanInfo *info) {
     constexpr uint32_t kCap = 65535;
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const size_t nthreads = n < (1u << 16) ? 1 : std::min<size_t>({(size_t)hw, (size_t)8, n >> 15});
-    std::vector<std::vector<uint32_t>> count(nthreads, std::vector<uint32_t>(kCap + 1, 0));
+    const size_t nthreads = n < (1u << 18) ? 1 : std::min<size_t>({(size_t)hw, (size_t)8, n >> 17});
+    static thread_local std::vector<uint32_t> key;      // min(blocks, kCap) of every item
+    if (key.size() < n) key.resize(n);
     std::vector<PlanInfo> part(nthreads);
     auto range = [&](size_t t) { return std::make_pair(n * t / nthreads, n * (t + 1) / nthreads); };
-    auto pass1 = [&](size_t t) {
-        PlanInfo &pi = part[t];
-        auto [lo, hi] = range(t);
-        uint32_t *cnt = count[t].data();
-        for (size_t i = lo; i < hi; i++) {
-            const SegDesc d = get(i);
-            if (d.len >= kMaxSegBytes && !pi.bad) { pi.bad = 1; pi.bad_index = i; }
-            if ((d.flags & kSegNoFinal) && (d.len & 127) && !pi.bad) { pi.bad = 2; pi.bad_index = i; }
-            pi.aligned = pi.aligned && ((d.off & 15) == 0);
-            const uint64_t nb = seg_blocks(d.len, d.flags);
-            pi.total_blocks += nb;
-            pi.max_blocks = std::max(pi.max_blocks, nb);
-            cnt[(size_t)std::min<uint64_t>(nb, kCap)]++;
-        }
-    };
     auto run_all = [&](auto fn) {
         if (nthreads == 1) { fn((size_t)0); return; }
         std::vector<std::thread> th;
@@ -304,7 +316,22 @@ static void bin_by_length(Get get, size_t n, SegDesc *dst, PlanInfo *info) {
         fn((size_t)0);
         for (auto &x : th) x.join();
     };
-    run_all(pass1);
+    uint32_t *keyp = key.data();
+    run_all([&](size_t t) {
+        PlanInfo &pi = part[t];
+        auto [lo, hi] = range(t);
+        for (size_t i = lo; i < hi; i++) {
+            const SegDesc d = get(i);
+            descs[i] = d;
+            if (d.len >= kMaxSegBytes && !pi.bad) { pi.bad = 1; pi.bad_index = i; }
+            if ((d.flags & kSegNoFinal) && (d.len & 127) && !pi.bad) { pi.bad = 2; pi.bad_index = i; }
+            pi.aligned = pi.aligned && ((d.off & 15) == 0);
+            const uint64_t nb = seg_blocks(d.len, d.flags);
+            pi.total_blocks += nb;
+            pi.max_blocks = std::max(pi.max_blocks, nb);
+            keyp[i] = (uint32_t)std::min<uint64_t>(nb, kCap);
+        }
+    });
     for (const PlanInfo &pi : part) {
         info->total_blocks += pi.total_blocks;
         info->max_blocks = std::max(info->max_blocks, pi.max_blocks);
@@ -312,27 +339,31 @@ static void bin_by_length(Get get, size_t n, SegDesc *dst, PlanInfo *info) {
         if (pi.bad && !info->bad) { info->bad = pi.bad; info->bad_index = pi.bad_index; }
     }
     if (info->bad) return;
-    // descending buckets; inside a bucket thread 0's items first (keeps the sort stable)
-    std::vector<std::vector<size_t>> start(nthreads, std::vector<size_t>(kCap + 1, 0));
-    size_t run = 0, n_long = 0;
-    for (int64_t k = kCap; k >= 0; k--)
-        for (size_t t = 0; t < nthreads; t++) {
-            start[t][(size_t)k] = run;
-            run += count[t][(size_t)k];
-            if (k == kCap) n_long += count[t][(size_t)k];
-        }
-    auto pass2 = [&](size_t t) {
+    const size_t nbuckets = (size_t)std::min<uint64_t>(info->max_blocks, kCap) + 1;
+    std::vector<size_t> start(nthreads * nbuckets, 0);
+    run_all([&](size_t t) {
         auto [lo, hi] = range(t);
-        size_t *st = start[t].data();
-        for (size_t i = lo; i < hi; i++) {
-            const SegDesc d = get(i);
-            dst[st[(size_t)std::min<uint64_t>(seg_blocks(d.len, d.flags), kCap)]++] = d;
+        size_t *cnt = start.data() + t * nbuckets;
+        for (size_t i = lo; i < hi; i++) cnt[keyp[i]]++;
+    });
+    // descending buckets; inside a bucket thread 0's items come first (keeps the sort stable)
+    size_t run = 0, n_long = 0;
+    for (size_t k = nbuckets; k-- > 0;)
+        for (size_t t = 0; t < nthreads; t++) {
+            size_t &c = start[t * nbuckets + k];
+            if (k == kCap) n_long += c;
+            const size_t here = c;
+            c = run;
+            run += here;
         }
-    };
-    run_all(pass2);
+    run_all([&](size_t t) {
+        auto [lo, hi] = range(t);
+        size_t *st = start.data() + t * nbuckets;
+        for (size_t i = lo; i < hi; i++) order[st[keyp[i]]++] = (u32)i;
+    });
     if (n_long > 1)
-        std::sort(dst, dst + n_long, [](const SegDesc &a, const SegDesc &b) {
-            return seg_blocks(a.len, a.flags) > seg_blocks(b.len, b.flags);
+        std::sort(order, order + n_long, [descs](u32 a, u32 b) {
+            return seg_blocks(descs[a].len, descs[a].flags) > seg_blocks(descs[b].len, descs[b].flags);
         });
 }
 
@@ -346,17 +377,21 @@ static int launch_sha512(Device &D, cudaStream_t stream, const uint8_t *d_data, 
     if (n > 0xfffffff0ull) return fail(SNAPGPU_EINVAL, "too many files in one launch (%zu)", n);
     auto &R = rt();
     PlanSlot *slot;
-    int rc = acquire_slot(D, n * sizeof(SegDesc), &slot);
+    const size_t plan_bytes = n * (sizeof(SegDesc) + sizeof(u32));
+    int rc = acquire_slot(D, plan_bytes, &slot);
     if (rc) return rc;
     PlanInfo info;
-    bin_by_length(get, n, static_cast<SegDesc *>(slot->h_buf), &info);
+    const double t_plan = now_ms();
+    SegDesc *h_descs = static_cast<SegDesc *>(slot->h_buf);
+    bin_by_length(get, n, h_descs, reinterpret_cast<u32 *>(h_descs + n), &info);
+    if (trace_on()) fprintf(stderr, "[snapgpu] length binning of %zu items: %.3f ms\n", n, now_ms() - t_plan);
     if (info.bad == 1) return fail(SNAPGPU_EINVAL, "file %zu too large", info.bad_index);
     if (info.bad == 2)
         return fail(SNAPGPU_EINVAL, "non-final segment %zu is not a multiple of 128 bytes", info.bad_index);
     const bool aligned = info.aligned && ((uintptr_t)d_data & 15) == 0;
     const uint64_t total_blocks = info.total_blocks, max_blocks = info.max_blocks;
 
-    SG_CUDA(cudaMemcpyAsync(slot->d_buf, slot->h_buf, n * sizeof(SegDesc), cudaMemcpyHostToDevice, D.copy_stream));
+    SG_CUDA(cudaMemcpyAsync(slot->d_buf, slot->h_buf, plan_bytes, cudaMemcpyHostToDevice, D.copy_stream));
     SG_CUDA(cudaMemsetAsync(slot->d_counter, 0, sizeof(u32), D.copy_stream));
     SG_CUDA(cudaEventRecord(slot->uploaded, D.copy_stream));
     SG_CUDA(cudaStreamWaitEvent(stream, slot->uploaded, 0));
@@ -383,7 +418,8 @@ static int launch_sha512(Device &D, cudaStream_t stream, const uint8_t *d_data, 
         if (tl->pending) harvest_timings(tl, 1, D.sha_ms_sum, D.sha_ms_n, D.sha_ms_last, true);
         SG_CUDA(cudaEventRecord(tl->beg, stream));
     }
-    k<<<grid, kShaThreads, 0, stream>>>(d_data, static_cast<const SegDesc *>(slot->d_buf), (u32)n, d_digests,
+    const SegDesc *d_descs = static_cast<const SegDesc *>(slot->d_buf);
+    k<<<grid, kShaThreads, 0, stream>>>(d_data, d_descs, reinterpret_cast<const u32 *>(d_descs + n), (u32)n, d_digests,
                                          slot->d_counter, 1u);
     SG_CUDA(cudaGetLastError());
     if (tl) {
@@ -512,74 +548,101 @@ struct ChunkPlan {
     const WorkItem &item(const Chunk &c, size_t i) const { return (c.in_pieces ? pieces.data() : base)[c.first + i]; }
 };
 
-// Cut the shard's item list into chunks that fit `cap` bytes of staging.  Items longer than
-// the staging buffer are split into continuation segments (SHA) or sub-ranges (cmp).  Items
-// that fit are referenced in place (no copy).
-static void build_chunks(const std::vector<WorkItem> &in, size_t cap, bool is_sha, ChunkPlan &plan) {
-    const uint64_t usable = (cap - 64) & ~(uint64_t)127;
-    plan.chunks.clear();
-    plan.pieces.clear();
-    plan.base = in.data();
-    Chunk cur{0, 0, false, 0, 0, false, true};
-    auto close = [&](size_t next_first) {
-        if (cur.count) plan.chunks.push_back(cur);
-        cur = Chunk{next_first, 0, false, 0, 0, false, true};
-    };
-    for (size_t k = 0; k < in.size(); k++) {
-        const WorkItem &w = in[k];
-        if (w.len + 16 > usable) {
-            close(k + 1);
-            uint64_t done = 0;
-            while (done < w.len) {
-                uint64_t piece = std::min<uint64_t>(w.len - done, usable - 128);
-                piece = (done + piece < w.len) ? (piece & ~(uint64_t)127) : piece;
-                WorkItem s = w;
-                s.off = w.off + done;
-                s.len = piece;
-                s.prefix = w.prefix + done;
-                if (is_sha) {
-                    s.flags = w.flags;
-                    if (done > 0) s.flags |= kSegContinue;
-                    if (done + piece < w.len) s.flags |= kSegNoFinal;
-                }
-                plan.pieces.push_back(s);
-                const uint64_t begin = s.off & ~(uint64_t)15;
-                plan.chunks.push_back(Chunk{plan.pieces.size() - 1, 1, true, begin, s.off + s.len,
-                                            (s.flags & kSegContinue) != 0, true});
-                done += piece;
-            }
-            continue;
-        }
-        const uint64_t begin = w.off & ~(uint64_t)15;
-        const uint64_t end = w.off + w.len;
-        const bool fits = cur.count > 0 && cur.count < kMaxChunkItems && begin >= cur.span_begin &&
-                          end - cur.span_begin <= usable && (w.off <= cur.span_end + (1u << 20));
-        if (!fits) {
-            close(k);
-            cur.span_begin = begin;
-            cur.span_end = end;
-        } else if (w.user_index != in[k - 1].user_index + 1) {
-            cur.dense_out = false;
-        }
-        cur.span_end = std::max(cur.span_end, end);
-        cur.count++;
-        cur.needs_state_in = cur.needs_state_in || (is_sha && (w.flags & kSegContinue));
+// Cuts a shard's item list into chunks that fit the staging buffer, one chunk per next() call,
+// so that the first host-to-device copy starts after a few thousand items have been looked at
+// instead of after the whole list.  Items longer than the staging buffer are split into
+// continuation segments (SHA) or sub-ranges (cmp); items that fit are referenced in place.
+struct ChunkStream {
+    const std::vector<WorkItem> &in;
+    const bool is_sha;
+    ChunkPlan &plan;
+    size_t k = 0;             // next item of `in`
+    uint64_t piece_done = 0;  // bytes of in[k] already emitted as pieces (only while splitting)
+    bool splitting = false;
+
+    ChunkStream(const std::vector<WorkItem> &items, bool sha, ChunkPlan &p) : in(items), is_sha(sha), plan(p) {
+        plan.chunks.clear();
+        plan.pieces.clear();
+        plan.base = in.data();
     }
-    close(in.size());
+
+    static uint64_t usable_of(size_t cap) { return (cap - 64) & ~(uint64_t)127; }
+
+    // cap_now: bytes this chunk should stay under (the pipeline starts with small chunks);
+    // cap_max: the staging buffer.  An item that does not fit cap_now but fits cap_max gets a
+    // cap_max chunk; an item that does not fit cap_max is split.
+    bool next(size_t cap_now, size_t cap_max, Chunk *out) {
+        const uint64_t usable_max = usable_of(cap_max);
+        if (!splitting) {
+            if (k >= in.size()) return false;
+            if (in[k].len + 16 > usable_max) {
+                splitting = true;
+                piece_done = 0;
+            }
+        }
+        if (splitting) {
+            const WorkItem &w = in[k];
+            uint64_t piece = std::min<uint64_t>(w.len - piece_done, usable_max - 128);
+            piece = (piece_done + piece < w.len) ? (piece & ~(uint64_t)127) : piece;
+            WorkItem s = w;
+            s.off = w.off + piece_done;
+            s.len = piece;
+            s.prefix = w.prefix + piece_done;
+            if (is_sha) {
+                s.flags = w.flags;
+                if (piece_done > 0) s.flags |= kSegContinue;
+                if (piece_done + piece < w.len) s.flags |= kSegNoFinal;
+            }
+            plan.pieces.push_back(s);
+            *out = Chunk{plan.pieces.size() - 1, 1, true, s.off & ~(uint64_t)15, s.off + s.len,
+                         (s.flags & kSegContinue) != 0, true};
+            piece_done += piece;
+            if (piece_done >= w.len) {
+                splitting = false;
+                k++;
+            }
+            plan.chunks.push_back(*out);
+            return true;
+        }
+        const uint64_t usable = in[k].len + 16 > usable_of(cap_now) ? usable_max : usable_of(cap_now);
+        Chunk cur{k, 0, false, in[k].off & ~(uint64_t)15, in[k].off + in[k].len, false, true};
+        for (; k < in.size(); k++) {
+            const WorkItem &w = in[k];
+            const uint64_t begin = w.off & ~(uint64_t)15;
+            const uint64_t end = w.off + w.len;
+            if (cur.count) {
+                const bool fits = w.len + 16 <= usable_max && cur.count < kMaxChunkItems && begin >= cur.span_begin &&
+                                  end - cur.span_begin <= usable && w.off <= cur.span_end + (1u << 20);
+                if (!fits) break;
+                if (w.user_index != in[k - 1].user_index + 1) cur.dense_out = false;
+            }
+            cur.span_end = std::max(cur.span_end, end);
+            cur.count++;
+            cur.needs_state_in = cur.needs_state_in || (is_sha && (w.flags & kSegContinue));
+        }
+        *out = cur;
+        plan.chunks.push_back(cur);
+        return true;
+    }
+};
+
+// All chunks of a list for one fixed staging size (test hook).
+static void build_chunks(const std::vector<WorkItem> &in, size_t cap, bool is_sha, ChunkPlan &plan) {
+    ChunkStream cs(in, is_sha, plan);
+    Chunk c;
+    while (cs.next(cap, cap, &c)) {}
+}
+
+// The host pipeline ramps its chunk size: a small first chunk gets the copy engine going
+// while the rest of the list is still being cut, later chunks are large because every launch
+// costs at least the serial chain of its longest file (~2 ms for 64 KiB).
+static size_t ramp_cap(size_t chunk_index, size_t cap_max) {
+    const size_t first = 64u << 20;
+    const size_t want = chunk_index >= 8 ? cap_max : (first << (2 * chunk_index));
+    return std::min(want, cap_max);
 }
 
 // Runs one device's shard of a host-buffer SHA-512 batch.  digests: caller's n*64 array.
-static double now_ms() {
-    struct timespec ts;
-    clock_gettime(CLOCK_MONOTONIC, &ts);
-    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
-}
-
-static bool trace_on() {
-    static const bool on = getenv("SNAPGPU_TRACE") != nullptr;
-    return on;
-}
-
 static int sha512_shard(Device &D, const uint8_t *data, const std::vector<WorkItem> &shard, uint8_t *digests) {
     if (shard.empty()) return 0;
     std::lock_guard<std::mutex> lock(D.mu);
@@ -588,22 +651,17 @@ static int sha512_shard(Device &D, const uint8_t *data, const std::vector<WorkIt
     const double t_begin = now_ms();
     const size_t cap = staging_bytes();
     ChunkPlan plan;
-    build_chunks(shard, cap, true, plan);
-    const std::vector<Chunk> &chunks = plan.chunks;
-    size_t max_items = 0;
-    for (auto &c : chunks) max_items = std::max(max_items, c.count);
-    int rc = ensure_staging(D, cap, max_items * 64);
+    ChunkStream stream(shard, true, plan);
+    const std::vector<Chunk> &chunks = plan.chunks;      // grows as the stream is consumed
+    int rc = ensure_staging(D, cap, std::min(shard.size(), kMaxChunkItems) * 64);
     if (rc) return rc;
-    if (trace_on())
-        fprintf(stderr, "[snapgpu] dev %d: %zu items -> %zu chunks, chunking %.2f ms\n", D.ordinal, shard.size(),
-                chunks.size(), now_ms() - t_begin);
 
     const size_t phase = (uintptr_t)data & 15;   // keep (data + off) mod 16 on the device
     int scatter_pending[2] = {-1, -1};            // chunk index whose digests wait in h_out[b]
     auto scatter = [&](int b) -> int {
         if (scatter_pending[b] < 0) return 0;
         SG_CUDA(cudaEventSynchronize(D.ev_done[b]));
-        const Chunk &c = chunks[(size_t)scatter_pending[b]];
+        const Chunk c = chunks[(size_t)scatter_pending[b]];
         if (c.dense_out) {
             memcpy(digests + 64 * plan.item(c, 0).user_index, D.h_out[b], 64 * c.count);
         } else {
@@ -614,8 +672,8 @@ static int sha512_shard(Device &D, const uint8_t *data, const std::vector<WorkIt
         return 0;
     };
 
-    for (size_t ci = 0; ci < chunks.size(); ci++) {
-        const Chunk &c = chunks[ci];
+    Chunk c;
+    for (size_t ci = 0; stream.next(ramp_cap(ci, cap), cap, &c); ci++) {
         const int b = (int)(ci & 1);
         const double t_chunk = now_ms();
         if ((rc = scatter(b))) return rc;        // buffer b (stage, out) is free again
@@ -667,11 +725,9 @@ static int cmp_shard(Device &D, const uint8_t *a, const uint8_t *b_host, const s
     const size_t cap = staging_bytes();
     const size_t half = (cap / 2) & ~(size_t)255;
     ChunkPlan plan;
-    build_chunks(shard, half, false, plan);
+    ChunkStream stream(shard, false, plan);
     const std::vector<Chunk> &chunks = plan.chunks;
-    size_t max_items = 0;
-    for (auto &c : chunks) max_items = std::max(max_items, c.count);
-    int rc = ensure_staging(D, cap, max_items);
+    int rc = ensure_staging(D, cap, std::min(shard.size(), kMaxChunkItems));
     if (rc) return rc;
     // the two streams may sit at different phases mod 16; the kernel then takes the byte path
     const size_t pa = (uintptr_t)a & 15, pb = (uintptr_t)b_host & 15;
@@ -680,14 +736,14 @@ static int cmp_shard(Device &D, const uint8_t *a, const uint8_t *b_host, const s
     auto gather = [&](int b) -> int {
         if (pending[b] < 0) return 0;
         SG_CUDA(cudaEventSynchronize(D.ev_done[b]));
-        const Chunk &c = chunks[(size_t)pending[b]];
+        const Chunk c = chunks[(size_t)pending[b]];
         for (size_t i = 0; i < c.count; i++)
             if (D.h_out[b][i] == 0) equal[plan.item(c, i).user_index] = 0;
         pending[b] = -1;
         return 0;
     };
-    for (size_t ci = 0; ci < chunks.size(); ci++) {
-        const Chunk &c = chunks[ci];
+    Chunk c;
+    for (size_t ci = 0; stream.next(ramp_cap(ci, half), half, &c); ci++) {
         const int b = (int)(ci & 1);
         if ((rc = gather(b))) return rc;
         // host-side early-out: a pair already known to differ is not copied again
@@ -952,7 +1008,7 @@ int snapgpu_cmp_batch(const uint8_t *a, const uint8_t *b, const uint64_t *offset
 
 int snapgpu_sha512_batch_device(int dev, const void *d_data, const uint64_t *offsets, const uint64_t *lengths,
                                 size_t nfiles, void *d_digests, void *stream) {
-    Device *D;
+    Device *D = nullptr;
     int rc = get_device(dev, &D);
     if (rc) return rc;
     if (nfiles == 0) return 0;
@@ -967,7 +1023,7 @@ int snapgpu_sha512_batch_device(int dev, const void *d_data, const uint64_t *off
 
 int snapgpu_cmp_batch_device(int dev, const void *d_a, const void *d_b, const uint64_t *offsets,
                              const uint64_t *lengths, size_t npairs, void *d_equal, void *stream) {
-    Device *D;
+    Device *D = nullptr;
     int rc = get_device(dev, &D);
     if (rc) return rc;
     if (npairs == 0) return 0;
@@ -982,7 +1038,7 @@ int snapgpu_cmp_batch_device(int dev, const void *d_a, const void *d_b, const ui
 
 int snapgpu_synth_fill_device(int dev, void *d_data, const uint64_t *offsets, const uint64_t *lengths, size_t nfiles,
                               uint64_t first_index, uint64_t seed, void *stream) {
-    Device *D;
+    Device *D = nullptr;
     int rc = get_device(dev, &D);
     if (rc) return rc;
     if (nfiles == 0) return 0;
@@ -1060,11 +1116,10 @@ void snapgpu_reset_stats(void) {
 // Launch order the length binning produces: order[k] = index of the k-th file of the plan.
 int snapgpu_test_plan_order(const uint64_t *lengths, size_t n, uint32_t *order) {
     if (!lengths || !order) return fail(SNAPGPU_EINVAL, "null argument");
-    std::vector<SegDesc> dst(n);
+    std::vector<SegDesc> descs(n);
     PlanInfo info;
     bin_by_length([lengths](size_t i) { return SegDesc{0, std::min<uint64_t>(lengths[i], kMaxSegBytes - 1), 0, (u32)i, 0}; },
-                  n, dst.data(), &info);
-    for (size_t i = 0; i < n; i++) order[i] = dst[i].out_idx;
+                  n, descs.data(), order, &info);
     return 0;
 }
 
@@ -1107,7 +1162,7 @@ typedef void (*ProbeKernel)(uint32_t *, int, uint32_t, uint32_t, unsigned long l
 
 int snapgpu_pipe_microbench(int dev, int kind, int warps_per_sm, double *inst_per_clk_per_sm, double *elapsed_ms,
                             double *sm_clock_mhz) {
-    Device *D;
+    Device *D = nullptr;
     int rc = get_device(dev, &D);
     if (rc) return rc;
     static const ProbeKernel table[kProbeCount] = {

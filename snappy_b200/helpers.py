@@ -64,7 +64,7 @@ def sha512_batch(data: np.ndarray, offsets, lengths) -> np.ndarray:
     data = np.ascontiguousarray(data, dtype=np.uint8)
     offsets, lengths = _u64(offsets), _u64(lengths)
     n = len(offsets)
-    out = np.zeros((n, 64), dtype=np.uint8)
+    out = np.empty((n, 64), dtype=np.uint8)
     N.check(N.lib().snapgpu_sha512_batch(data.ctypes.data, offsets.ctypes.data, lengths.ctypes.data, n,
                                           out.ctypes.data))
     return out

@@ -59,7 +59,7 @@ def test_every_length_0_to_300(gpu, oracle):
         assert got[i].tobytes() == hashlib.sha512(data[int(off[i]):int(off[i] + ln[i])].tobytes()).digest()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", list(range(12)))
 @pytest.mark.parametrize("warps", [0, 1, 2, 3])
 def test_kernel_variants_bit_exact(gpu, oracle, variant, warps):
     from snappy_b200 import helpers
