@@ -158,13 +158,15 @@ void snapgpu_reset_stats(void);
 int snapgpu_pipe_microbench(int dev, int kind, int warps_per_sm, double *inst_per_clk_per_sm,
                             double *elapsed_ms, double *sm_clock_mhz);
 
-/* ---- test hooks: host logic only, usable without a GPU (see tests/) -------------------- */
+/* ---- test hooks (see tests/) ------------------------------------------------------------ */
+/* host logic only, usable without a GPU */
 int snapgpu_test_yaml_from_digests(const char *build_dir, const uint8_t *digests, size_t ndigests,
                                    char **out, size_t *out_len);
-int snapgpu_test_plan_order(const uint64_t *lengths, size_t n, uint32_t *order);
 int snapgpu_test_shard(const uint64_t *weights, size_t n, int ndev, int *device_of);
 long long snapgpu_test_chunks(const uint64_t *offsets, const uint64_t *lengths, size_t n,
                               uint64_t cap, int is_sha, uint64_t *rows, size_t max_rows);
+/* the order the device-side length binning gives files of these lengths (needs a GPU) */
+int snapgpu_test_plan_order(const uint64_t *lengths, size_t n, uint32_t *order);
 
 #ifdef __cplusplus
 }

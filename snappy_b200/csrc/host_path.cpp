@@ -31,9 +31,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "runtime.hpp"
@@ -48,17 +51,21 @@ namespace {
 
 struct Staging {
     std::mutex mu;
-    uint8_t *buf = nullptr;
+    uint8_t *buf = nullptr;      // compare path: one buffer, two halves
     size_t cap = 0;
+    uint8_t *ring[2] = {nullptr, nullptr};   // hashing path: one batch is packed while the other is on the GPU
+    size_t ring_cap = 0;
 };
 Staging &staging() {
     static Staging s;
     return s;
 }
 
-// The drop-ins pack files into pinned memory of this size per batch; it never exceeds the
-// device-side staging buffer, so one batch is one H2D span.
+// The compare drop-ins pack files into pinned memory of this size per batch.
 size_t host_staging_bytes() { return std::min<size_t>(staging_bytes(), (size_t)64 << 20); }
+// The hashing drop-ins pack batches of this size (two pinned buffers); it never exceeds the
+// device-side staging buffer, so one batch is at most a few H2D spans.
+size_t host_ring_bytes() { return std::min<size_t>(staging_bytes(), (size_t)256 << 20); }
 
 int staging_acquire(Staging &s, size_t want) {
     if (s.cap >= want) return 0;
@@ -66,6 +73,20 @@ int staging_acquire(Staging &s, size_t want) {
     s.buf = static_cast<uint8_t *>(snapgpu_alloc_pinned(want));
     s.cap = s.buf ? want : 0;
     return s.buf ? 0 : SNAPGPU_ECUDA;
+}
+
+int ring_acquire(Staging &s, size_t want) {
+    if (s.ring_cap >= want) return 0;
+    for (auto &r : s.ring) {
+        if (r) snapgpu_free_pinned(r);
+        r = static_cast<uint8_t *>(snapgpu_alloc_pinned(want));
+        if (!r) {
+            s.ring_cap = 0;
+            return SNAPGPU_ECUDA;
+        }
+    }
+    s.ring_cap = want;
+    return 0;
 }
 
 std::string go_path_error(const char *op, const std::string &path, int err) {
@@ -90,86 +111,214 @@ ssize_t read_full(int fd, uint8_t *dst, size_t want) {
 constexpr size_t kAlign = 16;
 inline size_t align_up(size_t x) { return (x + kAlign - 1) & ~(kAlign - 1); }
 
-// Hash every file of `paths` (in order).  digests: paths.size()*64.  On the first I/O error
-// returns SNAPGPU_EIO with a Go-style message, like the reference aborts its walk.
-int hash_files(const std::vector<std::string> &paths, std::vector<uint8_t> &digests) {
+// One file streamed through `buf` in pieces that are multiples of 128 bytes: the io.Copy loop
+// of helpers.Sha512sum (helpers/helpers.go:195-196) with the chaining value carried between
+// GPU calls.  Used for files larger than a batch and for files that grew while being packed.
+int stream_file(const std::string &path, uint8_t *buf, size_t cap, uint8_t digest[64]) {
+    int fd = ::open(path.c_str(), O_RDONLY | O_CLOEXEC);
+    if (fd < 0) return fail(SNAPGPU_EIO, "%s", go_path_error("open", path, errno).c_str());
+    uint64_t prefix = 0;
+    size_t len = 0;
+    bool first = true;
+    int rc = 0;
+    for (;;) {
+        ssize_t r = read_full(fd, buf + len, cap - len);
+        if (r < 0) {
+            int e = errno;
+            ::close(fd);
+            return fail(SNAPGPU_EIO, "%s", go_path_error("read", path, e).c_str());
+        }
+        len += (size_t)r;
+        const bool eof = len < cap;
+        const size_t take = eof ? len : (len & ~(size_t)127);
+        HostSeg s{0, take, prefix, (first ? 0u : kHostSegContinue) | (eof ? 0u : kHostSegNoFinal)};
+        if ((rc = sha512_host_segments(buf, &s, 1, digest))) break;
+        if (eof) break;
+        first = false;
+        prefix += take;
+        memmove(buf, buf + take, len - take);
+        len -= take;
+    }
+    ::close(fd);
+    return rc;
+}
+
+// What the packer did with one file of a batch.
+struct PackedFile {
+    size_t index;          // position in `paths`
+    uint64_t off;          // slot in the batch buffer (16-byte aligned)
+    uint64_t planned;      // bytes reserved (size at stat time)
+    uint64_t len = 0;      // bytes read
+    int err = 0;           // errno of a failed open/read
+    const char *op = "";   // "open" / "read"
+    bool grew = false;     // more bytes than planned: re-hashed through stream_file
+};
+
+void pack_one(const std::string &path, uint8_t *buf, PackedFile &f) {
+    int fd = ::open(path.c_str(), O_RDONLY | O_CLOEXEC);
+    if (fd < 0) {
+        f.err = errno;
+        f.op = "open";
+        return;
+    }
+    ssize_t r = f.planned ? read_full(fd, buf + f.off, f.planned) : 0;
+    if (r < 0) {
+        f.err = errno;
+        f.op = "read";
+    } else {
+        f.len = (size_t)r;
+        if ((uint64_t)r == f.planned) {            // io.Copy reads to EOF, not to st_size: is there more?
+            uint8_t probe;
+            ssize_t more;
+            do more = ::read(fd, &probe, 1); while (more < 0 && errno == EINTR);
+            if (more < 0) {
+                f.err = errno;
+                f.op = "read";
+            } else if (more > 0) {
+                f.grew = true;
+            }
+        }
+    }
+    ::close(fd);
+}
+
+unsigned packer_threads(size_t nfiles) {
+    static const unsigned env = [] {
+        const char *e = getenv("SNAPGPU_PACK_THREADS");
+        return e ? (unsigned)atoi(e) : 0u;
+    }();
+    unsigned t = env ? env : std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    return (unsigned)std::min<size_t>(t, std::max<size_t>(1, nfiles / 16));
+}
+
+// Hash every file of `paths` (in order).  digests: paths.size()*64.  On the first I/O error (in
+// list order) returns SNAPGPU_EIO with a Go-style message, like the reference aborts its walk.
+//
+// The reference reads and hashes one file at a time (snappy/build.go:240-247).  Here the list
+// is cut into batches of up to host_ring_bytes(); a batch's files are read by several host
+// threads straight into their 16-byte aligned slots of a pinned buffer, and while the GPU
+// hashes batch k (one sha512_host_segments call) the threads already pack batch k+1 into the
+// other buffer.  size_hint (optional) carries the walk's lstat sizes so files are not stat'ed twice.
+int hash_files(const std::vector<std::string> &paths, std::vector<uint8_t> &digests,
+               const std::vector<int64_t> *size_hint = nullptr) {
     digests.assign(paths.size() * 64, 0);
     if (paths.empty()) return 0;
     int rc = ensure_init();
     if (rc) return rc;
     Staging &S = staging();
     std::lock_guard<std::mutex> lock(S.mu);
-    const size_t cap = host_staging_bytes();
-    if ((rc = staging_acquire(S, cap))) return rc;
+    const size_t n = paths.size();
+    const unsigned nthreads = packer_threads(n);
 
-    std::vector<HostSeg> segs;          // segments of the batch being packed
-    std::vector<size_t> seg_file;       // file index per segment
-    std::vector<uint8_t> out;
-    size_t used = 0;
-    auto flush = [&]() -> int {
-        if (segs.empty()) return 0;
-        out.assign(segs.size() * 64, 0);
-        int r = sha512_host_segments(S.buf, segs.data(), segs.size(), out.data());
-        if (r) return r;
-        for (size_t i = 0; i < segs.size(); i++) memcpy(&digests[64 * seg_file[i]], &out[64 * i], 64);
-        segs.clear();
-        seg_file.clear();
-        used = 0;
-        return 0;
+    auto parallel_for = [&](size_t count, const std::function<void(size_t)> &fn) {
+        if (nthreads <= 1 || count < 32) {
+            for (size_t i = 0; i < count; i++) fn(i);
+            return;
+        }
+        std::atomic<size_t> next{0};
+        auto work = [&]() {
+            for (;;) {
+                const size_t i0 = next.fetch_add(8);
+                if (i0 >= count) break;
+                for (size_t i = i0; i < std::min(count, i0 + 8); i++) fn(i);
+            }
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nthreads; t++) th.emplace_back(work);
+        work();
+        for (auto &x : th) x.join();
     };
 
-    for (size_t fi = 0; fi < paths.size(); fi++) {
-        int fd = ::open(paths[fi].c_str(), O_RDONLY | O_CLOEXEC);
-        if (fd < 0) return fail(SNAPGPU_EIO, "%s", go_path_error("open", paths[fi], errno).c_str());
-        size_t start = align_up(used);
-        if (cap - start < (64u << 10)) {             // keep at least one io.Copy buffer of room
-            if ((rc = flush())) { ::close(fd); return rc; }
-            start = 0;
+    // sizes at plan time (a file that is missing plans 0 bytes; its open fails in pack_one)
+    std::vector<uint64_t> planned(n, 0);
+    parallel_for(n, [&](size_t i) {
+        if (size_hint && (*size_hint)[i] >= 0) {
+            planned[i] = (uint64_t)(*size_hint)[i];
+            return;
         }
-        // read until EOF (io.Copy), not "st_size bytes"
-        size_t len = 0;
-        bool streamed = false;
-        uint64_t prefix = 0;
-        uint8_t state[64];
-        for (;;) {
-            const size_t room = cap - start - len;
-            ssize_t r = read_full(fd, S.buf + start + len, room);
-            if (r < 0) {
-                int e = errno;
-                ::close(fd);
-                return fail(SNAPGPU_EIO, "%s", go_path_error("read", paths[fi], e).c_str());
-            }
-            len += (size_t)r;
-            if ((size_t)r < room) break;             // EOF
-            // the buffer is full and the file goes on: hash what is batched, then stream
-            // this file through the buffer in multiples of 128 bytes
-            if (!segs.empty() || start != 0) {
-                if ((rc = flush())) { ::close(fd); return rc; }
-                memmove(S.buf, S.buf + start, len);
-                start = 0;
-                continue;
-            }
-            const size_t whole = len & ~(size_t)127;
-            HostSeg s{0, whole, prefix, kHostSegNoFinal | (streamed ? kHostSegContinue : 0u)};
-            if ((rc = sha512_host_segments(S.buf, &s, 1, state))) { ::close(fd); return rc; }
-            streamed = true;
-            prefix += whole;
-            memmove(S.buf, S.buf + whole, len - whole);
-            len -= whole;
+        struct stat st;
+        if (stat(paths[i].c_str(), &st) == 0 && S_ISREG(st.st_mode)) planned[i] = (uint64_t)st.st_size;
+    });
+
+    // pinned ring sized to the job (pinning memory costs ~0.4 ms per MiB): 16 MiB .. host_ring_bytes()
+    uint64_t total = 0;
+    for (size_t i = 0; i < n; i++) total += align_up(planned[i]);
+    size_t want = (size_t)16 << 20;
+    while (want < total + 4096 && want < host_ring_bytes()) want <<= 1;
+    want = std::min(want, std::max(host_ring_bytes(), (size_t)1 << 20));
+    if ((rc = ring_acquire(S, want))) return rc;
+    const size_t cap = S.ring_cap;
+
+    // batches: consecutive files whose slots fit one buffer; a file that does not fit alone is
+    // a batch of its own and is streamed
+    struct Batch { size_t first, count; bool streamed; };
+    std::vector<Batch> batches;
+    const size_t room = cap - 256;
+    for (size_t i = 0; i < n;) {
+        if (planned[i] > room) {
+            batches.push_back(Batch{i, 1, true});
+            i++;
+            continue;
         }
-        ::close(fd);
-        if (streamed) {
-            HostSeg s{0, len, prefix, kHostSegContinue};
-            if ((rc = sha512_host_segments(S.buf, &s, 1, state))) return rc;
-            memcpy(&digests[64 * fi], state, 64);
-            used = 0;
-        } else {
-            segs.push_back(HostSeg{start, len, 0, 0});
-            seg_file.push_back(fi);
-            used = start + len;
+        size_t used = 0, j = i;
+        while (j < n && planned[j] <= room && align_up(used) + planned[j] <= room) {
+            used = align_up(used) + planned[j];
+            j++;
         }
+        batches.push_back(Batch{i, j - i, false});
+        i = j;
     }
-    return flush();
+
+    std::vector<PackedFile> packed[2];
+    auto fill = [&](size_t bi) {
+        const Batch &B = batches[bi];
+        std::vector<PackedFile> &pf = packed[bi & 1];
+        pf.clear();
+        if (B.streamed) return;
+        size_t used = 0;
+        for (size_t k = 0; k < B.count; k++) {
+            used = align_up(used);
+            PackedFile f;
+            f.index = B.first + k;
+            f.off = used;
+            f.planned = planned[f.index];
+            pf.push_back(f);
+            used += f.planned;
+        }
+        uint8_t *buf = S.ring[bi & 1];
+        parallel_for(pf.size(), [&](size_t k) { pack_one(paths[pf[k].index], buf, pf[k]); });
+    };
+
+    std::vector<HostSeg> segs;
+    std::vector<uint8_t> out;
+    std::thread prefetch;
+    fill(0);
+    for (size_t bi = 0; bi < batches.size() && !rc; bi++) {
+        if (prefetch.joinable()) prefetch.join();             // batch bi is packed
+        if (bi + 1 < batches.size()) prefetch = std::thread(fill, bi + 1);
+        const Batch &B = batches[bi];
+        uint8_t *buf = S.ring[bi & 1];
+        if (B.streamed) {
+            rc = stream_file(paths[B.first], buf, cap, &digests[64 * B.first]);
+            continue;
+        }
+        std::vector<PackedFile> &pf = packed[bi & 1];
+        for (const PackedFile &f : pf)
+            if (f.err) {                                      // first failing file in list order
+                rc = fail(SNAPGPU_EIO, "%s", go_path_error(f.op, paths[f.index], f.err).c_str());
+                break;
+            }
+        if (rc) break;
+        segs.clear();
+        for (const PackedFile &f : pf) segs.push_back(HostSeg{f.off, f.grew ? 0 : f.len, 0, 0});
+        out.resize(segs.size() * 64);
+        if ((rc = sha512_host_segments(buf, segs.data(), segs.size(), out.data()))) break;
+        for (size_t k = 0; k < pf.size(); k++) memcpy(&digests[64 * pf[k].index], &out[64 * k], 64);
+        for (const PackedFile &f : pf)                        // rare: the file grew after its stat
+            if (f.grew && (rc = stream_file(paths[f.index], buf, cap, &digests[64 * f.index]))) break;
+    }
+    if (prefetch.joinable()) prefetch.join();
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -889,11 +1038,16 @@ int build_hashes_yaml(const std::string &build_dir, const std::string &data_tar,
     int rc = collect_tree(build_dir, entries);
     if (rc) return rc;
     std::vector<std::string> paths;
+    std::vector<int64_t> sizes;
     paths.push_back(data_tar);                           // archive-sha512 first (build.go:222)
+    sizes.push_back(-1);
     for (const TreeEntry &e : entries)
-        if (e.regular) paths.push_back(e.path);
+        if (e.regular) {
+            paths.push_back(e.path);
+            sizes.push_back((int64_t)e.size);            // the walk's lstat: no second stat
+        }
     std::vector<uint8_t> digests;
-    if ((rc = hash_files(paths, digests))) return rc;
+    if ((rc = hash_files(paths, digests, &sizes))) return rc;
     return emit_hashes_yaml(entries, digests.data(), paths.size(), yaml);
 }
 

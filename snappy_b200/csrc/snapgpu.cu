@@ -19,6 +19,7 @@
 
 #include "cmp_kernels.cuh"
 #include "pipe_microbench.cuh"
+#include "plan_kernels.cuh"
 #include "runtime.hpp"
 #include "sha512_kernels.cuh"
 
@@ -254,19 +255,20 @@ static bool trace_on() {
 typedef void (*ShaKernel)(const uint8_t *, const SegDesc *, const u32 *, u32, uint8_t *, u32 *, u32);
 
 constexpr int kShaCtasPerSmMax = 3;   // 168 registers per thread: no spills with the one-block-ahead prefetch
-constexpr int kShaVariants = 12;
+constexpr int kShaVariants = 6;
 
 // variant 0 (default): compact 16-round loop, cp.async staging through shared memory, plain
-//            64-bit adds (ptxas pairs them into 3-input IADD3 / IADD3.X)
-// variant 1: same, every add split IADD3 (low half, ALU) / IMAD.X (high half, FMA)
-// variant 2: 80 rounds fully unrolled, register prefetch, ALU adds          (round-1 first cut)
-// variant 3: fully unrolled, every add as IMAD.WIDE + IMAD on the FMA pipe  (measured slower)
+//            64-bit adds (ptxas pairs them into 3-input IADD3 / IADD3.X and already sends the
+//            high half of every 2-input add to the FMA pipe as IMAD.X)
+// variant 1: same, every add split IADD3 (low half, ALU) / IMAD.X (high half, FMA): loses the
+//            3-input merging, so the ALU count does not drop                 (measured 3-5 % slower)
+// variant 2: 80 rounds fully unrolled, register prefetch, ALU adds            (round-1 first cut)
+// variant 3: fully unrolled, every add as IMAD.WIDE + IMAD on the FMA pipe
 // variant 4: fully unrolled, round adds on FMA, schedule adds on ALU
-// variants 5..11: compact loop with a per-add choice of pipe (sha512_core.cuh, kAddMode 0x1000|...)
-//            5: every add on FMA         6: round adds on FMA        7: schedule adds on FMA
-//            8: off-chain round adds (W+K, h+KW, Sigma0+Maj) + schedule on FMA
-//            9: off-chain round adds on FMA      10: W+K and schedule sums on FMA
-//           11: W+K, h+KW, Sigma1+Ch, Sigma0+Maj and schedule on FMA (state adds stay on ALU)
+// variant 5: compact loop, every add as IMAD.WIDE + IMAD on the FMA pipe.  ALU instructions per
+//            block drop from 3425 to ~2700, yet it measured 19-29 % slower (and every partial mix
+//            between 0 and 5 fell in between, profiles/r01_sweep_fma_add_variants.txt): IMAD.WIDE
+//            issues at a quarter of the ALU rate and stalls the issue port it shares.
 // Input that is not 16-byte aligned always takes the register-load kernel (any alignment).
 static ShaKernel sha_kernel_for(int variant, bool aligned) {
     if (!aligned) return sha512_segments_kernel<0x00, 0x0, false, kShaCtasPerSmMax>;
@@ -276,23 +278,13 @@ static ShaKernel sha_kernel_for(int variant, bool aligned) {
     case 3: return sha512_segments_kernel<0x7f, 0x7, true, kShaCtasPerSmMax>;
     case 4: return sha512_segments_kernel<0x7f, 0x0, true, kShaCtasPerSmMax>;
     case 5: return sha512_segments_kernel_v2<0x1000 | 0x700 | 0x7f, kShaCtasPerSmMax>;
-    case 6: return sha512_segments_kernel_v2<0x1000 | 0x000 | 0x7f, kShaCtasPerSmMax>;
-    case 7: return sha512_segments_kernel_v2<0x1000 | 0x700 | 0x00, kShaCtasPerSmMax>;
-    case 8: return sha512_segments_kernel_v2<0x1000 | 0x700 | 0x13, kShaCtasPerSmMax>;
-    case 9: return sha512_segments_kernel_v2<0x1000 | 0x000 | 0x13, kShaCtasPerSmMax>;
-    case 10: return sha512_segments_kernel_v2<0x1000 | 0x400 | 0x01, kShaCtasPerSmMax>;
-    case 11: return sha512_segments_kernel_v2<0x1000 | 0x700 | 0x17, kShaCtasPerSmMax>;
     default: return sha512_segments_kernel_v2<0, kShaCtasPerSmMax>;
     }
 }
 
-// Length binning.  The `n` descriptors produced by get(i) are written to `descs` in the
-// caller's order (a streaming write into pinned memory) and `order` receives their indices
-// sorted by block count, longest first -- the kernel walks `order`, so only 4 bytes per file
-// are scattered on the host.  Counting sort over exactly the bucket range the batch uses
-// (514 buckets for files up to 64 KiB); the few items beyond 65535 blocks are ordered exactly
-// with std::sort.  Multi-million-file shards are binned by several host threads (per-thread
-// histograms, stable scatter).
+// Host half of the launch plan: the `n` descriptors produced by get(i) are streamed into
+// pinned memory in the caller's order and checked; the ordering by length is done on the
+// device (plan_kernels.cuh).  Multi-million-file shards are written by several host threads.
 struct PlanInfo {
     uint64_t total_blocks = 0, max_blocks = 0;
     bool aligned = true;
@@ -301,25 +293,13 @@ struct PlanInfo {
 };
 
 template <typename Get>
-static void bin_by_length(Get get, size_t n, SegDesc *descs, u32 *order, PlanInfo *info) {
-    constexpr uint32_t kCap = 65535;
+static void write_descriptors(Get get, size_t n, SegDesc *descs, PlanInfo *info) {
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const size_t nthreads = n < (1u << 18) ? 1 : std::min<size_t>({(size_t)hw, (size_t)8, n >> 17});
-    static thread_local std::vector<uint32_t> key;      // min(blocks, kCap) of every item
-    if (key.size() < n) key.resize(n);
+    const size_t nthreads = n < (1u << 19) ? 1 : std::min<size_t>({(size_t)hw, (size_t)8, n >> 18});
     std::vector<PlanInfo> part(nthreads);
-    auto range = [&](size_t t) { return std::make_pair(n * t / nthreads, n * (t + 1) / nthreads); };
-    auto run_all = [&](auto fn) {
-        if (nthreads == 1) { fn((size_t)0); return; }
-        std::vector<std::thread> th;
-        for (size_t t = 1; t < nthreads; t++) th.emplace_back(fn, t);
-        fn((size_t)0);
-        for (auto &x : th) x.join();
-    };
-    uint32_t *keyp = key.data();
-    run_all([&](size_t t) {
+    auto body = [&](size_t t) {
         PlanInfo &pi = part[t];
-        auto [lo, hi] = range(t);
+        const size_t lo = n * t / nthreads, hi = n * (t + 1) / nthreads;
         for (size_t i = lo; i < hi; i++) {
             const SegDesc d = get(i);
             descs[i] = d;
@@ -329,42 +309,51 @@ static void bin_by_length(Get get, size_t n, SegDesc *descs, u32 *order, PlanInf
             const uint64_t nb = seg_blocks(d.len, d.flags);
             pi.total_blocks += nb;
             pi.max_blocks = std::max(pi.max_blocks, nb);
-            keyp[i] = (uint32_t)std::min<uint64_t>(nb, kCap);
         }
-    });
+    };
+    if (nthreads == 1) {
+        body(0);
+    } else {
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < nthreads; t++) th.emplace_back(body, t);
+        body(0);
+        for (auto &x : th) x.join();
+    }
     for (const PlanInfo &pi : part) {
         info->total_blocks += pi.total_blocks;
         info->max_blocks = std::max(info->max_blocks, pi.max_blocks);
         info->aligned = info->aligned && pi.aligned;
         if (pi.bad && !info->bad) { info->bad = pi.bad; info->bad_index = pi.bad_index; }
     }
-    if (info->bad) return;
-    const size_t nbuckets = (size_t)std::min<uint64_t>(info->max_blocks, kCap) + 1;
-    std::vector<size_t> start(nthreads * nbuckets, 0);
-    run_all([&](size_t t) {
-        auto [lo, hi] = range(t);
-        size_t *cnt = start.data() + t * nbuckets;
-        for (size_t i = lo; i < hi; i++) cnt[keyp[i]]++;
-    });
-    // descending buckets; inside a bucket thread 0's items come first (keeps the sort stable)
-    size_t run = 0, n_long = 0;
-    for (size_t k = nbuckets; k-- > 0;)
-        for (size_t t = 0; t < nthreads; t++) {
-            size_t &c = start[t * nbuckets + k];
-            if (k == kCap) n_long += c;
-            const size_t here = c;
-            c = run;
-            run += here;
-        }
-    run_all([&](size_t t) {
-        auto [lo, hi] = range(t);
-        size_t *st = start.data() + t * nbuckets;
-        for (size_t i = lo; i < hi; i++) order[st[keyp[i]]++] = (u32)i;
-    });
-    if (n_long > 1)
-        std::sort(order, order + n_long, [descs](u32 a, u32 b) {
-            return seg_blocks(descs[a].len, descs[a].flags) > seg_blocks(descs[b].len, descs[b].flags);
-        });
+}
+
+// Device half: order[] = indices sorted by block count, longest first.  Layout of the plan
+// slot on the device: SegDesc[n] | u32 order[n] | u32 hist[nbuckets].
+struct DevicePlan {
+    const SegDesc *descs;
+    u32 *order;
+    u32 *hist;
+};
+
+static DevicePlan plan_layout(void *d_buf, size_t n) {
+    SegDesc *descs = static_cast<SegDesc *>(d_buf);
+    u32 *order = reinterpret_cast<u32 *>(descs + n);
+    return DevicePlan{descs, order, order + n};
+}
+
+static size_t plan_bytes(size_t n, size_t nbuckets) { return n * (sizeof(SegDesc) + sizeof(u32)) + nbuckets * sizeof(u32); }
+
+static int enqueue_length_binning(Device &D, cudaStream_t stream, const DevicePlan &p, size_t n, uint64_t max_blocks) {
+    const u32 top = (u32)std::min<uint64_t>(max_blocks, kPlanTopMax);
+    const u32 nbuckets = top + 1;
+    SG_CUDA(cudaMemsetAsync(p.hist, 0, nbuckets * sizeof(u32), stream));
+    const u32 grid = (u32)std::min<size_t>((n + kPlanThreads - 1) / kPlanThreads, (size_t)D.sm_count * 8);
+    plan_hist_kernel<<<grid, kPlanThreads, 0, stream>>>(p.descs, (u32)n, top, p.hist);
+    plan_scan_kernel<<<1, kPlanScanThreads, 0, stream>>>(p.hist, nbuckets);
+    plan_scatter_kernel<<<grid, kPlanThreads, 0, stream>>>(p.descs, (u32)n, top, p.hist, p.order);
+    SG_CUDA(cudaGetLastError());
+    rt().kernel_launches += 3;
+    return 0;
 }
 
 // Enqueue the hashing of `n` segments (get(i) -> SegDesc) of `d_data` on `stream`.
@@ -377,24 +366,26 @@ static int launch_sha512(Device &D, cudaStream_t stream, const uint8_t *d_data, 
     if (n > 0xfffffff0ull) return fail(SNAPGPU_EINVAL, "too many files in one launch (%zu)", n);
     auto &R = rt();
     PlanSlot *slot;
-    const size_t plan_bytes = n * (sizeof(SegDesc) + sizeof(u32));
-    int rc = acquire_slot(D, plan_bytes, &slot);
+    // descriptors are written before the slot's final size is known: the histogram needs at
+    // most kPlanTopMax + 1 buckets
+    int rc = acquire_slot(D, plan_bytes(n, kPlanTopMax + 1), &slot);
     if (rc) return rc;
     PlanInfo info;
     const double t_plan = now_ms();
-    SegDesc *h_descs = static_cast<SegDesc *>(slot->h_buf);
-    bin_by_length(get, n, h_descs, reinterpret_cast<u32 *>(h_descs + n), &info);
-    if (trace_on()) fprintf(stderr, "[snapgpu] length binning of %zu items: %.3f ms\n", n, now_ms() - t_plan);
+    write_descriptors(get, n, static_cast<SegDesc *>(slot->h_buf), &info);
+    if (trace_on()) fprintf(stderr, "[snapgpu] %zu descriptors written in %.3f ms\n", n, now_ms() - t_plan);
     if (info.bad == 1) return fail(SNAPGPU_EINVAL, "file %zu too large", info.bad_index);
     if (info.bad == 2)
         return fail(SNAPGPU_EINVAL, "non-final segment %zu is not a multiple of 128 bytes", info.bad_index);
     const bool aligned = info.aligned && ((uintptr_t)d_data & 15) == 0;
     const uint64_t total_blocks = info.total_blocks, max_blocks = info.max_blocks;
+    const DevicePlan plan = plan_layout(slot->d_buf, n);
 
-    SG_CUDA(cudaMemcpyAsync(slot->d_buf, slot->h_buf, plan_bytes, cudaMemcpyHostToDevice, D.copy_stream));
+    SG_CUDA(cudaMemcpyAsync(slot->d_buf, slot->h_buf, n * sizeof(SegDesc), cudaMemcpyHostToDevice, D.copy_stream));
     SG_CUDA(cudaMemsetAsync(slot->d_counter, 0, sizeof(u32), D.copy_stream));
     SG_CUDA(cudaEventRecord(slot->uploaded, D.copy_stream));
     SG_CUDA(cudaStreamWaitEvent(stream, slot->uploaded, 0));
+    if ((rc = enqueue_length_binning(D, stream, plan, n, max_blocks))) return rc;
 
     // warps per SM sub-partition: more hides latency better, fewer shortens the makespan when
     // one file is a large share of a lane's work (see DESIGN.md "makespan").
@@ -418,9 +409,7 @@ static int launch_sha512(Device &D, cudaStream_t stream, const uint8_t *d_data, 
         if (tl->pending) harvest_timings(tl, 1, D.sha_ms_sum, D.sha_ms_n, D.sha_ms_last, true);
         SG_CUDA(cudaEventRecord(tl->beg, stream));
     }
-    const SegDesc *d_descs = static_cast<const SegDesc *>(slot->d_buf);
-    k<<<grid, kShaThreads, 0, stream>>>(d_data, d_descs, reinterpret_cast<const u32 *>(d_descs + n), (u32)n, d_digests,
-                                         slot->d_counter, 1u);
+    k<<<grid, kShaThreads, 0, stream>>>(d_data, plan.descs, plan.order, (u32)n, d_digests, slot->d_counter, 1u);
     SG_CUDA(cudaGetLastError());
     if (tl) {
         SG_CUDA(cudaEventRecord(tl->end, stream));
@@ -1113,13 +1102,27 @@ void snapgpu_reset_stats(void) {
 
 // ---- test hooks: host logic only, callable without a GPU ---------------------------------
 
-// Launch order the length binning produces: order[k] = index of the k-th file of the plan.
+// Launch order the device-side length binning produces for files of these lengths:
+// order[k] = index of the k-th file of the plan.  Needs a GPU (runs the plan kernels on device 0).
 int snapgpu_test_plan_order(const uint64_t *lengths, size_t n, uint32_t *order) {
     if (!lengths || !order) return fail(SNAPGPU_EINVAL, "null argument");
-    std::vector<SegDesc> descs(n);
+    Device *D = nullptr;
+    int rc = get_device(0, &D);
+    if (rc) return rc;
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lock(D->mu);
+    SG_CUDA(cudaSetDevice(D->ordinal));
+    PlanSlot *slot;
+    if ((rc = acquire_slot(*D, plan_bytes(n, kPlanTopMax + 1), &slot))) return rc;
     PlanInfo info;
-    bin_by_length([lengths](size_t i) { return SegDesc{0, std::min<uint64_t>(lengths[i], kMaxSegBytes - 1), 0, (u32)i, 0}; },
-                  n, descs.data(), order, &info);
+    write_descriptors([lengths](size_t i) { return SegDesc{0, std::min<uint64_t>(lengths[i], kMaxSegBytes - 1), 0, (u32)i, 0}; },
+                      n, static_cast<SegDesc *>(slot->h_buf), &info);
+    const DevicePlan plan = plan_layout(slot->d_buf, n);
+    cudaStream_t s = D->compute_stream;
+    SG_CUDA(cudaMemcpyAsync(slot->d_buf, slot->h_buf, n * sizeof(SegDesc), cudaMemcpyHostToDevice, s));
+    if ((rc = enqueue_length_binning(*D, s, plan, n, info.max_blocks))) return rc;
+    SG_CUDA(cudaMemcpyAsync(order, plan.order, n * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    SG_CUDA(cudaStreamSynchronize(s));
     return 0;
 }
 

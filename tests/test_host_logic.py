@@ -130,20 +130,6 @@ def test_walk_order_and_trailing_slash(native, oracle, tmp_path):
 
 # ---- launch plan -----------------------------------------------------------------------------
 
-def test_plan_is_longest_first(native):
-    rng = np.random.default_rng(3)
-    lengths = np.concatenate([rng.integers(0, 70000, 5000), [0, 111, 112, 2**30, 2**31 + 5, 9_000_000, 8_388_608 * 128]]
-                             ).astype(np.uint64)
-    order = np.zeros(len(lengths), dtype=np.uint32)
-    native.check(native.lib().snapgpu_test_plan_order(lengths.ctypes.data, len(lengths), order.ctypes.data))
-    assert sorted(order.tolist()) == list(range(len(lengths)))
-    blocks = (lengths[order] + np.uint64(144)) // np.uint64(128)
-    assert np.all(blocks[:-1] >= blocks[1:])
-    # the 32 lanes of a warp see (nearly) the same block count once the list is binned
-    body = blocks[32: 32 * (len(blocks) // 32)].reshape(-1, 32).astype(np.int64)
-    assert np.median(body.max(axis=1) - body.min(axis=1)) <= 4
-
-
 def test_sharder_balances_and_covers(native):
     rng = np.random.default_rng(4)
     for ndev in (1, 2, 4, 8):

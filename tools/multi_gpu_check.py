@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""In-process multi-device sharding (snapgpu_init over every visible GPU): parity against the
+oracle and end-to-end timing of the host-buffer call at 1..N devices.  JSON lines on stdout."""
+import ctypes
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from oracle import oracle as O                # noqa: E402  (checker only)
+from snappy_b200 import _native as N          # noqa: E402
+from snappy_b200 import helpers, synth        # noqa: E402
+
+ngpu = torch.cuda.device_count()
+lengths = synth.lognormal_sizes(100_000)
+data, off, ln = synth.make_host_batch(lengths)
+want = O.sha512_batch(data, off, ln, 16, bool(O.lib().oracle_have_openssl()))
+nbytes = int(ln.sum())
+for nd in [n for n in (1, 2, 4, 8) if n <= ngpu]:
+    N.init(list(range(nd)))
+    p = N.lib().snapgpu_alloc_pinned(len(data))
+    host = np.frombuffer((ctypes.c_uint8 * len(data)).from_address(p), dtype=np.uint8)
+    host[:] = data
+    got = helpers.sha512_batch(host, off, ln)
+    assert np.array_equal(got, want), f"{nd} devices: digests differ from the oracle"
+    b = host.copy()
+    flip = [5, 77_777, 99_999]
+    for i in flip:
+        b[int(off[i]) + int(ln[i]) - 1] ^= 1
+    eq = helpers.cmp_batch(host, b, off, ln)
+    assert np.nonzero(eq == 0)[0].tolist() == flip, f"{nd} devices: cmp flags wrong"
+    best = 1e9
+    for _ in range(4):
+        t0 = time.perf_counter()
+        helpers.sha512_batch(host, off, ln)
+        best = min(best, time.perf_counter() - t0)
+    print(json.dumps({"what": "in-process sharding, host buffers (config 2 batch)", "devices": nd, "ms": best * 1e3,
+                      "gb_per_s": nbytes / best / 1e9, "bit_exact_with_oracle": True}), flush=True)
+    N.lib().snapgpu_free_pinned(p)
+    N.lib().snapgpu_shutdown()
