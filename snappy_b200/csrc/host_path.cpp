@@ -24,6 +24,7 @@
 #include <errno.h>
 #include <fcntl.h>
 #include <sys/stat.h>
+#include <time.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -87,6 +88,12 @@ int ring_acquire(Staging &s, size_t want) {
     }
     s.ring_cap = want;
     return 0;
+}
+
+double wall_ms() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
 std::string go_path_error(const char *op, const std::string &path, int err) {
@@ -154,6 +161,10 @@ struct PackedFile {
     bool grew = false;     // more bytes than planned: re-hashed through stream_file
 };
 
+// One file into its slot: open, ONE read of planned+1 bytes, close.  For a regular file a read
+// that returns exactly the size it had at stat time has reached EOF (the slot has one spare
+// byte, so a file that grew shows up as planned+1 bytes and is re-hashed by streaming); only a
+// file that shrank needs the io.Copy-style "read until 0" loop.
 void pack_one(const std::string &path, uint8_t *buf, PackedFile &f) {
     int fd = ::open(path.c_str(), O_RDONLY | O_CLOEXEC);
     if (fd < 0) {
@@ -161,23 +172,23 @@ void pack_one(const std::string &path, uint8_t *buf, PackedFile &f) {
         f.op = "open";
         return;
     }
-    ssize_t r = f.planned ? read_full(fd, buf + f.off, f.planned) : 0;
-    if (r < 0) {
-        f.err = errno;
-        f.op = "read";
-    } else {
-        f.len = (size_t)r;
-        if ((uint64_t)r == f.planned) {            // io.Copy reads to EOF, not to st_size: is there more?
-            uint8_t probe;
-            ssize_t more;
-            do more = ::read(fd, &probe, 1); while (more < 0 && errno == EINTR);
-            if (more < 0) {
-                f.err = errno;
-                f.op = "read";
-            } else if (more > 0) {
-                f.grew = true;
-            }
+    uint8_t *dst = buf + f.off;
+    const size_t want = f.planned + 1;
+    size_t got = 0;
+    for (;;) {
+        ssize_t r = ::read(fd, dst + got, want - got);
+        if (r < 0) {
+            if (errno == EINTR) continue;
+            f.err = errno;
+            f.op = "read";
+            break;
         }
+        got += (size_t)r;
+        if (r == 0 || got == f.planned || got == want) break;
+    }
+    if (!f.err) {
+        f.grew = got > f.planned;
+        f.len = std::min<uint64_t>(got, f.planned);
     }
     ::close(fd);
 }
@@ -242,7 +253,7 @@ int hash_files(const std::vector<std::string> &paths, std::vector<uint8_t> &dige
 
     // pinned ring sized to the job (pinning memory costs ~0.4 ms per MiB): 16 MiB .. host_ring_bytes()
     uint64_t total = 0;
-    for (size_t i = 0; i < n; i++) total += align_up(planned[i]);
+    for (size_t i = 0; i < n; i++) total += align_up(planned[i] + 1);
     size_t want = (size_t)16 << 20;
     while (want < total + 4096 && want < host_ring_bytes()) want <<= 1;
     want = std::min(want, std::max(host_ring_bytes(), (size_t)1 << 20));
@@ -255,14 +266,14 @@ int hash_files(const std::vector<std::string> &paths, std::vector<uint8_t> &dige
     std::vector<Batch> batches;
     const size_t room = cap - 256;
     for (size_t i = 0; i < n;) {
-        if (planned[i] > room) {
+        if (planned[i] + 1 > room) {
             batches.push_back(Batch{i, 1, true});
             i++;
             continue;
         }
         size_t used = 0, j = i;
-        while (j < n && planned[j] <= room && align_up(used) + planned[j] <= room) {
-            used = align_up(used) + planned[j];
+        while (j < n && planned[j] <= room && align_up(used) + planned[j] + 1 <= room) {
+            used = align_up(used) + planned[j] + 1;            // one spare byte per slot, see pack_one
             j++;
         }
         batches.push_back(Batch{i, j - i, false});
@@ -283,7 +294,7 @@ int hash_files(const std::vector<std::string> &paths, std::vector<uint8_t> &dige
             f.off = used;
             f.planned = planned[f.index];
             pf.push_back(f);
-            used += f.planned;
+            used += f.planned + 1;
         }
         uint8_t *buf = S.ring[bi & 1];
         parallel_for(pf.size(), [&](size_t k) { pack_one(paths[pf[k].index], buf, pf[k]); });
@@ -637,14 +648,24 @@ public:
 
     void key(const char *name, bool first_in_sequence_item = false) {
         if (!first_in_sequence_item) write_indent();
-        std::vector<uint32_t> cps;
-        for (const char *p = name; *p; p++) cps.push_back((unsigned char)*p);
-        write_plain(cps);
+        write_plain_ascii(name, strlen(name));           // keys are fixed identifiers without spaces
         write_indicator(":", false, false, false);
     }
 
     // encoder.stringv + emitter scalar selection for a mapping value in block context
     int string_value(const std::string &raw) {
+        // Fast path for what every entry of a real tree is: a non-empty run of [A-Za-z0-9_./+-]
+        // (no space, break, indicator or non-ASCII byte), for which the scalar analysis below
+        // allows the plain style and plain output is the text itself with no folding.  Anything
+        // else -- and any such text that yaml.v2 would resolve to a bool/int/float/null -- takes
+        // the general path.
+        if (plain_safe(raw) && !resolves_to_non_string(raw) && !is_base60_float(raw)) {
+            const int saved = indent_;
+            indent_ += 2;
+            write_plain_ascii(raw.data(), raw.size());
+            indent_ = saved;
+            return 0;
+        }
         std::vector<uint32_t> cps;
         std::string tag;
         bool non_str = false;
@@ -680,12 +701,10 @@ public:
         return 0;
     }
 
-    void plain_value(const std::string &ascii) {
-        std::vector<uint32_t> cps;
-        for (char c : ascii) cps.push_back((unsigned char)c);
+    void plain_value(const std::string &ascii) {          // decimal integers
         const int saved = indent_;
         indent_ += 2;
-        write_plain(cps);
+        write_plain_ascii(ascii.data(), ascii.size());
         indent_ = saved;
     }
 
@@ -709,7 +728,42 @@ private:
         bool block_plain = true, single = true, block = false;
     };
 
-    void put(uint32_t cp) { append_utf8(out, cp); column_++; }
+    void put(uint32_t cp) {
+        if (cp < 0x80) out.push_back((char)cp);
+        else append_utf8(out, cp);
+        column_++;
+    }
+
+    // see string_value: the texts whose plain rendering is the text itself
+    static bool plain_safe(const std::string &s) {
+        const size_t n = s.size();
+        if (n == 0 || (n == 1 && s[0] == '-')) return false;                  // "-" alone is a block indicator
+        if (n >= 3 && ((s[0] == '-' && s[1] == '-' && s[2] == '-') || (s[0] == '.' && s[1] == '.' && s[2] == '.')))
+            return false;                                                      // document markers
+        static const struct Table {
+            bool ok[256];
+            Table() {
+                for (bool &b : ok) b = false;
+                for (int c = 'a'; c <= 'z'; c++) ok[c] = true;
+                for (int c = 'A'; c <= 'Z'; c++) ok[c] = true;
+                for (int c = '0'; c <= '9'; c++) ok[c] = true;
+                ok[(int)'_'] = ok[(int)'.'] = ok[(int)'/'] = ok[(int)'+'] = ok[(int)'-'] = true;
+            }
+        } table;
+        for (size_t i = 0; i < n; i++)
+            if (!table.ok[(unsigned char)s[i]]) return false;
+        return true;
+    }
+
+    // write_plain for ASCII text without spaces: nothing to fold
+    void write_plain_ascii(const char *p, size_t n) {
+        if (!whitespace_) put(' ');
+        out.append(p, n);
+        column_ += (int)n;
+        if (n) indention_ = false;
+        whitespace_ = false;
+        indention_ = false;
+    }
     void put_break() { out.push_back('\n'); column_ = 0; }
     void write_indent() {
         const int ind = indent_ < 0 ? 0 : indent_;
@@ -932,8 +986,11 @@ struct TreeEntry {
 };
 
 // filepath.Walk: pre-order, names of each directory sorted bytewise, Lstat.
+// The children of one directory are lstat'ed through its descriptor (fstatat), and at the top
+// level the subtrees of the root's sub-directories are walked by several threads and stitched
+// back together in Walk order.
 int walk_children(const std::string &dir, const std::string &rel, mode_t dir_mode, off_t dir_size,
-                  std::vector<TreeEntry> &out) {
+                  std::vector<TreeEntry> &out, bool top_level = false) {
     DIR *d = opendir(dir.c_str());
     if (!d) {
         // Go reports the directory to the callback a second time with the error, and
@@ -947,19 +1004,61 @@ int walk_children(const std::string &dir, const std::string &rel, mode_t dir_mod
         if (!strcmp(e->d_name, ".") || !strcmp(e->d_name, "..")) continue;
         names.emplace_back(e->d_name);
     }
-    closedir(d);
     std::sort(names.begin(), names.end());
-    for (const std::string &n : names) {
-        const std::string child = dir + "/" + n;
-        const std::string crel = rel + "/" + n;
-        struct stat st;
-        if (lstat(child.c_str(), &st) != 0)
-            return fail(SNAPGPU_EIO, "%s", go_path_error("lstat", child, errno).c_str());
+    const int dfd = dirfd(d);
+    std::vector<struct stat> sts(names.size());
+    for (size_t i = 0; i < names.size(); i++)
+        if (fstatat(dfd, names[i].c_str(), &sts[i], AT_SYMLINK_NOFOLLOW) != 0) {
+            const int e = errno;
+            closedir(d);
+            return fail(SNAPGPU_EIO, "%s", go_path_error("lstat", dir + "/" + names[i], e).c_str());
+        }
+    closedir(d);
+
+    // sub-directories of the root: walked in parallel, each into its own list
+    std::vector<std::vector<TreeEntry>> sub;
+    std::vector<int> sub_rc;
+    std::vector<std::string> sub_err;
+    std::vector<size_t> subdirs;
+    if (top_level) {
+        for (size_t i = 0; i < names.size(); i++)
+            if (S_ISDIR(sts[i].st_mode)) subdirs.push_back(i);
+        const unsigned nthreads = std::min<unsigned>(packer_threads(16 * subdirs.size()), (unsigned)subdirs.size());
+        if (nthreads >= 2) {
+            sub.resize(subdirs.size());
+            sub_rc.assign(subdirs.size(), 0);
+            sub_err.resize(subdirs.size());
+            std::atomic<size_t> next{0};
+            auto work = [&]() {
+                for (size_t k; (k = next.fetch_add(1)) < subdirs.size();) {
+                    const size_t i = subdirs[k];
+                    sub_rc[k] = walk_children(dir + "/" + names[i], rel + "/" + names[i], sts[i].st_mode, sts[i].st_size, sub[k]);
+                    if (sub_rc[k]) sub_err[k] = snapgpu_last_error();
+                }
+            };
+            std::vector<std::thread> th;
+            for (unsigned t = 1; t < nthreads; t++) th.emplace_back(work);
+            work();
+            for (auto &x : th) x.join();
+        }
+    }
+
+    size_t k = 0;
+    for (size_t i = 0; i < names.size(); i++) {
+        const std::string child = dir + "/" + names[i];
+        const std::string crel = rel + "/" + names[i];
+        const struct stat &st = sts[i];
         const bool skip = crel.compare(0, 7, "/DEBIAN") == 0;     // prefix test (build.go:229)
         if (!skip) out.push_back(TreeEntry{crel.substr(1), child, st.st_mode, st.st_size, S_ISREG(st.st_mode)});
         if (S_ISDIR(st.st_mode)) {
-            int rc = walk_children(child, crel, st.st_mode, st.st_size, out);
-            if (rc) return rc;
+            if (!sub.empty()) {
+                if (sub_rc[k]) return fail(sub_rc[k], "%s", sub_err[k].c_str());
+                out.insert(out.end(), std::make_move_iterator(sub[k].begin()), std::make_move_iterator(sub[k].end()));
+                k++;
+            } else {
+                int rc = walk_children(child, crel, st.st_mode, st.st_size, out);
+                if (rc) return rc;
+            }
         }
     }
     return 0;
@@ -990,7 +1089,7 @@ int collect_tree(const std::string &build_dir, std::vector<TreeEntry> &entries) 
     entries.clear();
     struct stat root;
     if (lstat(build_dir.c_str(), &root) == 0 && S_ISDIR(root.st_mode))
-        return walk_children(build_dir, "", root.st_mode, root.st_size, entries);
+        return walk_children(build_dir, "", root.st_mode, root.st_size, entries, true);
     return 0;
 }
 
@@ -1161,8 +1260,10 @@ int snapgpu_test_yaml_from_digests(const char *build_dir, const uint8_t *digests
                                    size_t *out_len) {
     if (!build_dir || !out_len) return fail(SNAPGPU_EINVAL, "null argument");
     std::vector<TreeEntry> entries;
+    const double t0 = wall_ms();
     int rc = collect_tree(clean_dir(build_dir), entries);
     if (rc) return rc;
+    const double t1 = wall_ms();
     if (!digests) {
         size_t nreg = 0;
         for (const TreeEntry &e : entries) nreg += e.regular;
@@ -1172,6 +1273,8 @@ int snapgpu_test_yaml_from_digests(const char *build_dir, const uint8_t *digests
     if (!out) return fail(SNAPGPU_EINVAL, "null argument");
     std::string yaml;
     if ((rc = emit_hashes_yaml(entries, digests, ndigests, &yaml))) return rc;
+    if (getenv("SNAPGPU_TRACE"))
+        fprintf(stderr, "[snapgpu] walk of %zu entries %.2f ms, yaml emit %.2f ms\n", entries.size(), t1 - t0, wall_ms() - t1);
     char *buf = static_cast<char *>(malloc(yaml.size() + 1));
     if (!buf) return fail(SNAPGPU_EINVAL, "out of memory");
     memcpy(buf, yaml.data(), yaml.size());

@@ -89,7 +89,10 @@ struct PlanSlot {
 
 struct TimedLaunch {
     cudaEvent_t beg = nullptr, end = nullptr;
+    cudaEvent_t plan_ready = nullptr;   // trace only: the slot's "uploaded" event of this launch
+    cudaEvent_t prev_end = nullptr;     // trace only: end event of the launch before
     bool pending = false;
+    bool recorded = false;
 };
 
 struct Device {
@@ -174,7 +177,7 @@ static int init_device(Device &D, int ordinal) {
     SG_CUDA(cudaStreamCreateWithFlags(&D.compute_stream, cudaStreamNonBlocking));
     for (auto &s : D.slots) {
         SG_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
-        SG_CUDA(cudaEventCreateWithFlags(&s.uploaded, cudaEventDisableTiming));
+        SG_CUDA(cudaEventCreate(&s.uploaded));
         SG_CUDA(cudaMalloc(&s.d_counter, 256));
     }
     for (int b = 0; b < 2; b++) {
@@ -199,7 +202,9 @@ int ensure_init() {
     return snapgpu_init(nullptr, 0);
 }
 
-// Reserve a plan slot of at least `bytes`: waits for the launch that used it last.
+// Reserve a plan slot of at least `bytes`: waits for the launch that used it last.  When a
+// slot has to grow, all of them grow together, so the cost of pinning memory is paid in the
+// first call of a given size and not again three launches later.
 static int acquire_slot(Device &D, size_t bytes, PlanSlot **out) {
     PlanSlot &s = D.slots[D.next_slot];
     D.next_slot = (D.next_slot + 1) % kPlanSlots;
@@ -208,19 +213,28 @@ static int acquire_slot(Device &D, size_t bytes, PlanSlot **out) {
         s.in_flight = false;
     }
     if (s.cap < bytes) {
-        if (s.h_buf) cudaFreeHost(s.h_buf);
-        if (s.d_buf) cudaFree(s.d_buf);
-        s.h_buf = s.d_buf = nullptr;
-        s.cap = 0;
-        size_t want = std::max<size_t>(bytes + bytes / 4, 1u << 16);
-        SG_CUDA(cudaHostAlloc(&s.h_buf, want, cudaHostAllocPortable));
-        SG_CUDA(cudaMalloc(&s.d_buf, want));
-        s.cap = want;
+        const size_t want = std::max<size_t>(bytes + bytes / 4, 1u << 16);
+        for (PlanSlot &g : D.slots) {
+            if (g.cap >= want) continue;
+            if (g.in_flight) {
+                SG_CUDA(cudaEventSynchronize(g.done));
+                g.in_flight = false;
+            }
+            if (g.h_buf) cudaFreeHost(g.h_buf);
+            if (g.d_buf) cudaFree(g.d_buf);
+            g.h_buf = g.d_buf = nullptr;
+            g.cap = 0;
+            SG_CUDA(cudaHostAlloc(&g.h_buf, want, cudaHostAllocPortable));
+            SG_CUDA(cudaMalloc(&g.d_buf, want));
+            memset(g.h_buf, 0, want);          // touch the pages now, not inside a timed launch
+            g.cap = want;
+        }
     }
     *out = &s;
     return 0;
 }
 
+static bool trace_on();
 static void harvest_timings(TimedLaunch *ring, int n, double &sum, uint64_t &cnt, double &last, bool wait) {
     for (int i = 0; i < n; i++) {
         TimedLaunch &t = ring[i];
@@ -232,6 +246,14 @@ static void harvest_timings(TimedLaunch *ring, int n, double &sum, uint64_t &cnt
             sum += ms;
             cnt++;
             last = ms;
+        }
+        if (trace_on() && t.plan_ready) {
+            float since_plan = -1, gap = -1;
+            cudaEventElapsedTime(&since_plan, t.plan_ready, t.beg);
+            if (t.prev_end) cudaEventElapsedTime(&gap, t.prev_end, t.beg);
+            cudaGetLastError();
+            fprintf(stderr, "[snapgpu] kernel %.3f ms; started %.3f ms after its plan was ready, %.3f ms after the previous kernel ended\n",
+                    ms, since_plan, gap);
         }
         t.pending = false;
     }
@@ -368,10 +390,11 @@ static int launch_sha512(Device &D, cudaStream_t stream, const uint8_t *d_data, 
     PlanSlot *slot;
     // descriptors are written before the slot's final size is known: the histogram needs at
     // most kPlanTopMax + 1 buckets
+    const double t_plan = now_ms();
     int rc = acquire_slot(D, plan_bytes(n, kPlanTopMax + 1), &slot);
     if (rc) return rc;
     PlanInfo info;
-    const double t_plan = now_ms();
+    if (trace_on()) fprintf(stderr, "[snapgpu] plan slot acquired after %.3f ms\n", now_ms() - t_plan);
     write_descriptors(get, n, static_cast<SegDesc *>(slot->h_buf), &info);
     if (trace_on()) fprintf(stderr, "[snapgpu] %zu descriptors written in %.3f ms\n", n, now_ms() - t_plan);
     if (info.bad == 1) return fail(SNAPGPU_EINVAL, "file %zu too large", info.bad_index);
@@ -381,11 +404,13 @@ static int launch_sha512(Device &D, cudaStream_t stream, const uint8_t *d_data, 
     const uint64_t total_blocks = info.total_blocks, max_blocks = info.max_blocks;
     const DevicePlan plan = plan_layout(slot->d_buf, n);
 
+    // upload and binning run on the copy stream, i.e. beside whatever the caller's stream is
+    // still hashing; the hashing kernel waits for the finished plan
     SG_CUDA(cudaMemcpyAsync(slot->d_buf, slot->h_buf, n * sizeof(SegDesc), cudaMemcpyHostToDevice, D.copy_stream));
     SG_CUDA(cudaMemsetAsync(slot->d_counter, 0, sizeof(u32), D.copy_stream));
+    if ((rc = enqueue_length_binning(D, D.copy_stream, plan, n, max_blocks))) return rc;
     SG_CUDA(cudaEventRecord(slot->uploaded, D.copy_stream));
     SG_CUDA(cudaStreamWaitEvent(stream, slot->uploaded, 0));
-    if ((rc = enqueue_length_binning(D, stream, plan, n, max_blocks))) return rc;
 
     // warps per SM sub-partition: more hides latency better, fewer shortens the makespan when
     // one file is a large share of a lane's work (see DESIGN.md "makespan").
@@ -407,6 +432,9 @@ static int launch_sha512(Device &D, cudaStream_t stream, const uint8_t *d_data, 
         tl = &D.sha_t[D.sha_ti];
         D.sha_ti = (D.sha_ti + 1) % 8;
         if (tl->pending) harvest_timings(tl, 1, D.sha_ms_sum, D.sha_ms_n, D.sha_ms_last, true);
+        tl->plan_ready = slot->uploaded;
+        const TimedLaunch &before = D.sha_t[(D.sha_ti + 6) % 8];      // the launch before this one
+        tl->prev_end = before.recorded ? before.end : nullptr;
         SG_CUDA(cudaEventRecord(tl->beg, stream));
     }
     k<<<grid, kShaThreads, 0, stream>>>(d_data, plan.descs, plan.order, (u32)n, d_digests, slot->d_counter, 1u);
@@ -414,11 +442,13 @@ static int launch_sha512(Device &D, cudaStream_t stream, const uint8_t *d_data, 
     if (tl) {
         SG_CUDA(cudaEventRecord(tl->end, stream));
         tl->pending = true;
+        tl->recorded = true;
     }
     SG_CUDA(cudaEventRecord(slot->done, stream));
     slot->in_flight = true;
     R.kernel_launches++;
     R.sha_launches++;
+    if (trace_on()) fprintf(stderr, "[snapgpu] sha512 launch of %zu files enqueued in %.3f ms (host)\n", n, now_ms() - t_plan);
     return 0;
 }
 
