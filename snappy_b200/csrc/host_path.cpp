@@ -305,7 +305,9 @@ int hash_files(const std::vector<std::string> &paths, std::vector<uint8_t> &dige
     std::thread prefetch;
     fill(0);
     for (size_t bi = 0; bi < batches.size() && !rc; bi++) {
+        const double tb0 = wall_ms();
         if (prefetch.joinable()) prefetch.join();             // batch bi is packed
+        const double tb1 = wall_ms();
         if (bi + 1 < batches.size()) prefetch = std::thread(fill, bi + 1);
         const Batch &B = batches[bi];
         uint8_t *buf = S.ring[bi & 1];
@@ -324,6 +326,9 @@ int hash_files(const std::vector<std::string> &paths, std::vector<uint8_t> &dige
         for (const PackedFile &f : pf) segs.push_back(HostSeg{f.off, f.grew ? 0 : f.len, 0, 0});
         out.resize(segs.size() * 64);
         if ((rc = sha512_host_segments(buf, segs.data(), segs.size(), out.data()))) break;
+        if (getenv("SNAPGPU_TRACE"))
+            fprintf(stderr, "[snapgpu] batch %zu: %zu files, waited %.2f ms for the packer, GPU call %.2f ms\n", bi, pf.size(),
+                    tb1 - tb0, wall_ms() - tb1);
         for (size_t k = 0; k < pf.size(); k++) memcpy(&digests[64 * pf[k].index], &out[64 * k], 64);
         for (const PackedFile &f : pf)                        // rare: the file grew after its stat
             if (f.grew && (rc = stream_file(paths[f.index], buf, cap, &digests[64 * f.index]))) break;
@@ -1134,6 +1139,7 @@ int emit_hashes_yaml(const std::vector<TreeEntry> &entries, const uint8_t *diges
 
 int build_hashes_yaml(const std::string &build_dir, const std::string &data_tar, std::string *yaml) {
     std::vector<TreeEntry> entries;
+    const double t0 = wall_ms();
     int rc = collect_tree(build_dir, entries);
     if (rc) return rc;
     std::vector<std::string> paths;
@@ -1146,8 +1152,14 @@ int build_hashes_yaml(const std::string &build_dir, const std::string &data_tar,
             sizes.push_back((int64_t)e.size);            // the walk's lstat: no second stat
         }
     std::vector<uint8_t> digests;
+    const double t1 = wall_ms();
     if ((rc = hash_files(paths, digests, &sizes))) return rc;
-    return emit_hashes_yaml(entries, digests.data(), paths.size(), yaml);
+    const double t2 = wall_ms();
+    rc = emit_hashes_yaml(entries, digests.data(), paths.size(), yaml);
+    if (getenv("SNAPGPU_TRACE"))
+        fprintf(stderr, "[snapgpu] writeHashes: walk %.2f ms (%zu entries), pack+hash %.2f ms (%zu files), yaml %.2f ms\n",
+                t1 - t0, entries.size(), t2 - t1, paths.size(), wall_ms() - t2);
+    return rc;
 }
 
 int write_file_0644(const std::string &path, const std::string &content) {
