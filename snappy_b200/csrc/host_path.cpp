@@ -574,6 +574,16 @@ bool resolves_to_non_string(const std::string &s) {
     for (int i = 0; table[i]; i++) if (s == table[i]) return true;
     if (c == '.') return go_parse_float_ok(s);
     if (num_hint) {
+        // quick reject for long texts such as hex digests: 'c'/'d' can only occur in a number
+        // after a "0x" prefix, so without an 'x' the text is neither an int nor a float
+        if (s.size() > 24) {
+            bool has_x = false, has_cd = false;
+            for (char ch : s) {
+                has_x = has_x || ch == 'x' || ch == 'X';
+                has_cd = has_cd || ch == 'c' || ch == 'd' || ch == 'C' || ch == 'D';
+            }
+            if (has_cd && !has_x) return false;
+        }
         std::string plain;
         for (char ch : s) if (ch != '_') plain.push_back(ch);
         if (go_parse_int_ok(plain) || go_parse_float_ok(plain)) return true;
@@ -975,10 +985,9 @@ int yaml_file_mode(mode_t m, std::string *out) {
     else if (S_ISLNK(m)) t = 'l';
     else if (S_ISREG(m)) t = 'f';
     else return fail(SNAPGPU_EMODE, "Unknown file mode %s", go_mode_string(m).c_str());
-    std::string s(1, t);
     const char *rwx = "rwxrwxrwx";
-    for (int i = 0; i < 9; i++) s += (m & (1u << (8 - i))) ? rwx[i] : '-';
-    *out = s;
+    out->assign(10, t);
+    for (int i = 0; i < 9; i++) (*out)[1 + i] = (m & (1u << (8 - i))) ? rwx[i] : '-';
     return 0;
 }
 
@@ -1107,24 +1116,35 @@ int emit_hashes_yaml(const std::vector<TreeEntry> &entries, const uint8_t *diges
     if (ndigests != nreg + 1) return fail(SNAPGPU_EINVAL, "expected %zu digests, got %zu", nreg + 1, ndigests);
     int rc;
     YamlEmitter em;
+    em.out.reserve(256 + entries.size() * 224);           // ~200 bytes per regular entry
+    std::string hex(128, '0'), mode, num;
+    auto hex_into = [&hex](const uint8_t *p) {
+        static const char d[] = "0123456789abcdef";
+        for (int i = 0; i < 64; i++) {
+            hex[2 * i] = d[p[i] >> 4];
+            hex[2 * i + 1] = d[p[i] & 15];
+        }
+    };
     em.key("archive-sha512");
-    if ((rc = em.string_value(hex_lower(&digests[0], 64)))) return rc;
+    hex_into(&digests[0]);
+    if ((rc = em.string_value(hex))) return rc;
     em.key("files");
     if (entries.empty()) {
         em.empty_flow_sequence();
     } else {
         size_t di = 1;
         for (const TreeEntry &e : entries) {
-            std::string mode;
             if ((rc = yaml_file_mode(e.mode, &mode))) return rc;
             em.begin_sequence_item();
             em.key("name", true);
             if ((rc = em.string_value(e.name))) return rc;
             if (e.regular) {
                 em.key("size");
-                em.plain_value(std::to_string((long long)e.size));
+                num = std::to_string((long long)e.size);
+                em.plain_value(num);
                 em.key("sha512");
-                if ((rc = em.string_value(hex_lower(&digests[64 * di], 64)))) return rc;
+                hex_into(&digests[64 * di]);
+                if ((rc = em.string_value(hex))) return rc;
                 di++;
             }
             em.key("mode");
