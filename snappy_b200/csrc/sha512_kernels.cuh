@@ -29,9 +29,10 @@ struct SegDesc {
     u32 out_idx;  // digest slot
     u32 flags;
 };
-enum : u32 { kSegContinue = 1u, kSegNoFinal = 2u };
+enum : u32 { kSegContinue = 1u, kSegNoFinal = 2u, kSegSkip = 4u /* hashed by the long-file kernel instead */ };
 
 __host__ __device__ inline u64 seg_blocks(u64 len, u32 flags) {
+    if (flags & kSegSkip) return 0;
     return (flags & kSegNoFinal) ? (len >> 7) : ((len + 144) >> 7);   // (L+144)/128
 }
 
@@ -112,7 +113,7 @@ sha512_segments_kernel(const uint8_t *__restrict__ data, const SegDesc *__restri
 
     while (unit < nunits) {
         const u32 idx = unit * 32 + lane;
-        const bool have = idx < nsegs;
+        bool have = idx < nsegs;
         SegDesc sd;
         sd.off = 0; sd.len = 0; sd.prefix = 0; sd.out_idx = 0; sd.flags = kSegNoFinal;
         if (have) {
@@ -120,6 +121,7 @@ sha512_segments_kernel(const uint8_t *__restrict__ data, const SegDesc *__restri
             uint4 q0 = q[0], q1 = q[1];
             sd.off = pack64(q0.x, q0.y); sd.len = pack64(q0.z, q0.w);
             sd.prefix = pack64(q1.x, q1.y); sd.out_idx = q1.z; sd.flags = q1.w;
+            if (sd.flags & kSegSkip) have = false;
         }
         const u32 nblk = have ? (u32)seg_blocks(sd.len, sd.flags) : 0u;
         const u32 nblk_max = __reduce_max_sync(0xffffffffu, nblk);
@@ -240,7 +242,7 @@ sha512_segments_kernel_v2(const uint8_t *__restrict__ data, const SegDesc *__res
 
     while (unit < nunits) {
         const u32 idx = unit * 32 + lane;
-        const bool have = idx < nsegs;
+        bool have = idx < nsegs;
         SegDesc sd;
         sd.off = 0; sd.len = 0; sd.prefix = 0; sd.out_idx = 0; sd.flags = kSegNoFinal;
         if (have) {
@@ -248,6 +250,7 @@ sha512_segments_kernel_v2(const uint8_t *__restrict__ data, const SegDesc *__res
             uint4 q0 = q[0], q1 = q[1];
             sd.off = pack64(q0.x, q0.y); sd.len = pack64(q0.z, q0.w);
             sd.prefix = pack64(q1.x, q1.y); sd.out_idx = q1.z; sd.flags = q1.w;
+            if (sd.flags & kSegSkip) have = false;
         }
         const u32 nblk = have ? (u32)seg_blocks(sd.len, sd.flags) : 0u;
         const u32 nblk_max = __reduce_max_sync(0xffffffffu, nblk);

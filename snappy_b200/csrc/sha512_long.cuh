@@ -27,7 +27,9 @@ constexpr int kLongThreads = 64;          // warp 0 consumer, warp 1 producer
 constexpr int kLongFilesPerCta = 32;      // one consumer lane per file
 // ring[step][t][file], packed for the number of files nf the CTA actually has: it holds
 // 256 / nf block steps (8 for 32 files, 256 for a single file), i.e. 8 producer rounds.
-constexpr int kLongRingWords = 256 * 80;  // 160 KiB of dynamic shared memory
+constexpr int kLongSlotWords = 81;        // 80 words per (step, file) + 1 of padding: a single file's
+                                          // producer lanes (32 consecutive steps) then spread over the banks
+constexpr int kLongRingWords = 256 * kLongSlotWords;  // 162 KiB of dynamic shared memory
 constexpr size_t kLongRingBytes = (size_t)kLongRingWords * 8;
 constexpr size_t kLongSmemBytes = kLongRingBytes + 16;
 
@@ -90,13 +92,14 @@ sha512_long_kernel(const uint8_t *__restrict__ data, const SegDesc *__restrict__
 #pragma unroll
             for (int i = 0; i < 8; i++) st[i] = kIV512[i];
         }
-        u32 ready = 0;
+        u32 ready = 0, slot_index = 0;
         for (u32 b = 0; b < steps; b++) {
             if (b >= ready) {
                 do ready = ld_volatile_shared(produced); while (b >= ready);
                 __threadfence_block();
             }
-            const u64 *slot = ring + (size_t)(b % ring_steps) * 80 * nf + min(lane, nf - 1);
+            const u64 *slot = ring + (size_t)slot_index * kLongSlotWords * nf + min(lane, nf - 1);
+            slot_index = slot_index + 1 == ring_steps ? 0 : slot_index + 1;
             u64 a = st[0], bb = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
 #pragma unroll 1
             for (int grp = 0; grp < 5; grp++) {
@@ -153,7 +156,9 @@ sha512_long_kernel(const uint8_t *__restrict__ data, const SegDesc *__restrict__
             // room in the ring for `per` more steps?
             const u32 upto = min(steps, done + per);
             u32 freed;
-            do freed = ld_volatile_shared(consumed); while (upto > freed + ring_steps);
+            // the producer is far faster than the consumer: back off instead of hammering the
+            // shared-memory pipe the consumer's loads go through
+            while (freed = ld_volatile_shared(consumed), upto > freed + ring_steps) __nanosleep(200);
             __threadfence_block();
             const u32 b = done + ps;
             if (worker && b < upto) {
@@ -169,7 +174,7 @@ sha512_long_kernel(const uint8_t *__restrict__ data, const SegDesc *__restrict__
 #pragma unroll
                     for (int j = 0; j < 16; j++) w[j] = 0;       // past this file's end: result is discarded
                 }
-                u64 *slot = ring + (size_t)(b % ring_steps) * 80 * nf + pf;
+                u64 *slot = ring + (size_t)(b % ring_steps) * kLongSlotWords * nf + pf;
 #pragma unroll 1
                 for (int grp = 0; grp < 5; grp++) {
 #pragma unroll

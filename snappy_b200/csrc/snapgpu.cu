@@ -22,6 +22,7 @@
 #include "plan_kernels.cuh"
 #include "runtime.hpp"
 #include "sha512_kernels.cuh"
+#include "sha512_long.cuh"
 
 namespace snapgpu {
 
@@ -84,6 +85,7 @@ struct PlanSlot {
     u32 *d_counter = nullptr;
     cudaEvent_t done = nullptr;
     cudaEvent_t uploaded = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;   // around the long-file kernel on its own stream
     bool in_flight = false;
 };
 
@@ -99,7 +101,7 @@ struct Device {
     int ordinal = -1;
     int sm_count = 0;
     std::mutex mu;
-    cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+    cudaStream_t copy_stream = nullptr, compute_stream = nullptr, long_stream = nullptr;
     PlanSlot slots[kPlanSlots];
     int next_slot = 0;
     // host-buffer pipeline (allocated on first use)
@@ -122,13 +124,15 @@ struct Options {
     std::atomic<long long> sha_variant{0};
     std::atomic<long long> cmp_ctas_per_sm{0};
     std::atomic<long long> time_kernels{1};
+    std::atomic<long long> long_kernel{1};
 };
 
 struct Runtime {
     std::mutex mu;
     std::vector<std::unique_ptr<Device>> devs;
     Options opt;
-    std::atomic<uint64_t> kernel_launches{0}, sha_launches{0}, cmp_launches{0}, h2d_bytes{0}, d2h_bytes{0};
+    std::atomic<uint64_t> kernel_launches{0}, sha_launches{0}, sha_long_launches{0}, cmp_launches{0}, h2d_bytes{0},
+        d2h_bytes{0};
 };
 
 static Runtime &rt() {
@@ -149,6 +153,8 @@ static void destroy_device(Device &D) {
         if (s.d_counter) cudaFree(s.d_counter);
         if (s.done) cudaEventDestroy(s.done);
         if (s.uploaded) cudaEventDestroy(s.uploaded);
+        if (s.fork) cudaEventDestroy(s.fork);
+        if (s.join) cudaEventDestroy(s.join);
     }
     for (int b = 0; b < 2; b++) {
         if (D.d_stage[b]) cudaFree(D.d_stage[b]);
@@ -161,6 +167,7 @@ static void destroy_device(Device &D) {
     for (auto &t : D.cmp_t) { if (t.beg) cudaEventDestroy(t.beg); if (t.end) cudaEventDestroy(t.end); }
     if (D.copy_stream) cudaStreamDestroy(D.copy_stream);
     if (D.compute_stream) cudaStreamDestroy(D.compute_stream);
+    if (D.long_stream) cudaStreamDestroy(D.long_stream);
     D.ordinal = -1;
 }
 
@@ -175,9 +182,13 @@ static int init_device(Device &D, int ordinal) {
                     prop.major, prop.minor);
     SG_CUDA(cudaStreamCreateWithFlags(&D.copy_stream, cudaStreamNonBlocking));
     SG_CUDA(cudaStreamCreateWithFlags(&D.compute_stream, cudaStreamNonBlocking));
+    SG_CUDA(cudaStreamCreateWithFlags(&D.long_stream, cudaStreamNonBlocking));
+    SG_CUDA(cudaFuncSetAttribute(sha512_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytes));
     for (auto &s : D.slots) {
         SG_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         SG_CUDA(cudaEventCreate(&s.uploaded));
+        SG_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+        SG_CUDA(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
         SG_CUDA(cudaMalloc(&s.d_counter, 256));
     }
     for (int b = 0; b < 2; b++) {
@@ -307,11 +318,17 @@ static ShaKernel sha_kernel_for(int variant, bool aligned) {
 // Host half of the launch plan: the `n` descriptors produced by get(i) are streamed into
 // pinned memory in the caller's order and checked; the ordering by length is done on the
 // device (plan_kernels.cuh).  Multi-million-file shards are written by several host threads.
+constexpr uint64_t kLongMinBlocks = 16384;   // 2 MiB: from here on a file may go to the long-file kernel
+constexpr size_t kLongMaxFiles = 256;        // ... if the launch has no more than this many of them
+
 struct PlanInfo {
     uint64_t total_blocks = 0, max_blocks = 0;
     bool aligned = true;
     int bad = 0;            // 1: too large, 2: non-final segment not a multiple of 128
     size_t bad_index = 0;
+    uint64_t max_short_blocks = 0;      // longest item below kLongMinBlocks
+    size_t n_long = 0;                  // items of >= kLongMinBlocks blocks
+    std::vector<u32> long_idx;          // their indices (first kLongMaxFiles + 1)
 };
 
 template <typename Get>
@@ -331,6 +348,12 @@ static void write_descriptors(Get get, size_t n, SegDesc *descs, PlanInfo *info)
             const uint64_t nb = seg_blocks(d.len, d.flags);
             pi.total_blocks += nb;
             pi.max_blocks = std::max(pi.max_blocks, nb);
+            if (nb >= kLongMinBlocks) {
+                if (pi.long_idx.size() <= kLongMaxFiles) pi.long_idx.push_back((u32)i);
+                pi.n_long++;
+            } else {
+                pi.max_short_blocks = std::max(pi.max_short_blocks, nb);
+            }
         }
     };
     if (nthreads == 1) {
@@ -346,24 +369,31 @@ static void write_descriptors(Get get, size_t n, SegDesc *descs, PlanInfo *info)
         info->max_blocks = std::max(info->max_blocks, pi.max_blocks);
         info->aligned = info->aligned && pi.aligned;
         if (pi.bad && !info->bad) { info->bad = pi.bad; info->bad_index = pi.bad_index; }
+        info->n_long += pi.n_long;
+        info->max_short_blocks = std::max(info->max_short_blocks, pi.max_short_blocks);
+        for (u32 i : pi.long_idx)
+            if (info->long_idx.size() <= kLongMaxFiles) info->long_idx.push_back(i);
     }
 }
 
 // Device half: order[] = indices sorted by block count, longest first.  Layout of the plan
-// slot on the device: SegDesc[n] | u32 order[n] | u32 hist[nbuckets].
+// slot (host and device): SegDesc[n] | SegDesc long[kLongMaxFiles] | u32 order[n] | u32 hist[nbuckets].
 struct DevicePlan {
     const SegDesc *descs;
+    const SegDesc *long_descs;
     u32 *order;
     u32 *hist;
 };
 
 static DevicePlan plan_layout(void *d_buf, size_t n) {
     SegDesc *descs = static_cast<SegDesc *>(d_buf);
-    u32 *order = reinterpret_cast<u32 *>(descs + n);
-    return DevicePlan{descs, order, order + n};
+    u32 *order = reinterpret_cast<u32 *>(descs + n + kLongMaxFiles);
+    return DevicePlan{descs, descs + n, order, order + n};
 }
 
-static size_t plan_bytes(size_t n, size_t nbuckets) { return n * (sizeof(SegDesc) + sizeof(u32)) + nbuckets * sizeof(u32); }
+static size_t plan_bytes(size_t n, size_t nbuckets) {
+    return (n + kLongMaxFiles) * sizeof(SegDesc) + n * sizeof(u32) + nbuckets * sizeof(u32);
+}
 
 static int enqueue_length_binning(Device &D, cudaStream_t stream, const DevicePlan &p, size_t n, uint64_t max_blocks) {
     const u32 top = (u32)std::min<uint64_t>(max_blocks, kPlanTopMax);
@@ -401,14 +431,37 @@ static int launch_sha512(Device &D, cudaStream_t stream, const uint8_t *d_data, 
     if (info.bad == 2)
         return fail(SNAPGPU_EINVAL, "non-final segment %zu is not a multiple of 128 bytes", info.bad_index);
     const bool aligned = info.aligned && ((uintptr_t)d_data & 15) == 0;
-    const uint64_t total_blocks = info.total_blocks, max_blocks = info.max_blocks;
+    uint64_t total_blocks = info.total_blocks, max_blocks = info.max_blocks;
     const DevicePlan plan = plan_layout(slot->d_buf, n);
+
+    // The long-file bin: a handful of files far longer than the rest leave the batched kernel
+    // (their descriptors are marked kSegSkip there) and go to sha512_long_kernel, which runs
+    // beside it on its own stream.  With many long files the batched kernel keeps them: it has
+    // the higher throughput, the long kernel only the shorter chain.
+    SegDesc *h_descs = static_cast<SegDesc *>(slot->h_buf);
+    size_t n_long = 0;
+    if (aligned && info.n_long >= 1 && info.n_long <= kLongMaxFiles && R.opt.long_kernel.load()) {
+        n_long = info.n_long;
+        SegDesc *h_long = h_descs + n;
+        for (size_t k = 0; k < n_long; k++) {
+            SegDesc &d = h_descs[info.long_idx[k]];
+            h_long[k] = d;
+            total_blocks -= seg_blocks(d.len, d.flags);
+            d.flags |= kSegSkip;
+        }
+        std::sort(h_long, h_long + n_long, [](const SegDesc &a, const SegDesc &b) {
+            return seg_blocks(a.len, a.flags) > seg_blocks(b.len, b.flags);
+        });
+        max_blocks = info.max_short_blocks;
+    }
+    const size_t n_main = n - n_long;
 
     // upload and binning run on the copy stream, i.e. beside whatever the caller's stream is
     // still hashing; the hashing kernel waits for the finished plan
-    SG_CUDA(cudaMemcpyAsync(slot->d_buf, slot->h_buf, n * sizeof(SegDesc), cudaMemcpyHostToDevice, D.copy_stream));
+    SG_CUDA(cudaMemcpyAsync(slot->d_buf, slot->h_buf, (n + n_long) * sizeof(SegDesc), cudaMemcpyHostToDevice,
+                            D.copy_stream));
     SG_CUDA(cudaMemsetAsync(slot->d_counter, 0, sizeof(u32), D.copy_stream));
-    if ((rc = enqueue_length_binning(D, D.copy_stream, plan, n, max_blocks))) return rc;
+    if (n_main && (rc = enqueue_length_binning(D, D.copy_stream, plan, n, max_blocks))) return rc;
     SG_CUDA(cudaEventRecord(slot->uploaded, D.copy_stream));
     SG_CUDA(cudaStreamWaitEvent(stream, slot->uploaded, 0));
 
@@ -437,8 +490,24 @@ static int launch_sha512(Device &D, cudaStream_t stream, const uint8_t *d_data, 
         tl->prev_end = before.recorded ? before.end : nullptr;
         SG_CUDA(cudaEventRecord(tl->beg, stream));
     }
-    k<<<grid, kShaThreads, 0, stream>>>(d_data, plan.descs, plan.order, (u32)n, d_digests, slot->d_counter, 1u);
-    SG_CUDA(cudaGetLastError());
+    if (n_long) {
+        // everything `stream` has been asked to do so far (the data, a chaining value) comes first
+        SG_CUDA(cudaEventRecord(slot->fork, stream));
+        SG_CUDA(cudaStreamWaitEvent(D.long_stream, slot->fork, 0));
+        const u32 long_grid = (u32)((n_long + kLongFilesPerCta - 1) / kLongFilesPerCta);
+        sha512_long_kernel<<<long_grid, kLongThreads, kLongSmemBytes, D.long_stream>>>(d_data, plan.long_descs, (u32)n_long,
+                                                                                       d_digests);
+        SG_CUDA(cudaGetLastError());
+        SG_CUDA(cudaEventRecord(slot->join, D.long_stream));
+        R.kernel_launches++;
+        R.sha_long_launches++;
+    }
+    if (n_main) {
+        k<<<grid, kShaThreads, 0, stream>>>(d_data, plan.descs, plan.order, (u32)n, d_digests, slot->d_counter, 1u);
+        SG_CUDA(cudaGetLastError());
+        R.kernel_launches++;
+    }
+    if (n_long) SG_CUDA(cudaStreamWaitEvent(stream, slot->join, 0));
     if (tl) {
         SG_CUDA(cudaEventRecord(tl->end, stream));
         tl->pending = true;
@@ -446,7 +515,6 @@ static int launch_sha512(Device &D, cudaStream_t stream, const uint8_t *d_data, 
     }
     SG_CUDA(cudaEventRecord(slot->done, stream));
     slot->in_flight = true;
-    R.kernel_launches++;
     R.sha_launches++;
     if (trace_on()) fprintf(stderr, "[snapgpu] sha512 launch of %zu files enqueued in %.3f ms (host)\n", n, now_ms() - t_plan);
     return 0;
@@ -958,6 +1026,8 @@ int snapgpu_set_option(const char *key, long long value) {
         o.cmp_ctas_per_sm = value;
     } else if (k == "time_kernels") {
         o.time_kernels = value ? 1 : 0;
+    } else if (k == "long_kernel") {
+        o.long_kernel = value ? 1 : 0;
     } else {
         return fail(SNAPGPU_EINVAL, "unknown option %s", key);
     }
@@ -1116,6 +1186,7 @@ void snapgpu_reset_stats(void) {
     auto &R = rt();
     R.kernel_launches = 0;
     R.sha_launches = 0;
+    R.sha_long_launches = 0;
     R.cmp_launches = 0;
     R.h2d_bytes = 0;
     R.d2h_bytes = 0;

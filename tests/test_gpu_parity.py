@@ -18,6 +18,7 @@ def default_options(gpu):
     gpu.set_option("staging_bytes", 256 << 20)
     gpu.set_option("sha_variant", 0)
     gpu.set_option("sha_warps_per_sm", 0)
+    gpu.set_option("long_kernel", 1)
     yield
 
 
@@ -178,6 +179,49 @@ def test_long_file_chain(gpu):
     dg = device.sha512_batch_device(d, off, lengths).cpu().numpy()
     assert dg[0].tobytes() == hashlib.sha512(synth.file_bytes(0, 64 << 20)).digest()
     assert dg[1].tobytes() == hashlib.sha512(synth.file_bytes(1, 100)).digest()
+
+
+def test_long_file_kernel(gpu, oracle):
+    """The long-file bin (sha512_long.cuh): files of >= 2 MiB leave the batched kernel when a launch
+    has at most 256 of them.  Same digests with the bin switched off, and both equal the oracle."""
+    from snappy_b200 import helpers
+    rng = np.random.default_rng(21)
+    MiB = 1 << 20
+    cases = [
+        [3 * MiB + 5],                                                   # one file, one producer lane per block
+        [2 * MiB - 17, 2 * MiB, 2 * MiB + 111, 5 * MiB + 112],           # padding edges around the threshold
+        list(rng.integers(0, 9000, 300)) + [4 * MiB + 1, 2 * MiB + 128, 0, 7 * MiB],
+        [2 * MiB + 64 * i + (i % 3) for i in range(33)],                 # 33 long files: two CTAs, 32 + 1
+        [2 * MiB + 1024 * i for i in range(5)] + list(rng.integers(1, 70000, 64)),   # 5 files: 32 % 5 idle lanes
+    ]
+    for lengths in cases:
+        data, off, ln = pack(lengths, rng)
+        want = oracle.sha512_batch(data, off, ln, 8)
+        gpu.reset_stats()
+        gpu.set_option("long_kernel", 1)
+        got = helpers.sha512_batch(data, off, ln)
+        launches_with = gpu.stats().kernel_launches
+        gpu.set_option("long_kernel", 0)
+        plain = helpers.sha512_batch(data, off, ln)
+        gpu.set_option("long_kernel", 1)
+        assert np.array_equal(got, want), lengths[-4:]
+        assert np.array_equal(plain, want)
+        assert launches_with >= 1
+    # more long files than the bin takes: all stay in the batched kernel
+    lengths = [2 * MiB] * 260
+    data, off, ln = pack(lengths, rng)
+    assert np.array_equal(helpers.sha512_batch(data, off, ln), oracle.sha512_batch(data, off, ln, 16))
+    # a long message streamed in pieces (continuation segments go through the long kernel too)
+    msg = rng.integers(0, 256, 9 * MiB + 77, dtype=np.uint8).tobytes()
+    h = helpers.Sha512Stream()
+    h.Write(msg[: 4 * MiB])
+    h.Write(msg[4 * MiB: 4 * MiB + 100])
+    h.Write(msg[4 * MiB + 100:])
+    assert h.Sum() == hashlib.sha512(msg).digest()
+    # a file larger than the host staging buffer: pieces of 4 MiB, each a long segment
+    gpu.set_option("staging_bytes", 4 * MiB)
+    data, off, ln = pack([11 * MiB + 3, 100, 3 * MiB], rng)
+    assert np.array_equal(helpers.sha512_batch(data, off, ln), oracle.sha512_batch(data, off, ln, 4))
 
 
 # ---- hashes.yaml ---------------------------------------------------------------------------------
