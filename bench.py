@@ -248,6 +248,8 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libsnapgpu has no CPU fallback")
+    from snappy_b200 import numa
+    placement = numa.bind_to_gpu(local_rank)      # before any pinned allocation (first touch)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -403,6 +405,31 @@ def main():
                    "step_ms": c0.elapsed_time(c1) / csteps, "algorithmic_bytes": algo_bytes,
                    "traffic": (ncu_traffic("cmp") or {}).get("dram_bytes"), "traffic_detail": ncu_traffic("cmp"),
                    "peak_source": peaks["_source"]}
+        # end to end: the first 1,000 pairs from pinned host memory through snapgpu_cmp_batch
+        if not args.no_e2e:
+            ne = 1000
+            nbytes_e = int(co[ne - 1] + cl[ne - 1])
+            ha, pa = pinned_array(nbytes_e + 64)
+            hb, pb = pinned_array(nbytes_e + 64)
+            torch.from_numpy(ha)[:nbytes_e].copy_(da[:nbytes_e].cpu())
+            torch.from_numpy(hb)[:nbytes_e].copy_(db[:nbytes_e].cpu())
+            want_eq = eq[:ne]
+            got_eq = helpers.cmp_batch(ha, hb, co[:ne], cl[:ne])
+            assert np.array_equal(got_eq, want_eq), "end-to-end cmp flags differ from the device-resident run"
+            N.reset_stats()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                helpers.cmp_batch(ha, hb, co[:ne], cl[:ne])
+            dte = (time.perf_counter() - t0) / 3
+            se = N.stats()
+            cmp_res["e2e"] = {"value": 2 * int(cl[:ne].sum()) / dte / 1e9, "unit": "GB/s of compared bytes (both streams)",
+                              "pairs": ne, "ms": dte * 1e3, "h2d_bytes_per_step": int(se.h2d_bytes // 3),
+                              "d2h_bytes_per_step": int(se.d2h_bytes // 3),
+                              "bound": "PCIe host-to-device copy of both streams"}
+            launches += int(se.kernel_launches)
+            N.lib().snapgpu_free_pinned(pa)
+            N.lib().snapgpu_free_pinned(pb)
+            del ha, hb
         del da, db
 
     # ---- tail latency: the serial chain of ONE long file (north_star: reported separately) ----
@@ -466,7 +493,8 @@ def main():
         "config": {"workload": desc, "files_per_gpu": int(len(lengths)), "bytes_per_gpu": file_bytes,
                    "blocks_per_gpu": nblocks, "sharding": f"file list sharded over {world} GPU(s), no collective",
                    "cache": "inputs (1.29 GB per GPU) larger than the 126 MB L2; no flush needed",
-                   "sha_variant": int(args.variant or 0)},
+                   "sha_variant": int(args.variant or 0),
+                   "host_placement": placement},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
         "roofline_cmp": cmp_res, "tail_latency": tail, "cpu_baseline": cpu,
     }

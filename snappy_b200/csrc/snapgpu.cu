@@ -318,8 +318,14 @@ static ShaKernel sha_kernel_for(int variant, bool aligned) {
 // Host half of the launch plan: the `n` descriptors produced by get(i) are streamed into
 // pinned memory in the caller's order and checked; the ordering by length is done on the
 // device (plan_kernels.cuh).  Multi-million-file shards are written by several host threads.
-constexpr uint64_t kLongMinBlocks = 16384;   // 2 MiB: from here on a file may go to the long-file kernel
-constexpr size_t kLongMaxFiles = 256;        // ... if the launch has no more than this many of them
+// The long-file bin takes the files whose chain would dominate the launch: at least kLongMinBlocks
+// blocks (128 KiB) AND at least kLongDominance times the launch's blocks per lane -- if there are
+// no more than kLongMaxFiles of them.  Otherwise everything stays in the batched kernel, which has
+// the higher throughput.
+constexpr uint64_t kLongMinBlocks = 1024;
+constexpr uint64_t kLongDominance = 4;
+constexpr size_t kLongMaxFiles = 256;
+constexpr size_t kLongMaxCandidates = 4096;
 
 struct PlanInfo {
     uint64_t total_blocks = 0, max_blocks = 0;
@@ -328,7 +334,7 @@ struct PlanInfo {
     size_t bad_index = 0;
     uint64_t max_short_blocks = 0;      // longest item below kLongMinBlocks
     size_t n_long = 0;                  // items of >= kLongMinBlocks blocks
-    std::vector<u32> long_idx;          // their indices (first kLongMaxFiles + 1)
+    std::vector<u32> long_idx;          // their indices (the first kLongMaxCandidates)
 };
 
 template <typename Get>
@@ -349,7 +355,7 @@ static void write_descriptors(Get get, size_t n, SegDesc *descs, PlanInfo *info)
             pi.total_blocks += nb;
             pi.max_blocks = std::max(pi.max_blocks, nb);
             if (nb >= kLongMinBlocks) {
-                if (pi.long_idx.size() <= kLongMaxFiles) pi.long_idx.push_back((u32)i);
+                if (pi.long_idx.size() < kLongMaxCandidates) pi.long_idx.push_back((u32)i);
                 pi.n_long++;
             } else {
                 pi.max_short_blocks = std::max(pi.max_short_blocks, nb);
@@ -372,7 +378,7 @@ static void write_descriptors(Get get, size_t n, SegDesc *descs, PlanInfo *info)
         info->n_long += pi.n_long;
         info->max_short_blocks = std::max(info->max_short_blocks, pi.max_short_blocks);
         for (u32 i : pi.long_idx)
-            if (info->long_idx.size() <= kLongMaxFiles) info->long_idx.push_back(i);
+            if (info->long_idx.size() < kLongMaxCandidates) info->long_idx.push_back(i);
     }
 }
 
@@ -440,19 +446,30 @@ static int launch_sha512(Device &D, cudaStream_t stream, const uint8_t *d_data, 
     // the higher throughput, the long kernel only the shorter chain.
     SegDesc *h_descs = static_cast<SegDesc *>(slot->h_buf);
     size_t n_long = 0;
-    if (aligned && info.n_long >= 1 && info.n_long <= kLongMaxFiles && R.opt.long_kernel.load()) {
-        n_long = info.n_long;
-        SegDesc *h_long = h_descs + n;
-        for (size_t k = 0; k < n_long; k++) {
-            SegDesc &d = h_descs[info.long_idx[k]];
-            h_long[k] = d;
-            total_blocks -= seg_blocks(d.len, d.flags);
-            d.flags |= kSegSkip;
+    if (aligned && info.n_long >= 1 && info.n_long <= kLongMaxCandidates && R.opt.long_kernel.load()) {
+        const uint64_t lanes = (uint64_t)D.sm_count * kShaThreads;
+        const uint64_t threshold = std::max<uint64_t>(kLongMinBlocks, kLongDominance * (total_blocks / lanes));
+        size_t dominant = 0;
+        for (u32 i : info.long_idx) dominant += seg_blocks(h_descs[i].len, h_descs[i].flags) >= threshold;
+        if (dominant >= 1 && dominant <= kLongMaxFiles) {
+            SegDesc *h_long = h_descs + n;
+            uint64_t max_rest = info.max_short_blocks;
+            for (u32 i : info.long_idx) {
+                SegDesc &d = h_descs[i];
+                const uint64_t nb = seg_blocks(d.len, d.flags);
+                if (nb < threshold) {
+                    max_rest = std::max(max_rest, nb);
+                    continue;
+                }
+                h_long[n_long++] = d;
+                total_blocks -= nb;
+                d.flags |= kSegSkip;
+            }
+            std::sort(h_long, h_long + n_long, [](const SegDesc &a, const SegDesc &b) {
+                return seg_blocks(a.len, a.flags) > seg_blocks(b.len, b.flags);
+            });
+            max_blocks = max_rest;
         }
-        std::sort(h_long, h_long + n_long, [](const SegDesc &a, const SegDesc &b) {
-            return seg_blocks(a.len, a.flags) > seg_blocks(b.len, b.flags);
-        });
-        max_blocks = info.max_short_blocks;
     }
     const size_t n_main = n - n_long;
 
