@@ -492,7 +492,7 @@ def main():
         "files_per_s": world * len(lengths) / (ms_step * 1e-3),
         "config": {"workload": desc, "files_per_gpu": int(len(lengths)), "bytes_per_gpu": file_bytes,
                    "blocks_per_gpu": nblocks, "sharding": f"file list sharded over {world} GPU(s), no collective",
-                   "cache": "inputs (1.29 GB per GPU) larger than the 126 MB L2; no flush needed",
+                   "cache": f"inputs ({file_bytes / 1e9:.2f} GB per GPU) larger than the 126 MB L2; no flush needed",
                    "sha_variant": int(args.variant or 0),
                    "host_placement": placement},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,

@@ -123,6 +123,20 @@ int snapgpu_apparmor_delta(const char *old_path, const char *new_path, const cha
                            char **policies, size_t *npolicies, char **templates,
                            size_t *ntemplates);
 
+/* copyToBuildDir (snappy/build.go:362-418), the step of snappy.Build that stages the source
+ * tree before writeHashes runs: removes an empty build_dir, walks source_dir in filepath.Walk
+ * order skipping shouldExclude names (snappy/build.go:52-83; directories with their subtree),
+ * creates directories with the source's mode, hard-links files and copies what cannot be linked.
+ * Copied files are read ONCE: the bytes go to the build dir and through the SHA-512 kernel in the
+ * same pass, and the digest is kept (keyed by device, inode, size, mtime of the written file) so
+ * that the snapgpu_write_hashes that follows does not read them again.  On error the copy may be
+ * partial, as in the reference.  flags: SNAPGPU_COPY_NO_LINK = never hard-link. */
+#define SNAPGPU_COPY_NO_LINK 1
+int snapgpu_copy_to_build_dir(const char *source_dir, const char *build_dir, int flags);
+int snapgpu_should_exclude(const char *base_name);          /* shouldExclude, 1 = excluded */
+void snapgpu_digest_cache_clear(void);
+void snapgpu_digest_cache_stats(size_t *entries, uint64_t *hits);
+
 void snapgpu_free(void *p);
 
 /* ---- synthetic inputs and instrumentation (bench/test support, not product API) ------ */

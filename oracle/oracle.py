@@ -11,6 +11,7 @@ logic on the hot path:
 * ``streams_equal``     /root/reference/helpers/cmp.go:61-86
 * ``dir_updated``       /root/reference/helpers/cmp.go:97-114
 * ``apparmor_delta``    /root/reference/policy/policy.go:155-167
+* ``copy_to_build_dir`` /root/reference/snappy/build.go:362-418 (``should_exclude``: build.go:52-83)
 
 Third-party code that is NOT under /root/reference and is restated here from its
 published behaviour:
@@ -732,3 +733,66 @@ def write_hashes(build_dir: str, data_tar: str, hasher=None) -> bytes:
         f.write(content)
     os.chmod(out, 0o644)
     return content
+
+
+# ---------------------------------------------------------------------------------------------
+# copyToBuildDir (/root/reference/snappy/build.go:362-418) -- SURVEY.md section 8f, row 2
+# ---------------------------------------------------------------------------------------------
+
+# snappy/build.go:52-83, joined with "|" exactly as the reference does.  Go's regexp differs from
+# Python's in two ways that matter here: `$` matches only at the very end of the text (Python's
+# also matches before a trailing newline) and `{arch}` is a literal; hence \Z and the escapes.
+_SHOULD_EXCLUDE = re.compile("|".join([
+    r"\.snap\Z", r"\.click\Z", r"^\..*\.sw.\Z", r"~\Z", r"^,,", r"^\.[#~]", r"^\.arch-ids\Z", r"^\.arch-inventory\Z",
+    r"^\.bzr\Z", r"^\.bzr-builddeb\Z", r"^\.bzr\.backup\Z", r"^\.bzr\.tags\Z", r"^\.bzrignore\Z", r"^\.cvsignore\Z",
+    r"^\.git\Z", r"^\.gitattributes\Z", r"^\.gitignore\Z", r"^\.gitmodules\Z", r"^\.hg\Z", r"^\.hgignore\Z",
+    r"^\.hgsigs\Z", r"^\.hgtags\Z", r"^\.shelf\Z", r"^\.svn\Z", r"^CVS\Z", r"^DEADJOE\Z", r"^RCS\Z", r"^_MTN\Z",
+    r"^_darcs\Z", r"^\{arch\}\Z",
+]).encode())
+
+
+def should_exclude(basename) -> bool:
+    """shouldExclude (snappy/build.go:52-83) on a base name."""
+    return _SHOULD_EXCLUDE.search(os.fsencode(basename)) is not None
+
+
+def copy_to_build_dir(source_dir: str, build_dir: str, no_link: bool = False) -> None:
+    """copyToBuildDir (snappy/build.go:362-418): Walk order, exclusions, Mkdir with the source's
+    mode, hard link where possible, else open / O_EXCL create / io.Copy.  Raises OSError where Go
+    returns the error."""
+    source = os.fsencode(os.path.abspath(source_dir))
+    build = os.fsencode(build_dir)
+    try:
+        try:
+            os.unlink(build)                       # os.Remove: unlink, then rmdir
+        except (IsADirectoryError, PermissionError):
+            os.rmdir(build)
+    except FileNotFoundError:
+        pass
+
+    def visit(path: bytes, st) -> None:
+        if should_exclude(os.path.basename(path)):
+            return                                  # SkipDir for a directory, skip for a file
+        dest = build + path[len(source):]
+        if stat.S_ISDIR(st.st_mode):
+            os.mkdir(dest, stat.S_IMODE(st.st_mode))
+            for name in sorted(os.listdir(path)):
+                child = path + b"/" + name
+                visit(child, os.lstat(child))
+            return
+        if not no_link:
+            try:
+                os.link(path, dest, follow_symlinks=False)
+                return
+            except OSError:
+                pass
+        with open(path, "rb") as fin:               # os.Open follows symlinks
+            fd = os.open(dest, os.O_WRONLY | os.O_CREAT | os.O_EXCL, stat.S_IMODE(st.st_mode))
+            with os.fdopen(fd, "wb") as fout:
+                while True:
+                    chunk = fin.read(1 << 20)
+                    if not chunk:
+                        break
+                    fout.write(chunk)
+
+    visit(source, os.lstat(source))

@@ -69,6 +69,10 @@ SIGNATURES = {
     "snapgpu_dir_updated": (_i, [_cp, _cp, _cp, _pp, _psz]),
     "snapgpu_apparmor_delta": (_i, [_cp, _cp, _cp, _pp, _psz, _pp, _psz]),
     "snapgpu_free": (None, [_vp]),
+    "snapgpu_copy_to_build_dir": (_i, [_cp, _cp, _i]),
+    "snapgpu_should_exclude": (_i, [_cp]),
+    "snapgpu_digest_cache_clear": (None, []),
+    "snapgpu_digest_cache_stats": (None, [_psz, ctypes.POINTER(ctypes.c_uint64)]),
     "snapgpu_synth_fill_device": (_i, [_i, _vp, _vp, _vp, _sz, _u64, _u64, _vp]),
     "snapgpu_get_stats": (_i, [ctypes.POINTER(Stats)]),
     "snapgpu_reset_stats": (None, []),

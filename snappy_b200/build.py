@@ -2,6 +2,7 @@
 
 * ``writeHashes``   /root/reference/snappy/build.go:216-270
 * ``hashes_yaml``   the same walk, returning the document instead of writing it
+* ``copyToBuildDir`` /root/reference/snappy/build.go:362-418 (+ ``shouldExclude``, build.go:52-83)
 
 The tree walk, the batching of every regular file into one GPU call and the yaml.v2-exact
 emitter all live in libsnapgpu (csrc/host_path.cpp); this module is the binding.
@@ -28,6 +29,23 @@ def _raise(rc: int):
 def writeHashes(buildDir: str, dataTar: str) -> None:
     """Write ``<buildDir>/DEBIAN/hashes.yaml``; the first error aborts, as in the reference."""
     _raise(N.lib().snapgpu_write_hashes(N.fs(buildDir), N.fs(dataTar)))
+
+
+def copyToBuildDir(sourceDir: str, buildDir: str, no_link: bool = False) -> None:
+    """copyToBuildDir (/root/reference/snappy/build.go:362-418).  Files that have to be copied are
+    read once, for the copy and for the SHA-512 that the following writeHashes needs."""
+    _raise(N.lib().snapgpu_copy_to_build_dir(N.fs(sourceDir), N.fs(buildDir), 1 if no_link else 0))
+
+
+def shouldExclude(basename: str) -> bool:
+    """shouldExclude (/root/reference/snappy/build.go:52-83)."""
+    return bool(N.lib().snapgpu_should_exclude(N.fs(basename)))
+
+
+def digest_cache_stats() -> tuple[int, int]:
+    entries, hits = ctypes.c_size_t(), ctypes.c_uint64()
+    N.lib().snapgpu_digest_cache_stats(ctypes.byref(entries), ctypes.byref(hits))
+    return entries.value, hits.value
 
 
 def hashes_yaml(buildDir: str, dataTar: str) -> bytes:

@@ -210,8 +210,14 @@ unsigned packer_threads(size_t nfiles) {
 // threads straight into their 16-byte aligned slots of a pinned buffer, and while the GPU
 // hashes batch k (one sha512_host_segments call) the threads already pack batch k+1 into the
 // other buffer.  size_hint (optional) carries the walk's lstat sizes so files are not stat'ed twice.
+// sink (optional): called once per file while its bytes sit in the pinned buffer -- from several
+// threads, concurrently with the GPU call of that batch -- so that a caller can write the same
+// bytes somewhere (copyToBuildDir) without reading the file a second time.  bytes == nullptr means
+// the file did not go through a batch (larger than a batch, or it grew): the sink copies it itself.
+typedef std::function<int(size_t index, const uint8_t *bytes, uint64_t len)> FileSink;
+
 int hash_files(const std::vector<std::string> &paths, std::vector<uint8_t> &digests,
-               const std::vector<int64_t> *size_hint = nullptr) {
+               const std::vector<int64_t> *size_hint = nullptr, const FileSink *sink = nullptr) {
     digests.assign(paths.size() * 64, 0);
     if (paths.empty()) return 0;
     int rc = ensure_init();
@@ -313,6 +319,7 @@ int hash_files(const std::vector<std::string> &paths, std::vector<uint8_t> &dige
         uint8_t *buf = S.ring[bi & 1];
         if (B.streamed) {
             rc = stream_file(paths[B.first], buf, cap, &digests[64 * B.first]);
+            if (!rc && sink) rc = (*sink)(B.first, nullptr, 0);
             continue;
         }
         std::vector<PackedFile> &pf = packed[bi & 1];
@@ -325,7 +332,27 @@ int hash_files(const std::vector<std::string> &paths, std::vector<uint8_t> &dige
         segs.clear();
         for (const PackedFile &f : pf) segs.push_back(HostSeg{f.off, f.grew ? 0 : f.len, 0, 0});
         out.resize(segs.size() * 64);
-        if ((rc = sha512_host_segments(buf, segs.data(), segs.size(), out.data()))) break;
+        // the sink reads the same pinned bytes the GPU copy engine reads: it runs beside the GPU call
+        std::vector<int> sink_rc;
+        std::vector<std::string> sink_err;
+        std::thread sink_thread;
+        if (sink) {
+            sink_rc.assign(pf.size(), 0);
+            sink_err.resize(pf.size());
+            sink_thread = std::thread([&]() {
+                parallel_for(pf.size(), [&](size_t k) {
+                    const PackedFile &f = pf[k];
+                    sink_rc[k] = f.grew ? (*sink)(f.index, nullptr, 0) : (*sink)(f.index, buf + f.off, f.len);
+                    if (sink_rc[k]) sink_err[k] = snapgpu_last_error();
+                });
+            });
+        }
+        rc = sha512_host_segments(buf, segs.data(), segs.size(), out.data());
+        if (sink_thread.joinable()) sink_thread.join();
+        if (rc) break;
+        for (size_t k = 0; k < sink_rc.size() && !rc; k++)
+            if (sink_rc[k]) rc = fail(sink_rc[k], "%s", sink_err[k].c_str());
+        if (rc) break;
         if (getenv("SNAPGPU_TRACE"))
             fprintf(stderr, "[snapgpu] batch %zu: %zu files, waited %.2f ms for the packer, GPU call %.2f ms\n", bi, pf.size(),
                     tb1 - tb0, wall_ms() - tb1);
@@ -997,7 +1024,51 @@ struct TreeEntry {
     mode_t mode;
     off_t size;
     bool regular;
+    dev_t dev = 0;          // identity of the file at lstat time (digest cache key)
+    ino_t ino = 0;
+    struct timespec mtime = {0, 0};
 };
+
+// ------------------------------------------------------------------------------------------
+// digest cache: SHA-512 of files this library wrote itself (copyToBuildDir reads every copied
+// file once, for the copy and for the hash); writeHashes takes a cached digest only if device,
+// inode, size and mtime of the file are still what they were when it was written.
+// ------------------------------------------------------------------------------------------
+
+struct CachedDigest {
+    off_t size;
+    struct timespec mtime;
+    uint8_t digest[64];
+};
+struct DigestCache {
+    std::mutex mu;
+    std::map<std::pair<dev_t, ino_t>, CachedDigest> map;
+    uint64_t hits = 0;
+};
+DigestCache &digest_cache() {
+    static DigestCache c;
+    return c;
+}
+void cache_put(const struct stat &st, const uint8_t digest[64]) {
+    CachedDigest d;
+    d.size = st.st_size;
+    d.mtime = st.st_mtim;
+    memcpy(d.digest, digest, 64);
+    DigestCache &C = digest_cache();
+    std::lock_guard<std::mutex> lock(C.mu);
+    C.map[std::make_pair(st.st_dev, st.st_ino)] = d;
+}
+bool cache_get(const TreeEntry &e, uint8_t digest[64]) {
+    DigestCache &C = digest_cache();
+    std::lock_guard<std::mutex> lock(C.mu);
+    auto it = C.map.find(std::make_pair(e.dev, e.ino));
+    if (it == C.map.end()) return false;
+    const CachedDigest &d = it->second;
+    if (d.size != e.size || d.mtime.tv_sec != e.mtime.tv_sec || d.mtime.tv_nsec != e.mtime.tv_nsec) return false;
+    memcpy(digest, d.digest, 64);
+    C.hits++;
+    return true;
+}
 
 // filepath.Walk: pre-order, names of each directory sorted bytewise, Lstat.
 // The children of one directory are lstat'ed through its descriptor (fstatat), and at the top
@@ -1063,7 +1134,12 @@ int walk_children(const std::string &dir, const std::string &rel, mode_t dir_mod
         const std::string crel = rel + "/" + names[i];
         const struct stat &st = sts[i];
         const bool skip = crel.compare(0, 7, "/DEBIAN") == 0;     // prefix test (build.go:229)
-        if (!skip) out.push_back(TreeEntry{crel.substr(1), child, st.st_mode, st.st_size, S_ISREG(st.st_mode)});
+        if (!skip) {
+            out.push_back(TreeEntry{crel.substr(1), child, st.st_mode, st.st_size, S_ISREG(st.st_mode)});
+            out.back().dev = st.st_dev;
+            out.back().ino = st.st_ino;
+            out.back().mtime = st.st_mtim;
+        }
         if (S_ISDIR(st.st_mode)) {
             if (!sub.empty()) {
                 if (sub_rc[k]) return fail(sub_rc[k], "%s", sub_err[k].c_str());
@@ -1162,23 +1238,36 @@ int build_hashes_yaml(const std::string &build_dir, const std::string &data_tar,
     const double t0 = wall_ms();
     int rc = collect_tree(build_dir, entries);
     if (rc) return rc;
+    // digests: archive first, then one per regular entry in walk order; entries this library
+    // copied into place itself (copyToBuildDir) come from the digest cache, the rest are hashed
+    size_t nreg = 0;
+    for (const TreeEntry &e : entries) nreg += e.regular;
+    std::vector<uint8_t> digests((nreg + 1) * 64, 0);
     std::vector<std::string> paths;
     std::vector<int64_t> sizes;
+    std::vector<size_t> slot_of;                         // digest slot of paths[k]
     paths.push_back(data_tar);                           // archive-sha512 first (build.go:222)
     sizes.push_back(-1);
+    slot_of.push_back(0);
+    size_t slot = 1;
     for (const TreeEntry &e : entries)
         if (e.regular) {
-            paths.push_back(e.path);
-            sizes.push_back((int64_t)e.size);            // the walk's lstat: no second stat
+            if (!cache_get(e, &digests[64 * slot])) {
+                paths.push_back(e.path);
+                sizes.push_back((int64_t)e.size);        // the walk's lstat: no second stat
+                slot_of.push_back(slot);
+            }
+            slot++;
         }
-    std::vector<uint8_t> digests;
+    std::vector<uint8_t> fresh;
     const double t1 = wall_ms();
-    if ((rc = hash_files(paths, digests, &sizes))) return rc;
+    if ((rc = hash_files(paths, fresh, &sizes))) return rc;
+    for (size_t k = 0; k < paths.size(); k++) memcpy(&digests[64 * slot_of[k]], &fresh[64 * k], 64);
     const double t2 = wall_ms();
-    rc = emit_hashes_yaml(entries, digests.data(), paths.size(), yaml);
+    rc = emit_hashes_yaml(entries, digests.data(), nreg + 1, yaml);
     if (getenv("SNAPGPU_TRACE"))
-        fprintf(stderr, "[snapgpu] writeHashes: walk %.2f ms (%zu entries), pack+hash %.2f ms (%zu files), yaml %.2f ms\n",
-                t1 - t0, entries.size(), t2 - t1, paths.size(), wall_ms() - t2);
+        fprintf(stderr, "[snapgpu] writeHashes: walk %.2f ms (%zu entries), pack+hash %.2f ms (%zu files, %zu from the digest cache), yaml %.2f ms\n",
+                t1 - t0, entries.size(), t2 - t1, paths.size(), nreg + 1 - paths.size(), wall_ms() - t2);
     return rc;
 }
 
@@ -1232,6 +1321,192 @@ int dir_updated(const std::string &dir_a, const std::string &dir_b, const std::s
     if (rc) return rc;
     for (size_t i = 0; i < jobs.size(); i++)
         if (!jobs[i].equal) updated->push_back(pfx + job_names[i]);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// copyToBuildDir (snappy/build.go:362-418), the caller-side neighbour of writeHashes
+// (SURVEY.md section 8f, row 2): every file that has to be copied (not hard-linked) is read ONCE
+// into the pinned ring -- the same bytes are written to the build dir by the packer threads and
+// hashed by the GPU -- and its digest is remembered for the writeHashes that follows.
+// ------------------------------------------------------------------------------------------
+
+// shouldExclude (snappy/build.go:52-83) applied to a base name.  Go's regexp: `.` does not match
+// a newline and `$` matches only at the very end of the text.
+bool should_exclude(const std::string &b) {
+    const size_t n = b.size();
+    auto ends_with = [&](const char *suf) {
+        const size_t m = strlen(suf);
+        return n >= m && b.compare(n - m, m, suf) == 0;
+    };
+    if (ends_with(".snap") || ends_with(".click") || ends_with("~")) return true;
+    if (n >= 2 && b[0] == ',' && b[1] == ',') return true;                       // ^,,
+    if (n >= 2 && b[0] == '.' && (b[1] == '#' || b[1] == '~')) return true;      // ^\.[#~]
+    if (n >= 5 && b[0] == '.' && b.compare(n - 4, 3, ".sw") == 0 && b[n - 1] != '\n' &&
+        b.find('\n', 1) >= n - 4)                                                // ^\..*\.sw.$
+        return true;
+    static const char *const exact[] = {
+        ".arch-ids", ".arch-inventory", ".bzr", ".bzr-builddeb", ".bzr.backup", ".bzr.tags", ".bzrignore",
+        ".cvsignore", ".git", ".gitattributes", ".gitignore", ".gitmodules", ".hg", ".hgignore", ".hgsigs",
+        ".hgtags", ".shelf", ".svn", "CVS", "DEADJOE", "RCS", "_MTN", "_darcs", "{arch}", nullptr};
+    for (int i = 0; exact[i]; i++)
+        if (b == exact[i]) return true;
+    return false;
+}
+
+// filepath.Clean on an absolute or relative slash path
+std::string path_clean(const std::string &p) {
+    const bool rooted = !p.empty() && p[0] == '/';
+    std::vector<std::string> parts;
+    size_t i = 0;
+    while (i <= p.size()) {
+        size_t j = p.find('/', i);
+        if (j == std::string::npos) j = p.size();
+        const std::string part = p.substr(i, j - i);
+        if (part == "..") {
+            if (!parts.empty() && parts.back() != "..") parts.pop_back();
+            else if (!rooted) parts.push_back("..");
+        } else if (!part.empty() && part != ".") {
+            parts.push_back(part);
+        }
+        i = j + 1;
+    }
+    std::string out = rooted ? "/" : "";
+    for (size_t k = 0; k < parts.size(); k++) out += (k ? "/" : "") + parts[k];
+    return out.empty() ? "." : out;
+}
+
+std::string path_abs(const std::string &p) {           // filepath.Abs
+    if (!p.empty() && p[0] == '/') return path_clean(p);
+    char cwd[4096];
+    if (!getcwd(cwd, sizeof cwd)) return path_clean(p);
+    return path_clean(std::string(cwd) + "/" + p);
+}
+
+std::string base_name(const std::string &p) {           // filepath.Base of a cleaned path
+    if (p == "/") return "/";
+    const size_t k = p.rfind('/');
+    return k == std::string::npos ? p : p.substr(k + 1);
+}
+
+struct CopyAction {
+    std::string src, dest;
+    struct stat st;          // lstat of the source
+};
+
+// The Walk of copyToBuildDir: pre-order, sorted names, Lstat; excluded names are skipped
+// (directories with their whole subtree).  A directory that cannot be read, or an entry that
+// cannot be lstat'ed, is the error Walk hands to the callback and the callback returns.
+int copy_walk(const std::string &src, const std::string &dest, const struct stat &st, std::vector<CopyAction> &out) {
+    if (should_exclude(base_name(src))) return 0;
+    out.push_back(CopyAction{src, dest, st});
+    if (!S_ISDIR(st.st_mode)) return 0;
+    DIR *d = opendir(src.c_str());
+    if (!d) return fail(SNAPGPU_EIO, "%s", go_path_error("open", src, errno).c_str());
+    std::vector<std::string> names;
+    while (struct dirent *e = readdir(d)) {
+        if (!strcmp(e->d_name, ".") || !strcmp(e->d_name, "..")) continue;
+        names.emplace_back(e->d_name);
+    }
+    std::sort(names.begin(), names.end());
+    const int dfd = dirfd(d);
+    std::vector<struct stat> sts(names.size());
+    for (size_t i = 0; i < names.size(); i++)
+        if (fstatat(dfd, names[i].c_str(), &sts[i], AT_SYMLINK_NOFOLLOW) != 0) {
+            const int e = errno;
+            closedir(d);
+            return fail(SNAPGPU_EIO, "%s", go_path_error("lstat", src + "/" + names[i], e).c_str());
+        }
+    closedir(d);
+    for (size_t i = 0; i < names.size(); i++) {
+        int rc = copy_walk(src + "/" + names[i], dest + "/" + names[i], sts[i], out);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int write_all(int fd, const uint8_t *p, uint64_t n) {
+    while (n) {
+        ssize_t w = ::write(fd, p, n);
+        if (w < 0) {
+            if (errno == EINTR) continue;
+            return -1;
+        }
+        p += w;
+        n -= (uint64_t)w;
+    }
+    return 0;
+}
+
+int copy_to_build_dir(const std::string &source_in, const std::string &build_dir, int flags) {
+    const std::string source = path_abs(source_in);
+    // os.Remove(buildDir): a leftover empty directory (or file) goes away, "not there" is fine
+    if (unlink(build_dir.c_str()) != 0) {
+        const int e1 = errno;
+        if (rmdir(build_dir.c_str()) != 0) {
+            const int e2 = errno;
+            const int err = e2 != ENOTDIR ? e2 : e1;
+            if (err != ENOENT) return fail(SNAPGPU_EIO, "%s", go_path_error("remove", build_dir, err).c_str());
+        }
+    }
+    struct stat root;
+    if (lstat(source.c_str(), &root) != 0) return fail(SNAPGPU_EIO, "%s", go_path_error("lstat", source, errno).c_str());
+    std::vector<CopyAction> actions;
+    int rc = copy_walk(source, build_dir, root, actions);
+    if (rc) return rc;
+
+    // directories, then links; what cannot be linked is copied below
+    std::vector<size_t> to_copy;
+    for (size_t i = 0; i < actions.size(); i++) {
+        const CopyAction &a = actions[i];
+        if (S_ISDIR(a.st.st_mode)) {
+            if (mkdir(a.dest.c_str(), a.st.st_mode & 07777) != 0)
+                return fail(SNAPGPU_EIO, "%s", go_path_error("mkdir", a.dest, errno).c_str());
+        } else if ((flags & SNAPGPU_COPY_NO_LINK) || link(a.src.c_str(), a.dest.c_str()) != 0) {
+            to_copy.push_back(i);
+        }
+    }
+    if (to_copy.empty()) return 0;
+
+    std::vector<std::string> paths;
+    std::vector<int64_t> sizes;
+    for (size_t i : to_copy) {
+        paths.push_back(actions[i].src);
+        sizes.push_back(S_ISREG(actions[i].st.st_mode) ? (int64_t)actions[i].st.st_size : 0);
+    }
+    std::vector<struct stat> written(to_copy.size());
+    FileSink sink = [&](size_t k, const uint8_t *bytes, uint64_t len) -> int {
+        const CopyAction &a = actions[to_copy[k]];
+        int out = ::open(a.dest.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_CLOEXEC, a.st.st_mode & 07777);
+        if (out < 0) return fail(SNAPGPU_EIO, "%s", go_path_error("open", a.dest, errno).c_str());
+        int err = 0;
+        if (bytes) {
+            if (write_all(out, bytes, len) != 0) err = errno;
+        } else {                                   // did not pass through a batch: plain io.Copy
+            int in = ::open(a.src.c_str(), O_RDONLY | O_CLOEXEC);
+            if (in < 0) {
+                err = errno;
+                ::close(out);
+                return fail(SNAPGPU_EIO, "%s", go_path_error("open", a.src, err).c_str());
+            }
+            std::vector<uint8_t> buf(1 << 20);
+            for (;;) {
+                ssize_t r = ::read(in, buf.data(), buf.size());
+                if (r < 0 && errno == EINTR) continue;
+                if (r < 0) { err = errno; break; }
+                if (r == 0) break;
+                if (write_all(out, buf.data(), (uint64_t)r) != 0) { err = errno; break; }
+            }
+            ::close(in);
+        }
+        if (!err && fstat(out, &written[k]) != 0) err = errno;
+        if (::close(out) != 0 && !err) err = errno;
+        if (err) return fail(SNAPGPU_EIO, "%s", go_path_error("write", a.dest, err).c_str());
+        return 0;
+    };
+    std::vector<uint8_t> digests;
+    if ((rc = hash_files(paths, digests, &sizes, &sink))) return rc;
+    for (size_t k = 0; k < to_copy.size(); k++) cache_put(written[k], &digests[64 * k]);
     return 0;
 }
 
@@ -1340,6 +1615,27 @@ int snapgpu_dir_updated(const char *dir_a, const char *dir_b, const char *pfx, c
     int rc = dir_updated(clean_dir(dir_a), clean_dir(dir_b), pfx ? pfx : "", &up);
     if (rc) return rc;
     return pack_names(up, names, count);
+}
+
+int snapgpu_copy_to_build_dir(const char *source_dir, const char *build_dir, int flags) {
+    if (!source_dir || !build_dir) return fail(SNAPGPU_EINVAL, "null argument");
+    return copy_to_build_dir(source_dir, build_dir, flags);
+}
+
+int snapgpu_should_exclude(const char *base_name_) { return base_name_ && should_exclude(base_name_) ? 1 : 0; }
+
+void snapgpu_digest_cache_clear(void) {
+    DigestCache &C = digest_cache();
+    std::lock_guard<std::mutex> lock(C.mu);
+    C.map.clear();
+    C.hits = 0;
+}
+
+void snapgpu_digest_cache_stats(size_t *entries, uint64_t *hits) {
+    DigestCache &C = digest_cache();
+    std::lock_guard<std::mutex> lock(C.mu);
+    if (entries) *entries = C.map.size();
+    if (hits) *hits = C.hits;
 }
 
 int snapgpu_apparmor_delta(const char *old_path, const char *new_path, const char *prefix, char **policies,

@@ -412,3 +412,50 @@ def test_native_kernels_ran(gpu):
     """The numbers above came from this library's kernels, not from a fallback."""
     s = gpu.stats()
     assert s.sha512_launches > 0 and s.cmp_launches > 0 and s.kernel_launches >= s.sha512_launches + s.cmp_launches
+
+
+# ---- copyToBuildDir fused with hashing (SURVEY.md 8f row 2; snappy/build.go:362-418) -----------------
+
+def test_copy_to_build_dir_fused_with_hashing(gpu, oracle, tmp_path):
+    """TestCopyActuallyCopies (snappy/build_test.go:302-312) with the copy path forced: the copied tree
+    equals the oracle's, and the writeHashes that follows takes every copied file's digest from the
+    cache (one read per file for copy + hash) yet emits the document the oracle emits."""
+    from snappy_b200 import build
+    from test_host_logic import make_source_tree, snapshot
+    rng = np.random.default_rng(33)
+    src = tmp_path / "src"
+    make_source_tree(src)
+    for i in range(40):
+        (src / "lib" / f"blob{i:02d}").write_bytes(rng.integers(0, 256, int(rng.integers(0, 50_000)), dtype=np.uint8).tobytes())
+    (src / "lib" / "big.bin").write_bytes(rng.integers(0, 256, 3_000_001, dtype=np.uint8).tobytes())
+    got, want = tmp_path / "got", tmp_path / "want"
+    gpu.lib().snapgpu_digest_cache_clear()
+    build.copyToBuildDir(str(src), str(got), no_link=True)
+    oracle.copy_to_build_dir(str(src), str(want), no_link=True)
+    assert snapshot(got) == snapshot(want)
+    assert snapshot(got)["bin/hello-world"][3] is False          # really copied
+    nfiles = sum(1 for v in snapshot(got).values() if v[0] == "f")
+    entries, hits = build.digest_cache_stats()
+    assert entries == nfiles and hits == 0
+    tar = tmp_path / "data.tar.gz"
+    tar.write_bytes(b"not really a tarball")
+    doc = build.hashes_yaml(str(got), str(tar))
+    assert doc == oracle.write_hashes(str(want), str(tar))
+    assert build.digest_cache_stats()[1] == nfiles               # nothing was read a second time
+    # a file changed after the copy is hashed again (size or mtime no longer match)
+    victim = got / "lib" / "blob07"
+    body = bytearray(victim.read_bytes() or b"x")
+    body[0] ^= 0xFF
+    victim.write_bytes(bytes(body))
+    os.utime(victim, ns=(1, 1))
+    (want / "lib" / "blob07").write_bytes(bytes(body))
+    assert build.hashes_yaml(str(got), str(tar)) == oracle.write_hashes(str(want), str(tar))
+    # files larger than a packer batch are copied by the streaming path
+    gpu.set_option("staging_bytes", 1 << 20)
+    got2 = tmp_path / "got2"
+    build.copyToBuildDir(str(src), str(got2), no_link=True)
+    want2 = tmp_path / "want2"
+    oracle.copy_to_build_dir(str(src), str(want2), no_link=True)
+    assert snapshot(got2) == snapshot(want2)
+    assert build.hashes_yaml(str(got2), str(tar)) == oracle.write_hashes(str(want2), str(tar))
+    gpu.lib().snapgpu_digest_cache_clear()

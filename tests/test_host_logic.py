@@ -182,3 +182,78 @@ def test_chunker_covers_every_byte_once(native):
             begin = int(r[:, 1].min()) // 16 * 16
             end = int((r[:, 1] + r[:, 2]).max())
             assert end - begin <= cap
+
+
+# ---- copyToBuildDir (snappy/build.go:362-418): host logic that needs no GPU ---------------------
+
+EXCLUDE_CASES = ["foo.snap", "foo.click", ".foo.swp", "..swp", ".swp", "foo~", "~", ",,x", ",x", ".#lock", ".~tmp",
+                 ".bzr", ".bzrx", "x.bzr", ".git", ".gitignore", ".gitfoo", "CVS", "CVS2", "DEADJOE", "RCS", "_MTN",
+                 "_darcs", "{arch}", "arch", ".hgtags", ".shelf", ".svn", ".arch-ids", "foo.snap.txt", "snap",
+                 ".a.swo", ".a.sw", "a.swp", "foo.click~", ".bzr.backup", ".bzr.tags", ".bzr-builddeb", "normal.txt",
+                 ".x\n.swp", ".x.sw\n", "foo~\n", "README"]
+
+
+def test_should_exclude_matches_oracle(native, oracle):
+    from snappy_b200 import build
+    for name in EXCLUDE_CASES:
+        assert build.shouldExclude(name) == oracle.should_exclude(name), repr(name)
+    assert build.shouldExclude("foo~") and build.shouldExclude(".bzr") and not build.shouldExclude("README")
+
+
+def snapshot(root):
+    out = {}
+    for dirpath, dirnames, filenames in os.walk(root):
+        for n in dirnames + filenames:
+            p = os.path.join(dirpath, n)
+            st = os.lstat(p)
+            rel = os.path.relpath(p, root)
+            kind = "d" if stat.S_ISDIR(st.st_mode) else "l" if stat.S_ISLNK(st.st_mode) else "f"
+            body = os.readlink(p) if kind == "l" else (open(p, "rb").read() if kind == "f" else None)
+            out[rel] = (kind, stat.S_IMODE(st.st_mode), body, st.st_nlink > 1 if kind == "f" else None)
+    return out
+
+
+def make_source_tree(root):
+    """makeExampleSnapSourceDir-like tree plus what the copy tests add (snappy/build_test.go:294-345)."""
+    (root / "meta").mkdir(parents=True)
+    (root / "meta" / "package.yaml").write_text("name: hello\n")
+    (root / "bin").mkdir()
+    (root / "bin" / "hello-world").write_text("#!/bin/sh\necho hello\n")
+    os.chmod(root / "bin" / "hello-world", 0o755)
+    (root / "bin" / "empty").write_bytes(b"")
+    os.symlink("hello-world", root / "bin" / "link")
+    (root / "foo~").write_text("hi")                       # TestCopyExcludesBackups
+    (root / ".bzr").mkdir()                                # TestCopyExcludesWholeDirs
+    (root / ".bzr" / "foo").write_text("hi")
+    (root / "lib").mkdir(mode=0o750)
+    (root / "lib" / "data.bin").write_bytes(bytes(range(256)) * 40)
+    (root / "lib" / "x.click").write_text("excluded")
+    os.chmod(root / "lib", 0o750)
+
+
+def test_copy_to_build_dir_links_like_the_oracle(native, oracle, tmp_path):
+    """TestCopyCopies / TestCopyExcludesBackups / TestCopyExcludesWholeDirs: same file system, so every
+    file is hard-linked and no GPU is needed."""
+    from snappy_b200 import build
+    src = tmp_path / "src"
+    make_source_tree(src)
+    got, want = tmp_path / "got", tmp_path / "want"
+    got.mkdir()                                            # an empty target is removed and re-created
+    build.copyToBuildDir(str(src), str(got))
+    oracle.copy_to_build_dir(str(src), str(want))
+    assert snapshot(got) == snapshot(want)
+    assert "foo~" not in snapshot(got) and ".bzr" not in snapshot(got) and "lib/x.click" not in snapshot(got)
+    assert snapshot(got)["bin/hello-world"][3] is True     # linked, not copied
+    # a non-empty target is an error in both (os.Remove fails, build.go:368-372)
+    with pytest.raises(OSError):
+        build.copyToBuildDir(str(src), str(got))
+    with pytest.raises(OSError):
+        oracle.copy_to_build_dir(str(src), str(want))
+    # a missing source is the Walk error
+    with pytest.raises(OSError):
+        build.copyToBuildDir(str(tmp_path / "nope"), str(tmp_path / "t2"))
+    # an excluded source directory copies nothing at all
+    bak = tmp_path / "tree~"
+    make_source_tree(bak)
+    build.copyToBuildDir(str(bak), str(tmp_path / "t3"))
+    assert not (tmp_path / "t3").exists()

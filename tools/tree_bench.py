@@ -75,6 +75,30 @@ for cfg in configs:
            "yaml_bytes": len(doc), "yaml_identical_to_oracle": doc == want,
            "packer_threads": int(os.environ.get("SNAPGPU_PACK_THREADS", "0")) or min(16, os.cpu_count() or 1)}
     assert doc == want, "hashes.yaml differs from the oracle"
+    # build staging: copyToBuildDir with the copy path forced, then writeHashes
+    stage = base / (cfg + "_stage")
+    fused_best = 1e9
+    for _ in range(2):
+        if stage.exists():
+            shutil.rmtree(stage)
+        N.lib().snapgpu_digest_cache_clear()
+        t0 = time.perf_counter()
+        build.copyToBuildDir(str(root), str(stage), no_link=True)
+        t_copy = time.perf_counter() - t0
+        doc2 = build.hashes_yaml(str(stage), tar)
+        fused_best = min(fused_best, time.perf_counter() - t0)
+    hits = build.digest_cache_stats()[1]
+    # the staged tree has no DEBIAN/ yet at copy time, so its document is the source tree's
+    assert doc2 == want, "hashes.yaml of the staged tree differs from the oracle"
+    shutil.rmtree(stage)
+    N.lib().snapgpu_digest_cache_clear()
+    t0 = time.perf_counter()
+    O.copy_to_build_dir(str(root), str(stage), no_link=True)
+    cpu_copy_s = time.perf_counter() - t0
+    shutil.rmtree(stage)
+    row.update({"gpu_copy_then_write_hashes_ms": fused_best * 1e3, "gpu_copy_part_ms": t_copy * 1e3,
+                "digest_cache_hits": int(hits), "cpu_oracle_copy_ms": cpu_copy_s * 1e3,
+                "cpu_copy_plus_sha512sum_loop_ms": (cpu_copy_s + cpu_hash_s) * 1e3})
     print(json.dumps(row), flush=True)
     if out:
         out.write(json.dumps(row) + "\n")
