@@ -73,6 +73,17 @@ int snapgpu_sha512_batch(const uint8_t *data, const uint64_t *offsets, const uin
 int snapgpu_sha512_stream(uint8_t state[64], int first, const uint8_t *data, uint64_t len,
                           uint64_t prefix_bytes, int final);
 
+/* The same as an object with the method set of Go's hash.Hash, for io.Copy(hasher, r)
+ * (helpers/helpers.go:195-196) or io.MultiWriter(tarball, hasher) while data.tar.gz is being
+ * written (clickdeb/deb.go:360-366 -> snappy/build.go:222): Write gathers bytes in pinned
+ * memory and hashes each full 4 MiB piece on a worker thread while the caller goes on writing;
+ * Sum returns the digest of everything written so far without disturbing the state. */
+typedef struct snapgpu_hasher snapgpu_hasher;
+snapgpu_hasher *snapgpu_hasher_new(void);                                     /* sha512.New()  */
+int snapgpu_hasher_write(snapgpu_hasher *h, const uint8_t *p, size_t n);      /* Write         */
+int snapgpu_hasher_sum(snapgpu_hasher *h, uint8_t digest[64]);                /* Sum(nil)      */
+void snapgpu_hasher_free(snapgpu_hasher *h);
+
 /* Replaces streamsEqual / bytes.Equal (helpers/cmp.go:61-86) for `npairs` pairs whose sizes
  * were already found equal on the host (helpers/cmp.go:54).  Pair i is a[off..off+len) vs
  * b[off..off+len).  equal[i] = 1 if identical, else 0. */

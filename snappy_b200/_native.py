@@ -69,6 +69,10 @@ SIGNATURES = {
     "snapgpu_dir_updated": (_i, [_cp, _cp, _cp, _pp, _psz]),
     "snapgpu_apparmor_delta": (_i, [_cp, _cp, _cp, _pp, _psz, _pp, _psz]),
     "snapgpu_free": (None, [_vp]),
+    "snapgpu_hasher_new": (_vp, []),
+    "snapgpu_hasher_write": (_i, [_vp, _vp, _sz]),
+    "snapgpu_hasher_sum": (_i, [_vp, _vp]),
+    "snapgpu_hasher_free": (None, [_vp]),
     "snapgpu_copy_to_build_dir": (_i, [_cp, _cp, _i]),
     "snapgpu_should_exclude": (_i, [_cp]),
     "snapgpu_digest_cache_clear": (None, []),

@@ -1325,6 +1325,59 @@ int dir_updated(const std::string &dir_a, const std::string &dir_b, const std::s
 }
 
 // ------------------------------------------------------------------------------------------
+// hash.Hash-shaped streaming hasher: what `io.Copy(hasher, r)` of
+// helpers.Sha512sum (helpers/helpers.go:195-196) or an io.MultiWriter(tarball, hasher) drives.
+// Writes are gathered in one of two pinned buffers; a full buffer is hashed as a continuation
+// segment by a worker thread while the caller fills the other, so the writer only ever waits
+// when the serial chain on the GPU is slower than the producer of the bytes.
+// ------------------------------------------------------------------------------------------
+
+constexpr size_t kHasherBuffer = 4u << 20;      // multiple of 128
+
+}  // namespace
+}  // namespace snapgpu
+
+struct snapgpu_hasher {
+    uint8_t *buf[2] = {nullptr, nullptr};
+    size_t used = 0;
+    int fill = 0;
+    uint8_t state[64];
+    bool first = true;              // nothing hashed yet: the next segment starts from the IV
+    uint64_t prefix = 0;            // bytes already handed to the GPU
+    std::thread worker;
+    int worker_rc = 0;
+    std::string worker_err;
+};
+
+namespace snapgpu {
+namespace {
+
+int hasher_wait(snapgpu_hasher *h) {
+    if (h->worker.joinable()) h->worker.join();
+    if (h->worker_rc) return fail(h->worker_rc, "%s", h->worker_err.c_str());
+    return 0;
+}
+
+// hand the full buffer to the worker and continue in the other one
+int hasher_flush_full(snapgpu_hasher *h) {
+    int rc = hasher_wait(h);              // the chain is serial: the previous piece has to be done
+    if (rc) return rc;
+    const int b = h->fill;
+    const bool first = h->first;
+    const uint64_t prefix = h->prefix;
+    h->worker = std::thread([h, b, first, prefix]() {
+        HostSeg s{0, kHasherBuffer, prefix, kHostSegNoFinal | (first ? 0u : kHostSegContinue)};
+        h->worker_rc = sha512_host_segments(h->buf[b], &s, 1, h->state);
+        if (h->worker_rc) h->worker_err = snapgpu_last_error();
+    });
+    h->first = false;
+    h->prefix += kHasherBuffer;
+    h->fill ^= 1;
+    h->used = 0;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // copyToBuildDir (snappy/build.go:362-418), the caller-side neighbour of writeHashes
 // (SURVEY.md section 8f, row 2): every file that has to be copied (not hard-linked) is read ONCE
 // into the pinned ring -- the same bytes are written to the build dir by the packer threads and
@@ -1615,6 +1668,57 @@ int snapgpu_dir_updated(const char *dir_a, const char *dir_b, const char *pfx, c
     int rc = dir_updated(clean_dir(dir_a), clean_dir(dir_b), pfx ? pfx : "", &up);
     if (rc) return rc;
     return pack_names(up, names, count);
+}
+
+snapgpu_hasher *snapgpu_hasher_new(void) {
+    if (ensure_init()) return nullptr;
+    snapgpu_hasher *h = new (std::nothrow) snapgpu_hasher();
+    if (!h) return nullptr;
+    for (auto &b : h->buf) {
+        b = static_cast<uint8_t *>(snapgpu_alloc_pinned(kHasherBuffer));
+        if (!b) {
+            snapgpu_hasher_free(h);
+            return nullptr;
+        }
+    }
+    return h;
+}
+
+void snapgpu_hasher_free(snapgpu_hasher *h) {
+    if (!h) return;
+    if (h->worker.joinable()) h->worker.join();
+    for (auto &b : h->buf)
+        if (b) snapgpu_free_pinned(b);
+    delete h;
+}
+
+int snapgpu_hasher_write(snapgpu_hasher *h, const uint8_t *p, size_t n) {
+    if (!h || (!p && n)) return fail(SNAPGPU_EINVAL, "null argument");
+    while (n) {
+        const size_t take = std::min(n, kHasherBuffer - h->used);
+        memcpy(h->buf[h->fill] + h->used, p, take);
+        h->used += take;
+        p += take;
+        n -= take;
+        if (h->used == kHasherBuffer) {
+            int rc = hasher_flush_full(h);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+int snapgpu_hasher_sum(snapgpu_hasher *h, uint8_t digest[64]) {
+    if (!h || !digest) return fail(SNAPGPU_EINVAL, "null argument");
+    int rc = hasher_wait(h);
+    if (rc) return rc;
+    // like hash.Hash.Sum: the running state is not disturbed, more Writes may follow
+    uint8_t st[64];
+    memcpy(st, h->state, 64);
+    HostSeg s{0, h->used, h->prefix, h->first ? 0u : kHostSegContinue};
+    if ((rc = sha512_host_segments(h->buf[h->fill], &s, 1, st))) return rc;
+    memcpy(digest, st, 64);
+    return 0;
 }
 
 int snapgpu_copy_to_build_dir(const char *source_dir, const char *build_dir, int flags) {

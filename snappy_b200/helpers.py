@@ -84,30 +84,28 @@ def cmp_batch(a: np.ndarray, b: np.ndarray, offsets, lengths) -> np.ndarray:
 
 
 class Sha512Stream:
-    """hash.Hash-shaped streaming digest of one long message (state carried on the host)."""
+    """sha512.New(): a hash.Hash-shaped streaming digest of one long message (snapgpu_hasher_*).
+
+    ``Write`` gathers bytes in pinned memory; every full 4 MiB piece is hashed on the GPU by a
+    worker thread while the caller keeps writing.  ``Sum`` does not disturb the running state."""
 
     def __init__(self):
         N.ensure_init()
-        self._state = (ctypes.c_uint8 * 64)()
-        self._first = True
-        self._prefix = 0
-        self._tail = b""
+        self._h = N.lib().snapgpu_hasher_new()
+        if not self._h:
+            raise N.SnapGpuError(N.ECUDA, N.last_error())
 
-    def Write(self, p: bytes) -> int:
-        buf = self._tail + bytes(p)
-        whole = len(buf) & ~127
-        if whole:
-            arr = np.frombuffer(buf[:whole], dtype=np.uint8)
-            N.check(N.lib().snapgpu_sha512_stream(ctypes.addressof(self._state), int(self._first), arr.ctypes.data,
-                                                  whole, self._prefix, 0))
-            self._first = False
-            self._prefix += whole
-        self._tail = buf[whole:]
+    def Write(self, p) -> int:
+        arr = np.frombuffer(p, dtype=np.uint8) if len(p) else np.zeros(1, dtype=np.uint8)
+        N.check(N.lib().snapgpu_hasher_write(self._h, arr.ctypes.data, len(p)))
         return len(p)
 
     def Sum(self) -> bytes:
-        state = (ctypes.c_uint8 * 64).from_buffer_copy(bytes(self._state))
-        arr = np.frombuffer(self._tail, dtype=np.uint8) if self._tail else np.zeros(16, dtype=np.uint8)
-        N.check(N.lib().snapgpu_sha512_stream(ctypes.addressof(state), int(self._first), arr.ctypes.data,
-                                              len(self._tail), self._prefix, 1))
-        return bytes(state)
+        out = (ctypes.c_uint8 * 64)()
+        N.check(N.lib().snapgpu_hasher_sum(self._h, ctypes.addressof(out)))
+        return bytes(out)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            N.lib().snapgpu_hasher_free(h)

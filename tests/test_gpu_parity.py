@@ -151,6 +151,48 @@ def test_stream_api_matches_one_shot(gpu):
     assert helpers.Sha512Stream().Sum() == hashlib.sha512(b"").digest()
 
 
+def test_hasher_streams_like_hash_hash(gpu, tmp_path):
+    """snapgpu_hasher_*: Write in arbitrary pieces across several 4 MiB buffers, Sum in mid-stream without
+    disturbing the state, and the archive-sha512 use: hashing data.tar.gz WHILE it is written
+    (io.MultiWriter shape; clickdeb/deb.go:360-366 + snappy/build.go:222) equals hashing the finished file."""
+    import tarfile
+    from snappy_b200 import helpers
+    rng = np.random.default_rng(15)
+    msg = rng.integers(0, 256, 13 * (1 << 20) + 12345, dtype=np.uint8).tobytes()
+    h = helpers.Sha512Stream()
+    assert h.Sum() == hashlib.sha512(b"").digest()
+    pos = 0
+    for step in (0, 1, 127, 128, 4 << 20, (4 << 20) - 256, 3, 5_000_000):
+        h.Write(msg[pos:pos + step])
+        pos += step
+        assert h.Sum() == hashlib.sha512(msg[:pos]).digest()
+        assert h.Sum() == hashlib.sha512(msg[:pos]).digest()          # Sum twice: state untouched
+    h.Write(msg[pos:])
+    assert h.Sum() == hashlib.sha512(msg).digest()
+
+    class Tee:
+        def __init__(self, f, hasher):
+            self.f, self.h = f, hasher
+
+        def write(self, b):
+            self.h.Write(bytes(b))
+            return self.f.write(b)
+
+        def flush(self):
+            self.f.flush()
+
+    src = tmp_path / "tree"
+    src.mkdir()
+    for i in range(30):
+        (src / f"f{i}").write_bytes(rng.integers(0, 256, int(rng.integers(1, 400_000)), dtype=np.uint8).tobytes())
+    tar_path = tmp_path / "data.tar.gz"
+    hasher = helpers.Sha512Stream()
+    with open(tar_path, "wb") as raw:
+        with tarfile.open(fileobj=Tee(raw, hasher), mode="w|gz") as tar:
+            tar.add(src, arcname=".")
+    assert hasher.Sum().hex() == helpers.Sha512sum(str(tar_path)) == hashlib.sha512(tar_path.read_bytes()).hexdigest()
+
+
 def test_device_resident_api(gpu, oracle):
     import torch
     from snappy_b200 import device, synth
