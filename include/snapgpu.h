@@ -148,6 +148,19 @@ int snapgpu_should_exclude(const char *base_name);          /* shouldExclude, 1 
 void snapgpu_digest_cache_clear(void);
 void snapgpu_digest_cache_stats(size_t *entries, uint64_t *hits);
 
+/* hashes.yaml verification -- a consumer the reference does not have: it writes the per-file
+ * list (snappy/build.go:249-256) but reads back only archive-sha512 (snappy/snapp.go:466-478).
+ * Re-hashes the tree under `root` exactly as snapgpu_write_hashes would (DEBIAN/ is neither
+ * created nor listed) and compares entry by entry with the document at yaml_path.  *report gets
+ * NUL-terminated strings laid end to end (free with snapgpu_free), *count their number:
+ *   "missing: NAME"   listed but not in the tree      "extra: NAME"   in the tree but not listed
+ *   "changed: NAME (size sha512 mode)"  with the fields that differ
+ *   "archive-sha512 differs"  only when data_tar is given (NULL = do not check the archive)
+ * NAME is the name scalar as the document spells it.  count == 0 means the tree verifies.  A
+ * yaml_path inside the tree (meta/hashes.yaml at install time) is not reported as extra. */
+int snapgpu_verify_hashes(const char *root, const char *yaml_path, const char *data_tar, char **report,
+                          size_t *count);
+
 void snapgpu_free(void *p);
 
 /* ---- synthetic inputs and instrumentation (bench/test support, not product API) ------ */

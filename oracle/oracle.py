@@ -12,6 +12,8 @@ logic on the hot path:
 * ``dir_updated``       /root/reference/helpers/cmp.go:97-114
 * ``apparmor_delta``    /root/reference/policy/policy.go:155-167
 * ``copy_to_build_dir`` /root/reference/snappy/build.go:362-418 (``should_exclude``: build.go:52-83)
+* ``verify_hashes``     no reference counterpart: fileHash / yamlFileMode semantics
+                        of snappy/hashes.go:59-110 applied to a re-hash of the tree
 
 Third-party code that is NOT under /root/reference and is restated here from its
 published behaviour:
@@ -796,3 +798,51 @@ def copy_to_build_dir(source_dir: str, build_dir: str, no_link: bool = False) ->
                     fout.write(chunk)
 
     visit(source, os.lstat(source))
+
+
+# ---------------------------------------------------------------------------------------------
+# hashes.yaml verification -- SURVEY.md section 8f, row 4 (no function in the reference does this;
+# the fields compared are those of fileHash, snappy/hashes.go:93-101)
+# ---------------------------------------------------------------------------------------------
+
+def verify_hashes(root: str, yaml_path: str, data_tar: str | None = None) -> list[str]:
+    """Report lines in the order and spelling of snapgpu_verify_hashes, for documents whose names
+    are plain scalars.  The old document is read with PyYAML (an independent parser), the tree is
+    hashed with the oracle's own Sha512sum."""
+    import yaml
+    old = yaml.safe_load(open(yaml_path, "rb").read())
+    base = os.fsencode(root.rstrip("/") or "/")
+    fresh = {}
+    order = []
+    for path, st in _walk(base):
+        rel = path[len(base):]
+        if rel.startswith(b"/DEBIAN") or path == base:
+            continue
+        name = os.fsdecode(rel[1:])
+        e = {"mode": file_mode_string(st.st_mode)}
+        if stat.S_ISREG(st.st_mode):
+            e["size"] = st.st_size
+            e["sha512"] = sha512sum(os.fsdecode(path))
+        fresh[name] = e
+        order.append(name)
+    report = []
+    if data_tar is not None and old.get("archive-sha512") != sha512sum(data_tar):
+        report.append("archive-sha512 differs")
+    seen = set()
+    for ent in old.get("files") or []:
+        name = str(ent["name"])
+        seen.add(name)
+        if name not in fresh:
+            report.append(f"missing: {name}")
+            continue
+        what = [k for k in ("size", "sha512", "mode") if str(ent.get(k, "")) != str(fresh[name].get(k, ""))]
+        if what:
+            report.append(f"changed: {name} ({' '.join(what)})")
+    self_name = None
+    ap, ar = os.path.abspath(yaml_path), os.path.abspath(root)
+    if ap.startswith(ar + "/"):
+        self_name = ap[len(ar) + 1:]
+    for name in order:
+        if name not in seen and name != self_name:
+            report.append(f"extra: {name}")
+    return report

@@ -42,6 +42,16 @@ def shouldExclude(basename: str) -> bool:
     return bool(N.lib().snapgpu_should_exclude(N.fs(basename)))
 
 
+def verifyHashes(root: str, yamlPath: str, dataTar: str | None = None) -> list[str]:
+    """Re-hash ``root`` and diff it against the hashes.yaml at ``yamlPath`` (no counterpart in the
+    reference).  Returns the report lines; an empty list means it verifies."""
+    from .helpers import _names
+    ptr, count = ctypes.c_void_p(), ctypes.c_size_t()
+    _raise(N.lib().snapgpu_verify_hashes(N.fs(root), N.fs(yamlPath), N.fs(dataTar) if dataTar else None,
+                                         ctypes.byref(ptr), ctypes.byref(count)))
+    return _names(ptr, count)
+
+
 def digest_cache_stats() -> tuple[int, int]:
     entries, hits = ctypes.c_size_t(), ctypes.c_uint64()
     N.lib().snapgpu_digest_cache_stats(ctypes.byref(entries), ctypes.byref(hits))

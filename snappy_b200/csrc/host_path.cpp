@@ -1174,8 +1174,8 @@ int mkdir_all(const std::string &path, mode_t mode) {
     return (stat(path.c_str(), &st) == 0 && S_ISDIR(st.st_mode)) ? 0 : -1;
 }
 
-int collect_tree(const std::string &build_dir, std::vector<TreeEntry> &entries) {
-    mkdir_all(build_dir + "/DEBIAN", 0755);             // error ignored, like build.go:218-219
+int collect_tree(const std::string &build_dir, std::vector<TreeEntry> &entries, bool make_debian = true) {
+    if (make_debian) mkdir_all(build_dir + "/DEBIAN", 0755);   // error ignored, like build.go:218-219
     entries.clear();
     struct stat root;
     if (lstat(build_dir.c_str(), &root) == 0 && S_ISDIR(root.st_mode))
@@ -1233,11 +1233,15 @@ int emit_hashes_yaml(const std::vector<TreeEntry> &entries, const uint8_t *diges
     return 0;
 }
 
-int build_hashes_yaml(const std::string &build_dir, const std::string &data_tar, std::string *yaml) {
+// data_tar == nullptr (verification without the archive): the archive digest is left zero.
+// make_debian: create DEBIAN/ first as writeHashes does (build.go:218-219); verification does not.
+int build_hashes_yaml(const std::string &build_dir, const std::string *data_tar_opt, std::string *yaml,
+                      bool make_debian) {
     std::vector<TreeEntry> entries;
     const double t0 = wall_ms();
-    int rc = collect_tree(build_dir, entries);
+    int rc = collect_tree(build_dir, entries, make_debian);
     if (rc) return rc;
+    const std::string data_tar = data_tar_opt ? *data_tar_opt : std::string();
     // digests: archive first, then one per regular entry in walk order; entries this library
     // copied into place itself (copyToBuildDir) come from the digest cache, the rest are hashed
     size_t nreg = 0;
@@ -1246,9 +1250,11 @@ int build_hashes_yaml(const std::string &build_dir, const std::string &data_tar,
     std::vector<std::string> paths;
     std::vector<int64_t> sizes;
     std::vector<size_t> slot_of;                         // digest slot of paths[k]
-    paths.push_back(data_tar);                           // archive-sha512 first (build.go:222)
-    sizes.push_back(-1);
-    slot_of.push_back(0);
+    if (data_tar_opt) {
+        paths.push_back(data_tar);                       // archive-sha512 first (build.go:222)
+        sizes.push_back(-1);
+        slot_of.push_back(0);
+    }
     size_t slot = 1;
     for (const TreeEntry &e : entries)
         if (e.regular) {
@@ -1267,8 +1273,128 @@ int build_hashes_yaml(const std::string &build_dir, const std::string &data_tar,
     rc = emit_hashes_yaml(entries, digests.data(), nreg + 1, yaml);
     if (getenv("SNAPGPU_TRACE"))
         fprintf(stderr, "[snapgpu] writeHashes: walk %.2f ms (%zu entries), pack+hash %.2f ms (%zu files, %zu from the digest cache), yaml %.2f ms\n",
-                t1 - t0, entries.size(), t2 - t1, paths.size(), nreg + 1 - paths.size(), wall_ms() - t2);
+                t1 - t0, entries.size(), t2 - t1, paths.size(), nreg + (data_tar_opt ? 1 : 0) - paths.size(), wall_ms() - t2);
     return rc;
+}
+
+int build_hashes_yaml(const std::string &build_dir, const std::string &data_tar, std::string *yaml) {
+    return build_hashes_yaml(build_dir, &data_tar, yaml, true);
+}
+
+// ------------------------------------------------------------------------------------------
+// hashes.yaml verification: a consumer the reference does not
+// have -- it writes the per-file list (snappy/build.go:249-256) but only ever reads
+// archive-sha512 back (snappy/snapp.go:466-478).  The tree is hashed again with the same code
+// that wrote the document and the two documents are compared entry by entry.  No YAML parser is
+// needed for that: in what yaml.v2 emits for hashesYaml every entry starts with "- " in column
+// 0, its keys sit at indent 2 and every continuation line of a folded or literal scalar is
+// indented deeper, so the documents are cut into entry blocks textually and matched by the
+// (still encoded) name scalar.
+// ------------------------------------------------------------------------------------------
+
+struct YamlEntryBlock {
+    std::string name;      // encoded name scalar: text between "- name:" and the next indent-2 key
+    std::string size, sha512, mode;
+};
+
+bool starts_with(const std::string &s, size_t pos, const char *pfx) { return s.compare(pos, strlen(pfx), pfx) == 0; }
+
+// archive: value of archive-sha512; blocks: one per entry, in document order
+int split_hashes_yaml(const std::string &doc, std::string *archive, std::vector<YamlEntryBlock> *blocks) {
+    archive->clear();
+    blocks->clear();
+    size_t pos = 0;
+    YamlEntryBlock *cur = nullptr;
+    std::string *field = nullptr;          // the scalar continuation lines are appended to
+    while (pos < doc.size()) {
+        size_t eol = doc.find('\n', pos);
+        if (eol == std::string::npos) eol = doc.size();
+        const std::string line = doc.substr(pos, eol - pos);
+        pos = eol + 1;
+        if (starts_with(line, 0, "archive-sha512:")) {
+            *archive = line.substr(15);
+            field = archive;
+        } else if (starts_with(line, 0, "files:")) {
+            field = nullptr;
+        } else if (starts_with(line, 0, "- name:")) {
+            blocks->emplace_back();
+            cur = &blocks->back();
+            cur->name = line.substr(7);
+            field = &cur->name;
+        } else if (cur && starts_with(line, 0, "  size:")) {
+            cur->size = line.substr(7);
+            field = &cur->size;
+        } else if (cur && starts_with(line, 0, "  sha512:")) {
+            cur->sha512 = line.substr(9);
+            field = &cur->sha512;
+        } else if (cur && starts_with(line, 0, "  mode:")) {
+            cur->mode = line.substr(7);
+            field = &cur->mode;
+        } else if (field && (line.empty() || line[0] == ' ')) {
+            *field += "\n" + line;                                   // folded / literal continuation
+        } else if (!line.empty()) {
+            return fail(SNAPGPU_EINVAL, "hashes.yaml: unexpected line \"%.60s\"", line.c_str());
+        }
+    }
+    return 0;
+}
+
+int verify_hashes(const std::string &root, const std::string &yaml_path, const std::string *data_tar,
+                  std::vector<std::string> *report) {
+    report->clear();
+    std::string old_doc;
+    {
+        int fd = ::open(yaml_path.c_str(), O_RDONLY | O_CLOEXEC);
+        if (fd < 0) return fail(SNAPGPU_EIO, "%s", go_path_error("open", yaml_path, errno).c_str());
+        char buf[1 << 16];
+        for (;;) {
+            ssize_t r = ::read(fd, buf, sizeof buf);
+            if (r < 0 && errno == EINTR) continue;
+            if (r < 0) {
+                const int e = errno;
+                ::close(fd);
+                return fail(SNAPGPU_EIO, "%s", go_path_error("read", yaml_path, e).c_str());
+            }
+            if (r == 0) break;
+            old_doc.append(buf, (size_t)r);
+        }
+        ::close(fd);
+    }
+    std::string new_doc;
+    int rc = build_hashes_yaml(root, data_tar, &new_doc, false);
+    if (rc) return rc;
+    std::string old_archive, new_archive;
+    std::vector<YamlEntryBlock> old_blocks, new_blocks;
+    if ((rc = split_hashes_yaml(old_doc, &old_archive, &old_blocks))) return rc;
+    if ((rc = split_hashes_yaml(new_doc, &new_archive, &new_blocks))) return rc;
+    if (data_tar && old_archive != new_archive) report->push_back("archive-sha512 differs");
+
+    // the document being verified may itself sit in the tree (meta/hashes.yaml is put there at
+    // install time, snappy/click.go:330-338): it is not part of what it describes
+    std::string self_name;
+    if (yaml_path.size() > root.size() + 1 && yaml_path.compare(0, root.size(), root) == 0 && yaml_path[root.size()] == '/')
+        self_name = " " + yaml_path.substr(root.size() + 1);
+
+    std::map<std::string, const YamlEntryBlock *> fresh;
+    for (const YamlEntryBlock &b : new_blocks) fresh[b.name] = &b;
+    std::map<std::string, bool> seen;
+    for (const YamlEntryBlock &o : old_blocks) {
+        seen[o.name] = true;
+        auto it = fresh.find(o.name);
+        if (it == fresh.end()) {
+            report->push_back("missing:" + o.name);
+            continue;
+        }
+        const YamlEntryBlock &n = *it->second;
+        std::string what;
+        if (o.size != n.size) what += " size";
+        if (o.sha512 != n.sha512) what += " sha512";
+        if (o.mode != n.mode) what += " mode";
+        if (!what.empty()) report->push_back("changed:" + o.name + " (" + what.substr(1) + ")");
+    }
+    for (const YamlEntryBlock &n : new_blocks)
+        if (!seen.count(n.name) && n.name != self_name) report->push_back("extra:" + n.name);
+    return 0;
 }
 
 int write_file_0644(const std::string &path, const std::string &content) {
@@ -1668,6 +1794,15 @@ int snapgpu_dir_updated(const char *dir_a, const char *dir_b, const char *pfx, c
     int rc = dir_updated(clean_dir(dir_a), clean_dir(dir_b), pfx ? pfx : "", &up);
     if (rc) return rc;
     return pack_names(up, names, count);
+}
+
+int snapgpu_verify_hashes(const char *root, const char *yaml_path, const char *data_tar, char **report, size_t *count) {
+    if (!root || !yaml_path || !report || !count) return fail(SNAPGPU_EINVAL, "null argument");
+    std::vector<std::string> lines;
+    const std::string tar = data_tar ? data_tar : "";
+    int rc = verify_hashes(clean_dir(root), yaml_path, data_tar ? &tar : nullptr, &lines);
+    if (rc) return rc;
+    return pack_names(lines, report, count);
 }
 
 snapgpu_hasher *snapgpu_hasher_new(void) {

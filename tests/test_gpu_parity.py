@@ -501,3 +501,49 @@ def test_copy_to_build_dir_fused_with_hashing(gpu, oracle, tmp_path):
     assert snapshot(got2) == snapshot(want2)
     assert build.hashes_yaml(str(got2), str(tar)) == oracle.write_hashes(str(want2), str(tar))
     gpu.lib().snapgpu_digest_cache_clear()
+
+
+# ---- hashes.yaml verification -------------------------------------------------
+
+def test_verify_hashes(gpu, oracle, tmp_path):
+    """Build -> hashes.yaml -> 'install' (copy of the tree with meta/hashes.yaml, snappy/click.go:330-338)
+    -> verify.  The report equals the oracle's (PyYAML parse + CPU re-hash) for every kind of drift."""
+    import shutil
+    from snappy_b200 import build
+    from test_host_logic import make_source_tree
+    rng = np.random.default_rng(44)
+    src = tmp_path / "build"
+    make_source_tree(src)
+    for i in range(25):
+        (src / "lib" / f"blob{i:02d}").write_bytes(rng.integers(0, 256, int(rng.integers(1, 30_000)), dtype=np.uint8).tobytes())
+    (src / "lib" / "with space and a very long name that yaml folds at eighty columns because it has spaces in it.txt").write_text("x")
+    (src / "lib" / "true").write_text("quoted name")
+    tar = tmp_path / "data.tar.gz"
+    tar.write_bytes(b"archive bytes")
+    build.writeHashes(str(src), str(tar))
+    inst = tmp_path / "inst"
+    shutil.copytree(src, inst, symlinks=True, ignore=shutil.ignore_patterns("DEBIAN"))
+    shutil.copy(src / "DEBIAN" / "hashes.yaml", inst / "meta" / "hashes.yaml")
+    y = str(inst / "meta" / "hashes.yaml")
+    assert build.verifyHashes(str(inst), y) == [] == oracle.verify_hashes(str(inst), y)
+    assert build.verifyHashes(str(inst), y, str(tar)) == []
+    assert not (inst / "DEBIAN").exists()                            # verification does not touch the tree
+    other = tmp_path / "other.tar.gz"
+    other.write_bytes(b"another archive")
+    assert build.verifyHashes(str(inst), y, str(other)) == ["archive-sha512 differs"] == oracle.verify_hashes(str(inst), y, str(other))
+    # drift of every kind
+    b = bytearray((inst / "lib" / "blob03").read_bytes())
+    b[-1] ^= 1
+    (inst / "lib" / "blob03").write_bytes(bytes(b))                  # same size, other content
+    (inst / "lib" / "blob04").write_bytes(b"shorter")                # size and content
+    os.chmod(inst / "bin" / "hello-world", 0o700)                    # mode only
+    os.remove(inst / "lib" / "blob05")                               # missing
+    (inst / "lib" / "new-file").write_text("added")                  # extra
+    os.remove(inst / "bin" / "link")
+    (inst / "bin" / "link").write_text("was a symlink")              # type change: size/sha512 appear, mode differs
+    got = build.verifyHashes(str(inst), y)
+    assert got == oracle.verify_hashes(str(inst), y)
+    assert got == ["changed: bin/hello-world (mode)", "changed: bin/link (size sha512 mode)", "changed: lib/blob03 (sha512)",
+                   "changed: lib/blob04 (size sha512)", "missing: lib/blob05", "extra: lib/new-file"]
+    with pytest.raises(OSError):
+        build.verifyHashes(str(inst), str(tmp_path / "no-such.yaml"))
