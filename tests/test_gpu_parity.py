@@ -547,3 +547,96 @@ def test_verify_hashes(gpu, oracle, tmp_path):
                    "changed: lib/blob04 (size sha512)", "missing: lib/blob05", "extra: lib/new-file"]
     with pytest.raises(OSError):
         build.verifyHashes(str(inst), str(tmp_path / "no-such.yaml"))
+
+
+# ---- BASELINE.json configs at full size: size-independent properties --------------------------------
+
+def _spot_check(dg, lengths, picks, first_index=0):
+    from snappy_b200 import synth
+    for i in picks:
+        want = hashlib.sha512(synth.file_bytes(first_index + int(i), int(lengths[i]))).digest()
+        assert dg[i].tobytes() == want, f"file {i} differs from hashlib"
+
+
+def test_config2_full_size_properties(gpu):
+    """Config 2 as benchmarked (100,000 files, log-normal 1-64 KiB, 1.29 GB, generated in HBM): spot checks
+    against hashlib, order independence (checksum of checksums), launch-shape independence, and the
+    host-buffer pipeline on the same bytes."""
+    import torch
+    from snappy_b200 import device, helpers, synth
+    lengths = synth.lognormal_sizes(100_000)
+    off, total = synth.layout(lengths)
+    d = torch.empty(total, dtype=torch.uint8, device="cuda:0")
+    device.synth_fill_device(d, off, lengths)
+    dg = device.sha512_batch_device(d, off, lengths).cpu().numpy()
+    rng = np.random.default_rng(2)
+    longest = np.argsort(lengths)[-8:]
+    _spot_check(dg, lengths, np.concatenate([rng.integers(0, len(lengths), 48), longest, [0, len(lengths) - 1]]))
+    perm = rng.permutation(len(lengths))
+    dg_perm = device.sha512_batch_device(d, off[perm], lengths[perm]).cpu().numpy()
+    assert hashlib.sha512(dg_perm[np.argsort(perm)].tobytes()).digest() == hashlib.sha512(dg.tobytes()).digest()
+    for warps in (2, 3):
+        gpu.set_option("sha_warps_per_sm", warps)
+        assert np.array_equal(device.sha512_batch_device(d, off, lengths).cpu().numpy(), dg)
+    gpu.set_option("sha_warps_per_sm", 0)
+    host = d.cpu().numpy()
+    assert np.array_equal(helpers.sha512_batch(host, off, lengths), dg)
+
+
+def test_config5_shard_full_size_properties(gpu):
+    """One GPU's shard of config 5 (250,000 files x 64 KiB = 16.4 GB in HBM)."""
+    import torch
+    from snappy_b200 import device, synth
+    n = 250_000
+    lengths = np.full(n, 65536, dtype=np.uint64)
+    off, total = synth.layout(lengths)
+    d = torch.empty(total, dtype=torch.uint8, device="cuda:0")
+    device.synth_fill_device(d, off, lengths, first_index=3 * n)          # rank 3's files
+    dg = device.sha512_batch_device(d, off, lengths).cpu().numpy()
+    rng = np.random.default_rng(3)
+    _spot_check(dg, lengths, np.concatenate([rng.integers(0, n, 24), [0, n - 1]]), first_index=3 * n)
+    assert len(np.unique(dg.view(np.dtype((np.void, 64))))) == n        # distinct contents, distinct digests
+    gpu.set_option("sha_warps_per_sm", 1)
+    assert np.array_equal(device.sha512_batch_device(d, off, lengths).cpu().numpy(), dg)
+    gpu.set_option("sha_warps_per_sm", 0)
+
+
+def test_config4_full_size_properties(gpu):
+    """Config 4 as benchmarked: 10,000 pairs x 1 MiB, 100 of them differing in one byte."""
+    import torch
+    from snappy_b200 import device, synth
+    n = 10_000
+    lengths = np.full(n, 1 << 20, dtype=np.uint64)
+    off, total = synth.layout(lengths)
+    da = torch.empty(total, dtype=torch.uint8, device="cuda:0")
+    device.synth_fill_device(da, off, lengths)
+    db = da.clone()
+    rng = np.random.default_rng(synth.SEED)
+    differ = np.sort(rng.choice(n, 100, replace=False))
+    pos = rng.integers(0, 1 << 20, 100)
+    pos[:3] = [0, (1 << 20) - 1, 16384]                                    # first byte, last byte, a tile edge
+    db[torch.from_numpy(off[differ].astype(np.int64) + pos).to("cuda:0")] ^= 0x80
+    eq_ab = device.cmp_batch_device(da, db, off, lengths).cpu().numpy()
+    eq_ba = device.cmp_batch_device(db, da, off, lengths).cpu().numpy()
+    assert np.nonzero(eq_ab == 0)[0].tolist() == differ.tolist()
+    assert np.array_equal(eq_ab, eq_ba)                                    # symmetric
+    assert device.cmp_batch_device(da, da, off, lengths).cpu().numpy().all()   # reflexive
+    del db
+
+
+def test_config3_shape_at_reduced_size(gpu):
+    """Config 3's shape (50,000 small files + 4 long ones) with 48 MiB instead of 1 GiB long files; the
+    full-size run is tools/cfg3_tail.py (profiles/), which checks the 1 GiB digests against hashlib too."""
+    import torch
+    from snappy_b200 import device, synth
+    lengths = np.concatenate([synth.lognormal_sizes(100_000)[:50_000], np.full(4, 48 << 20, dtype=np.uint64)])
+    off, total = synth.layout(lengths)
+    d = torch.empty(total, dtype=torch.uint8, device="cuda:0")
+    device.synth_fill_device(d, off, lengths)
+    gpu.reset_stats()
+    dg = device.sha512_batch_device(d, off, lengths).cpu().numpy()
+    _spot_check(dg, lengths, [50_000, 50_001, 50_002, 50_003, 0, 49_999, 123, 31_337])
+    gpu.set_option("long_kernel", 0)
+    small = device.sha512_batch_device(d, off[:50_000], lengths[:50_000]).cpu().numpy()
+    gpu.set_option("long_kernel", 1)
+    assert np.array_equal(small, dg[:50_000])
