@@ -74,6 +74,8 @@ std::string hex_lower(const uint8_t *p, size_t n) {
 // ------------------------------------------------------------------------------------------
 
 constexpr int kPlanSlots = 4;
+constexpr int kFeeders = 4;                     // host threads that move pageable memory into pinned bounce buffers
+constexpr size_t kBounceBytes = 4u << 20;
 constexpr size_t kMaxChunkItems = 1u << 20;
 constexpr uint64_t kMaxSegBytes = 1ULL << 39;   // block counts stay below 2^32
 constexpr size_t kStageSlack = 256;
@@ -111,6 +113,12 @@ struct Device {
     uint8_t *h_out[2] = {nullptr, nullptr};
     size_t out_cap = 0;       // bytes
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    // bounce buffers for callers whose host buffer is ordinary pageable memory (allocated on first use)
+    uint8_t *bounce[kFeeders][2] = {};
+    cudaEvent_t bounce_free[kFeeders][2] = {};
+    cudaEvent_t feeder_done[kFeeders] = {};
+    cudaEvent_t feeder_fork = nullptr;
+    cudaStream_t feeder_stream[kFeeders] = {};
     // kernel timing ring (events on the launching stream)
     TimedLaunch sha_t[8], cmp_t[8];
     int sha_ti = 0, cmp_ti = 0;
@@ -165,6 +173,19 @@ static void destroy_device(Device &D) {
     }
     for (auto &t : D.sha_t) { if (t.beg) cudaEventDestroy(t.beg); if (t.end) cudaEventDestroy(t.end); }
     for (auto &t : D.cmp_t) { if (t.beg) cudaEventDestroy(t.beg); if (t.end) cudaEventDestroy(t.end); }
+    for (int f = 0; f < kFeeders; f++) {
+        for (int k = 0; k < 2; k++) {
+            if (D.bounce[f][k]) cudaFreeHost(D.bounce[f][k]);
+            if (D.bounce_free[f][k]) cudaEventDestroy(D.bounce_free[f][k]);
+            D.bounce[f][k] = nullptr;
+            D.bounce_free[f][k] = nullptr;
+        }
+        if (f == 0 && D.feeder_fork) { cudaEventDestroy(D.feeder_fork); D.feeder_fork = nullptr; }
+        if (D.feeder_done[f]) cudaEventDestroy(D.feeder_done[f]);
+        if (D.feeder_stream[f]) cudaStreamDestroy(D.feeder_stream[f]);
+        D.feeder_done[f] = nullptr;
+        D.feeder_stream[f] = nullptr;
+    }
     if (D.copy_stream) cudaStreamDestroy(D.copy_stream);
     if (D.compute_stream) cudaStreamDestroy(D.compute_stream);
     if (D.long_stream) cudaStreamDestroy(D.long_stream);
@@ -630,6 +651,75 @@ static int ensure_staging(Device &D, size_t stage_bytes, size_t out_bytes) {
     return 0;
 }
 
+// Is `p` memory the copy engine can read directly (cudaHostAlloc / cudaHostRegister)?
+static bool host_pointer_is_pinned(const void *p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged;
+}
+
+// Host-to-device copy of one span on D.copy_stream (in stream order with what was enqueued before).
+// Pinned memory is one DMA.  Pageable memory -- a Go slice handed straight through cgo -- would make
+// cudaMemcpyAsync stage through the driver's single bounce buffer at ~10 GB/s; instead kFeeders
+// host threads copy 4 MiB pieces into pinned bounce buffers of their own (two each, so the memcpy
+// of a piece overlaps the DMA of the previous one) and enqueue the DMAs on their own streams.
+static int h2d_span(Device &D, uint8_t *dst, const uint8_t *src, size_t bytes, bool pinned) {
+    if (bytes == 0) return 0;
+    if (pinned || bytes < kBounceBytes) {
+        SG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, D.copy_stream));
+        return 0;
+    }
+    for (int f = 0; f < kFeeders; f++) {
+        if (D.feeder_stream[f]) continue;
+        SG_CUDA(cudaStreamCreateWithFlags(&D.feeder_stream[f], cudaStreamNonBlocking));
+        SG_CUDA(cudaEventCreateWithFlags(&D.feeder_done[f], cudaEventDisableTiming));
+        for (int k = 0; k < 2; k++) {
+            SG_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&D.bounce[f][k]), kBounceBytes, cudaHostAllocPortable));
+            SG_CUDA(cudaEventCreateWithFlags(&D.bounce_free[f][k], cudaEventDisableTiming));
+        }
+    }
+    // the DMAs must not overtake what the copy stream was asked to do before (the previous chunk
+    // may still be reading the same staging buffer's neighbour; plan uploads): fork from it
+    if (!D.feeder_fork) SG_CUDA(cudaEventCreateWithFlags(&D.feeder_fork, cudaEventDisableTiming));
+    SG_CUDA(cudaEventRecord(D.feeder_fork, D.copy_stream));
+    for (int f = 0; f < kFeeders; f++) SG_CUDA(cudaStreamWaitEvent(D.feeder_stream[f], D.feeder_fork, 0));
+    const size_t pieces = (bytes + kBounceBytes - 1) / kBounceBytes;
+    int rcs[kFeeders] = {};
+    std::string errs[kFeeders];
+    auto feed = [&](int f) {
+        if (cudaSetDevice(D.ordinal) != cudaSuccess) { rcs[f] = SNAPGPU_ECUDA; errs[f] = "cudaSetDevice failed"; return; }
+        int use = 0;
+        for (size_t p = (size_t)f; p < pieces; p += kFeeders, use ^= 1) {
+            const size_t off = p * kBounceBytes, len = std::min(kBounceBytes, bytes - off);
+            cudaError_t e = cudaEventSynchronize(D.bounce_free[f][use]);       // its previous DMA has drained
+            if (e == cudaSuccess) {
+                memcpy(D.bounce[f][use], src + off, len);
+                e = cudaMemcpyAsync(dst + off, D.bounce[f][use], len, cudaMemcpyHostToDevice, D.feeder_stream[f]);
+            }
+            if (e == cudaSuccess) e = cudaEventRecord(D.bounce_free[f][use], D.feeder_stream[f]);
+            if (e != cudaSuccess) {
+                rcs[f] = SNAPGPU_ECUDA;
+                errs[f] = cudaGetErrorString(e);
+                return;
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int f = 1; f < kFeeders; f++) th.emplace_back(feed, f);
+    feed(0);
+    for (auto &t : th) t.join();
+    for (int f = 0; f < kFeeders; f++)
+        if (rcs[f]) return fail(rcs[f], "host-to-device copy through the bounce buffers failed: %s", errs[f].c_str());
+    for (int f = 0; f < kFeeders; f++) {                      // join: the copy stream continues after all pieces
+        SG_CUDA(cudaEventRecord(D.feeder_done[f], D.feeder_stream[f]));
+        SG_CUDA(cudaStreamWaitEvent(D.copy_stream, D.feeder_done[f], 0));
+    }
+    return 0;
+}
+
 // A unit of pipelined work: a run of items whose bytes form one dense span of the host buffer.
 struct WorkItem {
     size_t user_index;     // digest slot / pair index in the caller's arrays
@@ -761,6 +851,7 @@ static int sha512_shard(Device &D, const uint8_t *data, const std::vector<WorkIt
     if (rc) return rc;
 
     const size_t phase = (uintptr_t)data & 15;   // keep (data + off) mod 16 on the device
+    const bool pinned = host_pointer_is_pinned(data);
     int scatter_pending[2] = {-1, -1};            // chunk index whose digests wait in h_out[b]
     auto scatter = [&](int b) -> int {
         if (scatter_pending[b] < 0) return 0;
@@ -784,8 +875,7 @@ static int sha512_shard(Device &D, const uint8_t *data, const std::vector<WorkIt
         const double t_free = now_ms();
         const size_t span = (size_t)(c.span_end - c.span_begin);
         if (span) {
-            SG_CUDA(cudaMemcpyAsync(D.d_stage[b] + phase, data + c.span_begin, span, cudaMemcpyHostToDevice,
-                                    D.copy_stream));
+            if ((rc = h2d_span(D, D.d_stage[b] + phase, data + c.span_begin, span, pinned))) return rc;
             R.h2d_bytes += span;
         }
         SG_CUDA(cudaEventRecord(D.ev_copied[b], D.copy_stream));
@@ -835,6 +925,7 @@ static int cmp_shard(Device &D, const uint8_t *a, const uint8_t *b_host, const s
     if (rc) return rc;
     // the two streams may sit at different phases mod 16; the kernel then takes the byte path
     const size_t pa = (uintptr_t)a & 15, pb = (uintptr_t)b_host & 15;
+    const bool a_pinned = host_pointer_is_pinned(a), b_pinned = host_pointer_is_pinned(b_host);
     std::vector<CmpItem> ci_items;
     int pending[2] = {-1, -1};
     auto gather = [&](int b) -> int {
@@ -855,8 +946,8 @@ static int cmp_shard(Device &D, const uint8_t *a, const uint8_t *b_host, const s
         const size_t span = (size_t)(c.span_end - c.span_begin);
         uint8_t *da = D.d_stage[b] + pa, *db = D.d_stage[b] + half + 128 + pb;
         if (span) {
-            SG_CUDA(cudaMemcpyAsync(da, a + c.span_begin, span, cudaMemcpyHostToDevice, D.copy_stream));
-            SG_CUDA(cudaMemcpyAsync(db, b_host + c.span_begin, span, cudaMemcpyHostToDevice, D.copy_stream));
+            if ((rc = h2d_span(D, da, a + c.span_begin, span, a_pinned))) return rc;
+            if ((rc = h2d_span(D, db, b_host + c.span_begin, span, b_pinned))) return rc;
             R.h2d_bytes += 2 * span;
         }
         SG_CUDA(cudaEventRecord(D.ev_copied[b], D.copy_stream));
