@@ -640,3 +640,71 @@ def test_config3_shape_at_reduced_size(gpu):
     small = device.sha512_batch_device(d, off[:50_000], lengths[:50_000]).cpu().numpy()
     gpu.set_option("long_kernel", 1)
     assert np.array_equal(small, dg[:50_000])
+
+
+# ---- the boundary under concurrency and with several devices -------------------------------------------
+
+def test_concurrent_callers(gpu, oracle, tmp_path):
+    """cgo calls arrive on arbitrary OS threads: eight threads hash, compare and write hashes.yaml at the
+    same time (ctypes releases the GIL around every call); every result equals the oracle's."""
+    import threading
+    from snappy_b200 import build, helpers
+    rng = np.random.default_rng(55)
+    jobs = []
+    for t in range(8):
+        lengths = np.concatenate([rng.integers(0, 40_000, 400 + 50 * t), [0, 111, 112, 3_000_000 if t % 3 == 0 else 5]])
+        data, off, ln = pack(lengths, rng)
+        b = data.copy()
+        b[int(off[7]) + int(ln[7]) // 2] ^= 4
+        jobs.append((data, b, off, ln))
+    tree = tmp_path / "tree"
+    tree.mkdir()
+    make_reference_tree(tree)
+    tar = tmp_path / "data.tar.gz"
+    tar.write_bytes(b"")
+    want_yaml = oracle.write_hashes(str(tree), str(tar))
+    results, errors = [None] * 8, []
+
+    def work(t):
+        try:
+            data, b, off, ln = jobs[t]
+            for _ in range(3):
+                dg = helpers.sha512_batch(data, off, ln)
+                eq = helpers.cmp_batch(data, b, off, ln)
+                doc = build.hashes_yaml(str(tree), str(tar))
+            results[t] = (dg, eq, doc)
+        except Exception as e:                        # noqa: BLE001 -- reported below
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    for t, (data, b, off, ln) in enumerate(jobs):
+        dg, eq, doc = results[t]
+        assert np.array_equal(dg, oracle.sha512_batch(data, off, ln, 4))
+        assert np.array_equal(eq, oracle.cmp_batch(data, b, off, ln, 4))
+        assert doc == want_yaml
+
+
+def test_in_process_sharding_over_all_devices(native, oracle):
+    """snapgpu_init over every visible GPU: the file list is sharded across them inside one call (no
+    collective; results gathered by index).  With one GPU this is the single-device path again."""
+    import torch
+    from snappy_b200 import helpers, synth
+    ndev = torch.cuda.device_count()
+    native.init(list(range(ndev)))
+    try:
+        lengths = np.concatenate([synth.lognormal_sizes(20_000), [5_000_000, 0, 3]]).astype(np.uint64)
+        data, off, ln = synth.make_host_batch(lengths)
+        assert np.array_equal(helpers.sha512_batch(data, off, ln), oracle.sha512_batch(data, off, ln, 8))
+        b = data.copy()
+        flips = [0, 9_999, 19_999, 20_000]
+        for i in flips:
+            b[int(off[i])] ^= 1
+        assert np.nonzero(helpers.cmp_batch(data, b, off, ln) == 0)[0].tolist() == flips
+        assert native.lib().snapgpu_num_devices() == ndev
+    finally:
+        native.init([int(os.environ.get("LOCAL_RANK", "0"))])
