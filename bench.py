@@ -325,7 +325,7 @@ def main():
         sampler.begin()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            dg = helpers.sha512_batch(host_view, offsets, lengths)
+            dg = helpers.sha512_batch(host_view, offsets, lengths, out=dg)     # digests land in host memory
         torch.cuda.synchronize()
         dt = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
         sampler.end()

@@ -747,11 +747,25 @@ struct Chunk {
     bool dense_out;        // user_index runs first..first+count-1: results move with one memcpy
 };
 
+// The items of one shard: an explicit list, or -- the common call, plain files on one device --
+// the caller's offsets/lengths arrays used in place (no per-file copy in front of the first DMA).
+struct ItemList {
+    const WorkItem *items = nullptr;
+    const uint64_t *offs = nullptr, *lens = nullptr;
+    size_t n = 0;
+    ItemList() {}
+    ItemList(const std::vector<WorkItem> &v) : items(v.data()), n(v.size()) {}
+    ItemList(const uint64_t *o, const uint64_t *l, size_t count) : offs(o), lens(l), n(count) {}
+    WorkItem at(size_t k) const { return items ? items[k] : WorkItem{k, offs[k], lens[k], 0, 0}; }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+};
+
 struct ChunkPlan {
     std::vector<Chunk> chunks;
     std::vector<WorkItem> pieces;   // continuation segments (SHA) / sub-ranges (cmp) of oversized items
-    const WorkItem *base = nullptr;
-    const WorkItem &item(const Chunk &c, size_t i) const { return (c.in_pieces ? pieces.data() : base)[c.first + i]; }
+    ItemList base;
+    WorkItem item(const Chunk &c, size_t i) const { return c.in_pieces ? pieces[c.first + i] : base.at(c.first + i); }
 };
 
 // Cuts a shard's item list into chunks that fit the staging buffer, one chunk per next() call,
@@ -759,17 +773,17 @@ struct ChunkPlan {
 // instead of after the whole list.  Items longer than the staging buffer are split into
 // continuation segments (SHA) or sub-ranges (cmp); items that fit are referenced in place.
 struct ChunkStream {
-    const std::vector<WorkItem> &in;
+    const ItemList in;
     const bool is_sha;
     ChunkPlan &plan;
     size_t k = 0;             // next item of `in`
     uint64_t piece_done = 0;  // bytes of in[k] already emitted as pieces (only while splitting)
     bool splitting = false;
 
-    ChunkStream(const std::vector<WorkItem> &items, bool sha, ChunkPlan &p) : in(items), is_sha(sha), plan(p) {
+    ChunkStream(const ItemList &items, bool sha, ChunkPlan &p) : in(items), is_sha(sha), plan(p) {
         plan.chunks.clear();
         plan.pieces.clear();
-        plan.base = in.data();
+        plan.base = in;
     }
 
     static uint64_t usable_of(size_t cap) { return (cap - 64) & ~(uint64_t)127; }
@@ -781,13 +795,13 @@ struct ChunkStream {
         const uint64_t usable_max = usable_of(cap_max);
         if (!splitting) {
             if (k >= in.size()) return false;
-            if (in[k].len + 16 > usable_max) {
+            if (in.at(k).len + 16 > usable_max) {
                 splitting = true;
                 piece_done = 0;
             }
         }
         if (splitting) {
-            const WorkItem &w = in[k];
+            const WorkItem w = in.at(k);
             uint64_t piece = std::min<uint64_t>(w.len - piece_done, usable_max - 128);
             piece = (piece_done + piece < w.len) ? (piece & ~(uint64_t)127) : piece;
             WorkItem s = w;
@@ -810,18 +824,21 @@ struct ChunkStream {
             plan.chunks.push_back(*out);
             return true;
         }
-        const uint64_t usable = in[k].len + 16 > usable_of(cap_now) ? usable_max : usable_of(cap_now);
-        Chunk cur{k, 0, false, in[k].off & ~(uint64_t)15, in[k].off + in[k].len, false, true};
+        const WorkItem head = in.at(k);
+        const uint64_t usable = head.len + 16 > usable_of(cap_now) ? usable_max : usable_of(cap_now);
+        Chunk cur{k, 0, false, head.off & ~(uint64_t)15, head.off + head.len, false, true};
+        size_t prev_user = 0;
         for (; k < in.size(); k++) {
-            const WorkItem &w = in[k];
+            const WorkItem w = in.at(k);
             const uint64_t begin = w.off & ~(uint64_t)15;
             const uint64_t end = w.off + w.len;
             if (cur.count) {
                 const bool fits = w.len + 16 <= usable_max && cur.count < kMaxChunkItems && begin >= cur.span_begin &&
                                   end - cur.span_begin <= usable && w.off <= cur.span_end + (1u << 20);
                 if (!fits) break;
-                if (w.user_index != in[k - 1].user_index + 1) cur.dense_out = false;
+                if (w.user_index != prev_user + 1) cur.dense_out = false;
             }
+            prev_user = w.user_index;
             cur.span_end = std::max(cur.span_end, end);
             cur.count++;
             cur.needs_state_in = cur.needs_state_in || (is_sha && (w.flags & kSegContinue));
@@ -833,7 +850,7 @@ struct ChunkStream {
 };
 
 // All chunks of a list for one fixed staging size (test hook).
-static void build_chunks(const std::vector<WorkItem> &in, size_t cap, bool is_sha, ChunkPlan &plan) {
+static void build_chunks(const ItemList &in, size_t cap, bool is_sha, ChunkPlan &plan) {
     ChunkStream cs(in, is_sha, plan);
     Chunk c;
     while (cs.next(cap, cap, &c)) {}
@@ -849,7 +866,7 @@ static size_t ramp_cap(size_t chunk_index, size_t cap_max) {
 }
 
 // Runs one device's shard of a host-buffer SHA-512 batch.  digests: caller's n*64 array.
-static int sha512_shard(Device &D, const uint8_t *data, const std::vector<WorkItem> &shard, uint8_t *digests) {
+static int sha512_shard(Device &D, const uint8_t *data, const ItemList &shard, uint8_t *digests) {
     if (shard.empty()) return 0;
     std::lock_guard<std::mutex> lock(D.mu);
     SG_CUDA(cudaSetDevice(D.ordinal));
@@ -901,10 +918,10 @@ static int sha512_shard(Device &D, const uint8_t *data, const std::vector<WorkIt
         }
         SG_CUDA(cudaStreamWaitEvent(D.compute_stream, D.ev_copied[b], 0));
         {
-            const WorkItem *wp = &plan.item(c, 0);
             const uint64_t rebase = phase - c.span_begin;       // host offset -> staging offset
-            auto get = [wp, rebase](size_t i) {
-                return SegDesc{wp[i].off + rebase, wp[i].len, wp[i].prefix, (u32)i, wp[i].flags};
+            auto get = [&plan, &c, rebase](size_t i) {
+                const WorkItem w = plan.item(c, i);
+                return SegDesc{w.off + rebase, w.len, w.prefix, (u32)i, w.flags};
             };
             if ((rc = launch_sha512(D, D.compute_stream, D.d_stage[b], get, c.count, D.d_out[b]))) return rc;
         }
@@ -922,7 +939,7 @@ static int sha512_shard(Device &D, const uint8_t *data, const std::vector<WorkIt
     return 0;
 }
 
-static int cmp_shard(Device &D, const uint8_t *a, const uint8_t *b_host, const std::vector<WorkItem> &shard,
+static int cmp_shard(Device &D, const uint8_t *a, const uint8_t *b_host, const ItemList &shard,
                      uint8_t *equal) {
     if (shard.empty()) return 0;
     std::lock_guard<std::mutex> lock(D.mu);
@@ -1180,6 +1197,8 @@ int snapgpu_sha512_batch(const uint8_t *data, const uint64_t *offsets, const uin
     if (nfiles == 0) return runtime_ready() ? 0 : fail(SNAPGPU_ENOINIT, "snapgpu_init has not been called (or failed)");
     if (!data || !offsets || !lengths || !digests) return fail(SNAPGPU_EINVAL, "null argument");
     if (!runtime_ready()) return fail(SNAPGPU_ENOINIT, "snapgpu_init has not been called (or failed)");
+    if (rt().devs.size() == 1)       // one device: the caller's arrays are the item list
+        return sha512_shard(*rt().devs[0], data, ItemList(offsets, lengths, nfiles), digests);
     std::vector<WorkItem> all(nfiles);
     for (size_t i = 0; i < nfiles; i++) {
         if (lengths[i] >= kMaxSegBytes) return fail(SNAPGPU_EINVAL, "file %zu too large", i);
@@ -1203,12 +1222,13 @@ int snapgpu_cmp_batch(const uint8_t *a, const uint8_t *b, const uint64_t *offset
     if (!runtime_ready()) return fail(SNAPGPU_ENOINIT, "snapgpu_init has not been called (or failed)");
     if (npairs == 0) return 0;
     if (!a || !b || !offsets || !lengths || !equal) return fail(SNAPGPU_EINVAL, "null argument");
+    memset(equal, 1, npairs);
+    if (rt().devs.size() == 1) return cmp_shard(*rt().devs[0], a, b, ItemList(offsets, lengths, npairs), equal);
     std::vector<WorkItem> all(npairs);
     std::vector<uint64_t> weight(npairs);
     for (size_t i = 0; i < npairs; i++) {
         all[i] = WorkItem{i, offsets[i], lengths[i], 0, 0};
         weight[i] = lengths[i] + 64;
-        equal[i] = 1;
     }
     std::vector<std::vector<WorkItem>> shards;
     shard_items(all, weight, (int)rt().devs.size(), shards);

@@ -58,13 +58,16 @@ def _u64(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.uint64)
 
 
-def sha512_batch(data: np.ndarray, offsets, lengths) -> np.ndarray:
-    """Digests ``(n, 64) uint8`` of ``data[offsets[i] : offsets[i] + lengths[i]]`` (host buffers)."""
+def sha512_batch(data: np.ndarray, offsets, lengths, out: np.ndarray | None = None) -> np.ndarray:
+    """Digests ``(n, 64) uint8`` of ``data[offsets[i] : offsets[i] + lengths[i]]`` (host buffers).
+    ``out`` may be a caller-owned ``(n, 64) uint8`` array to be filled (a loop reuses it)."""
     N.ensure_init()
     data = np.ascontiguousarray(data, dtype=np.uint8)
     offsets, lengths = _u64(offsets), _u64(lengths)
     n = len(offsets)
-    out = np.empty((n, 64), dtype=np.uint8)
+    if out is None:
+        out = np.empty((n, 64), dtype=np.uint8)
+    assert out.shape == (n, 64) and out.dtype == np.uint8 and out.flags.c_contiguous
     N.check(N.lib().snapgpu_sha512_batch(data.ctypes.data, offsets.ctypes.data, lengths.ctypes.data, n,
                                           out.ctypes.data))
     return out
