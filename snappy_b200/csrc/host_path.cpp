@@ -1056,6 +1056,7 @@ void cache_put(const struct stat &st, const uint8_t digest[64]) {
     memcpy(d.digest, digest, 64);
     DigestCache &C = digest_cache();
     std::lock_guard<std::mutex> lock(C.mu);
+    if (C.map.size() >= ((size_t)1 << 22)) C.map.clear();      // bounded: a build stages one tree at a time
     C.map[std::make_pair(st.st_dev, st.st_ino)] = d;
 }
 bool cache_get(const TreeEntry &e, uint8_t digest[64]) {
