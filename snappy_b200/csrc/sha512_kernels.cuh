@@ -227,12 +227,35 @@ __device__ __forceinline__ void stage_block(u32 stage_addr, u32 lane, const uint
     cp_async_commit();
 }
 
-template <int kAddMode, int kCtasPerSm>
+// Any byte alignment: the copies start at the 16-byte boundary at or below the block (p16), so the
+// staged line holds `phase` bytes of whatever precedes the file followed by the block, 144 bytes
+// in nine chunks.  end = phase + (bytes of the file in this block); nothing past it is read.
+__device__ __forceinline__ void stage_block_any(u32 stage_addr, u32 lane, const uint8_t *p16, long long end,
+                                                const uint8_t *safe) {
+    const u32 dst = stage_addr + lane * 16u;
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+        long long left = end - 16 * j;
+        u32 nbytes = left <= 0 ? 0u : (left >= 16 ? 16u : (u32)left);
+        const uint8_t *src = nbytes ? p16 + 16 * j : safe;
+        cp_async_16(dst + (u32)j * 512u, src, nbytes);
+    }
+    cp_async_commit();
+}
+
+constexpr int kStageBytesPerWarpAny = 9 * 32 * 16;   // 4.5 KiB: 144 bytes per lane
+
+// kAligned16 = false: files may start at any byte.  The staged line is read back as 33 words from
+// the file's own phase (four per-lane address deltas, one per word position mod 4, so a load is
+// still "register + immediate"), and ONE byte-permute per word both realigns by the sub-word
+// phase and swaps to big-endian -- the same 32 PRMTs the aligned form spends on the swap alone.
+template <int kAddMode, int kCtasPerSm, bool kAligned16 = true>
 __global__ void __launch_bounds__(kShaThreads, kCtasPerSm)
 sha512_segments_kernel_v2(const uint8_t *__restrict__ data, const SegDesc *__restrict__ descs,
                           const u32 *__restrict__ order, u32 nsegs,
                           uint8_t *__restrict__ digests, u32 *__restrict__ unit_counter, u32 one) {
-    __shared__ __align__(16) uint8_t stages[kShaWarpsPerCta][2][kStageBytesPerWarp];
+    constexpr int kStage = kAligned16 ? kStageBytesPerWarp : kStageBytesPerWarpAny;
+    __shared__ __align__(16) uint8_t stages[kShaWarpsPerCta][2][kStage];
     const u32 lane = threadIdx.x & 31;
     const u32 warp = threadIdx.x >> 5;
     const u32 nunits = (nsegs + 31) >> 5;
@@ -274,25 +297,50 @@ sha512_segments_kernel_v2(const uint8_t *__restrict__ data, const SegDesc *__res
 
         const uint8_t *p = data + sd.off;
         long long rem = (long long)sd.len;
-        stage_block(stage0, lane, p, rem, data);
+        // any alignment: phase of the file inside its 16-byte line, and what follows from it
+        const u32 phase = kAligned16 ? 0u : (u32)((uintptr_t)p & 15);
+        u32 delta[4] = {0, 0, 0, 0};      // smem byte offset of staged word (4m + r) minus 512 m
+        u32 prmt_sel = 0x0123;            // big-endian swap, shifted by the sub-word phase
+        if (!kAligned16) {
+            p -= phase;                   // 16-byte aligned from here on
+            const u32 ws = phase >> 2, bs = phase & 3;
+#pragma unroll
+            for (u32 r = 0; r < 4; r++) delta[r] = lane * 16u + (ws + r < 4 ? (ws + r) * 4u : 512u + (ws + r - 4) * 4u);
+            prmt_sel = (bs + 3) | ((bs + 2) << 4) | ((bs + 1) << 8) | (bs << 12);
+        }
+        auto stage = [&](u32 addr, const uint8_t *q, long long left) {
+            if (kAligned16) stage_block(addr, lane, q, left, data);
+            else stage_block_any(addr, lane, q, left > 0 ? (long long)phase + (left < 128 ? left : 128) : 0, data);
+        };
+        stage(stage0, p, rem);
 
         for (u32 blk = 0; blk < nblk_max; blk++) {
-            const u32 cur = stage0 + (blk & 1) * kStageBytesPerWarp;
-            const u32 nxt = stage0 + ((blk + 1) & 1) * kStageBytesPerWarp;
+            const u32 cur = stage0 + (blk & 1) * kStage;
+            const u32 nxt = stage0 + ((blk + 1) & 1) * kStage;
             const bool active = blk < nblk;
             const long long rem_now = rem;
             p += 128;
             rem -= 128;
-            stage_block(nxt, lane, p, rem, data);        // block blk+1 starts moving ...
+            stage(nxt, p, rem);                          // block blk+1 starts moving ...
             cp_async_wait<1>();                          // ... block blk has landed
             u64 w[16];
+            if (kAligned16) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                uint4 v;
-                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(cur + lane * 16u + (u32)j * 512u));
-                w[2 * j] = be64_from_le_words(v.x, v.y);
-                w[2 * j + 1] = be64_from_le_words(v.z, v.w);
+                for (int j = 0; j < 8; j++) {
+                    uint4 v;
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(cur + lane * 16u + (u32)j * 512u));
+                    w[2 * j] = be64_from_le_words(v.x, v.y);
+                    w[2 * j + 1] = be64_from_le_words(v.z, v.w);
+                }
+            } else {
+                u32 x[33];
+#pragma unroll
+                for (int k = 0; k < 33; k++)
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x[k]) : "r"(cur + delta[k & 3] + (u32)(k >> 2) * 512u));
+#pragma unroll
+                for (int j = 0; j < 16; j++)      // word j = bytes [8j, 8j+8) of the block, big-endian
+                    w[j] = pack64(__byte_perm(x[2 * j + 1], x[2 * j + 2], prmt_sel), __byte_perm(x[2 * j], x[2 * j + 1], prmt_sel));
             }
             if (__any_sync(0xffffffffu, active && rem_now < 128))
                 pad_block(w, rem_now, final_seg && (blk + 1 == nblk), total_len);

@@ -325,7 +325,12 @@ constexpr int kShaVariants = 6;
 //            issues at a quarter of the ALU rate and stalls the issue port it shares.
 // Input that is not 16-byte aligned always takes the register-load kernel (any alignment).
 static ShaKernel sha_kernel_for(int variant, bool aligned) {
-    if (!aligned) return sha512_segments_kernel<0x00, 0x0, false, kShaCtasPerSmMax>;
+    if (!aligned) {
+        // any byte alignment: the staged kernel reading from each file's own phase; variant 2
+        // selects the register-load kernel (33 aligned words + funnel shifts) it replaced
+        if (variant == 2) return sha512_segments_kernel<0x00, 0x0, false, kShaCtasPerSmMax>;
+        return sha512_segments_kernel_v2<0, kShaCtasPerSmMax, false>;
+    }
     switch (variant) {
     case 1: return sha512_segments_kernel_v2<1, kShaCtasPerSmMax>;
     case 2: return sha512_segments_kernel<0x00, 0x0, true, kShaCtasPerSmMax>;

@@ -43,7 +43,7 @@ def test_only_sm100a_code(native):
 
 def test_default_kernel_is_compact_and_staged(sass):
     """Variant 0: 16-round loop (fits the instruction cache), cp.async staging, no spills."""
-    c = find(sass, "sha512_segments_kernel_v2", "ILi0E")
+    c = find(sass, "sha512_segments_kernel_v2", "ILi0ELi3ELb1E")
     total = sum(c.values())
     assert total < 2600                                     # ~33 KB of code, was ~65 KB fully unrolled
     assert count(c, "LDGSTS") >= 16                         # cp.async: 8 full + 8 tail copies per block
@@ -51,6 +51,16 @@ def test_default_kernel_is_compact_and_staged(sass):
     assert count(c, "SHF.R.W") >= 16 * 12 * 2 + 16 * 10     # two round groups + one schedule group
     assert count(c, "LDL") == 0 and count(c, "STL") == 0
     assert count(c, "IMAD.WIDE") < 8 and count(c, "IMAD.HI") == 0   # both measured at half rate
+
+
+def test_any_alignment_kernel_is_staged_too(sass):
+    """Unaligned input: nine zero-filling cp.async per block, 33 word loads from the file's own phase, and
+    the same 32 byte-permutes as the aligned form (realign + byte swap in one PRMT); no spills."""
+    c = find(sass, "sha512_segments_kernel_v2", "ILi0ELi3ELb0E")
+    assert count(c, "LDGSTS") >= 9 and count(c, "LDS") >= 33
+    assert 32 <= count(c, "PRMT") <= 80
+    assert count(c, "LDL") == 0 and count(c, "STL") == 0
+    assert sum(c.values()) < 2700
 
 
 def test_fma_add_variant_mix(sass):
