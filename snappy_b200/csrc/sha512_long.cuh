@@ -43,6 +43,9 @@ __device__ __forceinline__ void st_volatile_shared(u32 *p, u32 v) {
 }
 
 // descs[first .. first+count) are the long segments of this CTA, count <= 32, similar lengths.
+// kAligned16 = false: the producer reads 33 aligned words per block and realigns them by the
+// file's byte phase (load_block<false>); the producer has time to spare, the chain is unaffected.
+template <bool kAligned16>
 __global__ void __launch_bounds__(kLongThreads, 1)
 sha512_long_kernel(const uint8_t *__restrict__ data, const SegDesc *__restrict__ descs, u32 nsegs,
                    uint8_t *__restrict__ digests) {
@@ -166,7 +169,7 @@ sha512_long_kernel(const uint8_t *__restrict__ data, const SegDesc *__restrict__
                 if (b < f_blocks) {
                     const long long rem = (long long)sd.len - (long long)b * 128;
                     u32 raw[32];
-                    load_block<true>(data + sd.off + (size_t)b * 128, rem, raw);
+                    load_block<kAligned16>(data + sd.off + (size_t)b * 128, rem, raw);
 #pragma unroll
                     for (int j = 0; j < 16; j++) w[j] = be64_from_le_words(raw[2 * j], raw[2 * j + 1]);
                     if (rem < 128) pad_block(w, rem, final_seg && (b + 1 == f_blocks), total_len);

@@ -204,7 +204,8 @@ static int init_device(Device &D, int ordinal) {
     SG_CUDA(cudaStreamCreateWithFlags(&D.copy_stream, cudaStreamNonBlocking));
     SG_CUDA(cudaStreamCreateWithFlags(&D.compute_stream, cudaStreamNonBlocking));
     SG_CUDA(cudaStreamCreateWithFlags(&D.long_stream, cudaStreamNonBlocking));
-    SG_CUDA(cudaFuncSetAttribute(sha512_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytes));
+    SG_CUDA(cudaFuncSetAttribute(sha512_long_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytes));
+    SG_CUDA(cudaFuncSetAttribute(sha512_long_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytes));
     for (auto &s : D.slots) {
         SG_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         SG_CUDA(cudaEventCreate(&s.uploaded));
@@ -472,7 +473,7 @@ static int launch_sha512(Device &D, cudaStream_t stream, const uint8_t *d_data, 
     // the higher throughput, the long kernel only the shorter chain.
     SegDesc *h_descs = static_cast<SegDesc *>(slot->h_buf);
     size_t n_long = 0;
-    if (aligned && info.n_long >= 1 && info.n_long <= kLongMaxCandidates && R.opt.long_kernel.load()) {
+    if (info.n_long >= 1 && info.n_long <= kLongMaxCandidates && R.opt.long_kernel.load()) {
         const uint64_t lanes = (uint64_t)D.sm_count * kShaThreads;
         const uint64_t threshold = std::max<uint64_t>(kLongMinBlocks, kLongDominance * (total_blocks / lanes));
         size_t dominant = 0;
@@ -538,8 +539,12 @@ static int launch_sha512(Device &D, cudaStream_t stream, const uint8_t *d_data, 
         SG_CUDA(cudaEventRecord(slot->fork, stream));
         SG_CUDA(cudaStreamWaitEvent(D.long_stream, slot->fork, 0));
         const u32 long_grid = (u32)((n_long + kLongFilesPerCta - 1) / kLongFilesPerCta);
-        sha512_long_kernel<<<long_grid, kLongThreads, kLongSmemBytes, D.long_stream>>>(d_data, plan.long_descs, (u32)n_long,
-                                                                                       d_digests);
+        if (aligned)
+            sha512_long_kernel<true><<<long_grid, kLongThreads, kLongSmemBytes, D.long_stream>>>(d_data, plan.long_descs,
+                                                                                                 (u32)n_long, d_digests);
+        else
+            sha512_long_kernel<false><<<long_grid, kLongThreads, kLongSmemBytes, D.long_stream>>>(d_data, plan.long_descs,
+                                                                                                  (u32)n_long, d_digests);
         SG_CUDA(cudaGetLastError());
         SG_CUDA(cudaEventRecord(slot->join, D.long_stream));
         R.kernel_launches++;

@@ -249,6 +249,10 @@ def test_long_file_kernel(gpu, oracle):
         assert np.array_equal(got, want), lengths[-4:]
         assert np.array_equal(plain, want)
         assert launches_with >= 1
+    # long files at odd offsets: the producer realigns, the consumer does not care
+    data, off, ln = pack([3 * MiB + 5, 100, 2 * MiB + 1, 17], rng, align=1, jitter=True)
+    assert (off % 16 != 0).any()
+    assert np.array_equal(helpers.sha512_batch(data, off, ln), oracle.sha512_batch(data, off, ln, 4))
     # more long files than the bin takes: all stay in the batched kernel
     lengths = [2 * MiB] * 260
     data, off, ln = pack(lengths, rng)
