@@ -712,3 +712,21 @@ def test_in_process_sharding_over_all_devices(native, oracle):
         assert native.lib().snapgpu_num_devices() == ndev
     finally:
         native.init([int(os.environ.get("LOCAL_RANK", "0"))])
+
+
+def test_cmp_large_pageable_buffers(gpu, oracle):
+    """Pairs of 1-6 MiB in ordinary (pageable) numpy memory: the spans go through the pinned bounce buffers
+    (h2d_span) and several staging chunks; differences at the first byte, the last byte and a tile edge."""
+    from snappy_b200 import helpers
+    gpu.set_option("staging_bytes", 16 << 20)
+    rng = np.random.default_rng(61)
+    lengths = [6 << 20, (1 << 20) + 5, 3 << 20, 4096, 0, (2 << 20) - 1, 5 << 20]
+    a, off, ln = pack(lengths, rng)
+    b = a.copy()
+    b[int(off[0])] ^= 1                                  # first byte of a pair
+    b[int(off[2]) + (3 << 20) - 1] ^= 1                  # last byte
+    b[int(off[6]) + 16384 * 77] ^= 1                     # first byte of a 16 KiB tile
+    got = helpers.cmp_batch(a, b, off, ln)
+    assert got.tolist() == [0, 1, 0, 1, 1, 1, 0]
+    assert np.array_equal(got, oracle.cmp_batch(a, b, off, ln, 4))
+    assert np.array_equal(helpers.sha512_batch(a, off, ln), oracle.sha512_batch(a, off, ln, 4))
