@@ -761,6 +761,14 @@ public:
         write_indicator("]", false, false, false);
     }
     void end_document() { put_break(); }
+    // Start as if a line had just been written by another emitter: the first sequence item
+    // then opens with the line break.  Lets several emitters write consecutive runs of entries
+    // whose outputs are simply concatenated.
+    void continue_after_line() {
+        column_ = 1;
+        whitespace_ = false;
+        indention_ = false;
+    }
 
 private:
     int column_ = 0, indent_ = 0;
@@ -1209,24 +1217,65 @@ int emit_hashes_yaml(const std::vector<TreeEntry> &entries, const uint8_t *diges
     if (entries.empty()) {
         em.empty_flow_sequence();
     } else {
-        size_t di = 1;
-        for (const TreeEntry &e : entries) {
-            if ((rc = yaml_file_mode(e.mode, &mode))) return rc;
-            em.begin_sequence_item();
-            em.key("name", true);
-            if ((rc = em.string_value(e.name))) return rc;
-            if (e.regular) {
-                em.key("size");
-                num = std::to_string((long long)e.size);
-                em.plain_value(num);
-                em.key("sha512");
-                hex_into(&digests[64 * di]);
-                if ((rc = em.string_value(hex))) return rc;
-                di++;
+        // one run of entries: the sequence items entries[lo, hi), digests from slot di on
+        auto emit_run = [&entries, digests](YamlEmitter &out, size_t lo, size_t hi, size_t di) -> int {
+            std::string hx(128, '0'), md, nm;
+            static const char dd[] = "0123456789abcdef";
+            int r;
+            for (size_t k = lo; k < hi; k++) {
+                const TreeEntry &e = entries[k];
+                if ((r = yaml_file_mode(e.mode, &md))) return r;
+                out.begin_sequence_item();
+                out.key("name", true);
+                if ((r = out.string_value(e.name))) return r;
+                if (e.regular) {
+                    out.key("size");
+                    nm = std::to_string((long long)e.size);
+                    out.plain_value(nm);
+                    out.key("sha512");
+                    const uint8_t *p = &digests[64 * di++];
+                    for (int i = 0; i < 64; i++) {
+                        hx[2 * i] = dd[p[i] >> 4];
+                        hx[2 * i + 1] = dd[p[i] & 15];
+                    }
+                    if ((r = out.string_value(hx))) return r;
+                }
+                out.key("mode");
+                if ((r = out.string_value(md))) return r;
+                out.end_sequence_item();
             }
-            em.key("mode");
-            if ((rc = em.string_value(mode))) return rc;
-            em.end_sequence_item();
+            return 0;
+        };
+        const unsigned nthreads = std::min<unsigned>(packer_threads(entries.size() / 256), 8);
+        if (nthreads < 2) {
+            if ((rc = emit_run(em, 0, entries.size(), 1))) return rc;
+        } else {
+            // large trees: consecutive runs of entries are written by several threads, each into
+            // its own emitter that starts "after a line"; the pieces are concatenated in order
+            std::vector<size_t> lo(nthreads + 1), first_digest(nthreads + 1, 1);
+            for (unsigned t = 0; t <= nthreads; t++) lo[t] = entries.size() * t / nthreads;
+            for (unsigned t = 0; t < nthreads; t++) {
+                size_t regs = 0;
+                for (size_t k = lo[t]; k < lo[t + 1]; k++) regs += entries[k].regular;
+                first_digest[t + 1] = first_digest[t] + regs;
+            }
+            std::vector<YamlEmitter> part(nthreads);
+            std::vector<int> rcs(nthreads, 0);
+            std::vector<std::string> errs(nthreads);
+            auto work = [&](unsigned t) {
+                part[t].out.reserve((lo[t + 1] - lo[t]) * 224);
+                part[t].continue_after_line();
+                rcs[t] = emit_run(part[t], lo[t], lo[t + 1], first_digest[t]);
+                if (rcs[t]) errs[t] = snapgpu_last_error();
+            };
+            std::vector<std::thread> th;
+            for (unsigned t = 1; t < nthreads; t++) th.emplace_back(work, t);
+            work(0);
+            for (auto &x : th) x.join();
+            for (unsigned t = 0; t < nthreads; t++) {          // the first failing entry in walk order
+                if (rcs[t]) return fail(rcs[t], "%s", errs[t].c_str());
+                em.out += part[t].out;
+            }
         }
     }
     em.end_document();
