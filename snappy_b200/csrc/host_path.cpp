@@ -340,11 +340,25 @@ int hash_files(const std::vector<std::string> &paths, std::vector<uint8_t> &dige
             sink_rc.assign(pf.size(), 0);
             sink_err.resize(pf.size());
             sink_thread = std::thread([&]() {
-                parallel_for(pf.size(), [&](size_t k) {
-                    const PackedFile &f = pf[k];
-                    sink_rc[k] = f.grew ? (*sink)(f.index, nullptr, 0) : (*sink)(f.index, buf + f.off, f.len);
-                    if (sink_rc[k]) sink_err[k] = snapgpu_last_error();
-                });
+                // contiguous ranges, one per thread: neighbouring files live in the same directory and
+                // creating files there serialises on the directory's lock, so threads should be in
+                // different directories at any one time
+                const size_t nt = std::max<size_t>(1, std::min<size_t>(nthreads, pf.size() / 64));
+                auto run = [&](size_t t) {
+                    for (size_t k = pf.size() * t / nt; k < pf.size() * (t + 1) / nt; k++) {
+                        const PackedFile &f = pf[k];
+                        sink_rc[k] = f.grew ? (*sink)(f.index, nullptr, 0) : (*sink)(f.index, buf + f.off, f.len);
+                        if (sink_rc[k]) sink_err[k] = snapgpu_last_error();
+                    }
+                };
+                const double ts = wall_ms();
+                std::vector<std::thread> th;
+                for (size_t t = 1; t < nt; t++) th.emplace_back(run, t);
+                run(0);
+                for (auto &x : th) x.join();
+                if (getenv("SNAPGPU_TRACE"))
+                    fprintf(stderr, "[snapgpu] batch %zu: sink wrote %zu files in %.2f ms on %zu threads\n", bi, pf.size(),
+                            wall_ms() - ts, nt);
             });
         }
         rc = sha512_host_segments(buf, segs.data(), segs.size(), out.data());
@@ -1681,8 +1695,10 @@ int copy_to_build_dir(const std::string &source_in, const std::string &build_dir
     struct stat root;
     if (lstat(source.c_str(), &root) != 0) return fail(SNAPGPU_EIO, "%s", go_path_error("lstat", source, errno).c_str());
     std::vector<CopyAction> actions;
+    const double t0 = wall_ms();
     int rc = copy_walk(source, build_dir, root, actions);
     if (rc) return rc;
+    const double t1 = wall_ms();
 
     // directories, then links; what cannot be linked is copied below
     std::vector<size_t> to_copy;
@@ -1696,6 +1712,7 @@ int copy_to_build_dir(const std::string &source_in, const std::string &build_dir
         }
     }
     if (to_copy.empty()) return 0;
+    const double t2 = wall_ms();
 
     std::vector<std::string> paths;
     std::vector<int64_t> sizes;
@@ -1735,7 +1752,11 @@ int copy_to_build_dir(const std::string &source_in, const std::string &build_dir
     };
     std::vector<uint8_t> digests;
     if ((rc = hash_files(paths, digests, &sizes, &sink))) return rc;
+    const double t3 = wall_ms();
     for (size_t k = 0; k < to_copy.size(); k++) cache_put(written[k], &digests[64 * k]);
+    if (getenv("SNAPGPU_TRACE"))
+        fprintf(stderr, "[snapgpu] copyToBuildDir: walk %.2f ms (%zu entries), mkdir/link %.2f ms, copy+hash %.2f ms (%zu files), cache %.2f ms\n",
+                t1 - t0, actions.size(), t2 - t1, t3 - t2, to_copy.size(), wall_ms() - t3);
     return 0;
 }
 
