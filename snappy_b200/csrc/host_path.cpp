@@ -1640,7 +1640,8 @@ struct CopyAction {
 // The Walk of copyToBuildDir: pre-order, sorted names, Lstat; excluded names are skipped
 // (directories with their whole subtree).  A directory that cannot be read, or an entry that
 // cannot be lstat'ed, is the error Walk hands to the callback and the callback returns.
-int copy_walk(const std::string &src, const std::string &dest, const struct stat &st, std::vector<CopyAction> &out) {
+int copy_walk(const std::string &src, const std::string &dest, const struct stat &st, std::vector<CopyAction> &out,
+              bool top_level = false) {
     if (should_exclude(base_name(src))) return 0;
     out.push_back(CopyAction{src, dest, st});
     if (!S_ISDIR(st.st_mode)) return 0;
@@ -1661,6 +1662,43 @@ int copy_walk(const std::string &src, const std::string &dest, const struct stat
             return fail(SNAPGPU_EIO, "%s", go_path_error("lstat", src + "/" + names[i], e).c_str());
         }
     closedir(d);
+
+    // sub-directories of the root: walked by several threads, each into its own list, and
+    // stitched back in Walk order below (the first error in that order is the one returned)
+    std::vector<size_t> subdirs;
+    if (top_level)
+        for (size_t i = 0; i < names.size(); i++)
+            if (S_ISDIR(sts[i].st_mode)) subdirs.push_back(i);
+    const unsigned nthreads = std::min<unsigned>(packer_threads(16 * subdirs.size()), (unsigned)subdirs.size());
+    if (nthreads >= 2) {
+        std::vector<std::vector<CopyAction>> sub(subdirs.size());
+        std::vector<int> sub_rc(subdirs.size(), 0);
+        std::vector<std::string> sub_err(subdirs.size());
+        std::atomic<size_t> next{0};
+        auto work = [&]() {
+            for (size_t k; (k = next.fetch_add(1)) < subdirs.size();) {
+                const size_t i = subdirs[k];
+                sub_rc[k] = copy_walk(src + "/" + names[i], dest + "/" + names[i], sts[i], sub[k]);
+                if (sub_rc[k]) sub_err[k] = snapgpu_last_error();
+            }
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nthreads; t++) th.emplace_back(work);
+        work();
+        for (auto &x : th) x.join();
+        size_t k = 0;
+        for (size_t i = 0; i < names.size(); i++) {
+            if (S_ISDIR(sts[i].st_mode)) {
+                if (sub_rc[k]) return fail(sub_rc[k], "%s", sub_err[k].c_str());
+                out.insert(out.end(), std::make_move_iterator(sub[k].begin()), std::make_move_iterator(sub[k].end()));
+                k++;
+            } else {
+                int rc = copy_walk(src + "/" + names[i], dest + "/" + names[i], sts[i], out);
+                if (rc) return rc;
+            }
+        }
+        return 0;
+    }
     for (size_t i = 0; i < names.size(); i++) {
         int rc = copy_walk(src + "/" + names[i], dest + "/" + names[i], sts[i], out);
         if (rc) return rc;
@@ -1696,7 +1734,7 @@ int copy_to_build_dir(const std::string &source_in, const std::string &build_dir
     if (lstat(source.c_str(), &root) != 0) return fail(SNAPGPU_EIO, "%s", go_path_error("lstat", source, errno).c_str());
     std::vector<CopyAction> actions;
     const double t0 = wall_ms();
-    int rc = copy_walk(source, build_dir, root, actions);
+    int rc = copy_walk(source, build_dir, root, actions, true);
     if (rc) return rc;
     const double t1 = wall_ms();
 
@@ -1704,15 +1742,35 @@ int copy_to_build_dir(const std::string &source_in, const std::string &build_dir
     std::vector<size_t> to_copy;
     for (size_t i = 0; i < actions.size(); i++) {
         const CopyAction &a = actions[i];
-        if (S_ISDIR(a.st.st_mode)) {
-            if (mkdir(a.dest.c_str(), a.st.st_mode & 07777) != 0)
-                return fail(SNAPGPU_EIO, "%s", go_path_error("mkdir", a.dest, errno).c_str());
-        } else if ((flags & SNAPGPU_COPY_NO_LINK) || link(a.src.c_str(), a.dest.c_str()) != 0) {
-            to_copy.push_back(i);
-        }
+        if (S_ISDIR(a.st.st_mode) && mkdir(a.dest.c_str(), a.st.st_mode & 07777) != 0)
+            return fail(SNAPGPU_EIO, "%s", go_path_error("mkdir", a.dest, errno).c_str());
     }
-    if (to_copy.empty()) return 0;
+    {
+        // link() for every non-directory, contiguous ranges of the walk per thread (threads then
+        // work in different directories); a failed link is not an error, the entry is copied
+        std::vector<uint8_t> need_copy(actions.size(), 0);
+        const size_t nt = (flags & SNAPGPU_COPY_NO_LINK) ? 1 : std::max<size_t>(1, packer_threads(actions.size() / 64));
+        auto run = [&](size_t t) {
+            for (size_t i = actions.size() * t / nt; i < actions.size() * (t + 1) / nt; i++) {
+                const CopyAction &a = actions[i];
+                if (S_ISDIR(a.st.st_mode)) continue;
+                need_copy[i] = (flags & SNAPGPU_COPY_NO_LINK) || link(a.src.c_str(), a.dest.c_str()) != 0;
+            }
+        };
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < nt; t++) th.emplace_back(run, t);
+        run(0);
+        for (auto &x : th) x.join();
+        for (size_t i = 0; i < actions.size(); i++)
+            if (need_copy[i]) to_copy.push_back(i);
+    }
     const double t2 = wall_ms();
+    if (to_copy.empty()) {
+        if (getenv("SNAPGPU_TRACE"))
+            fprintf(stderr, "[snapgpu] copyToBuildDir: walk %.2f ms (%zu entries), mkdir/link %.2f ms, nothing to copy\n",
+                    t1 - t0, actions.size(), t2 - t1);
+        return 0;
+    }
 
     std::vector<std::string> paths;
     std::vector<int64_t> sizes;

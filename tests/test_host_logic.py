@@ -257,3 +257,41 @@ def test_copy_to_build_dir_links_like_the_oracle(native, oracle, tmp_path):
     make_source_tree(bak)
     build.copyToBuildDir(str(bak), str(tmp_path / "t3"))
     assert not (tmp_path / "t3").exists()
+
+
+def test_copy_to_build_dir_wide_tree_parallel_walk(native, oracle, tmp_path):
+    """Many sub-directories: the root's subtrees are walked and linked by several threads; the result
+    (including exclusions below the top level and an unreadable directory's error) equals the oracle's."""
+    from snappy_b200 import build
+    rng = np.random.default_rng(7)
+    src = tmp_path / "src"
+    src.mkdir()
+    for d in range(40):
+        sub = src / f"d{d:03d}"
+        (sub / "deep" / "er").mkdir(parents=True)
+        for f in range(25):
+            (sub / f"f{f:02d}.bin").write_bytes(rng.bytes(int(rng.integers(0, 300))))
+        (sub / "deep" / "x~").write_text("backup")
+        (sub / "deep" / ".git").mkdir()
+        (sub / "deep" / ".git" / "HEAD").write_text("ref")
+        (sub / "deep" / "er" / "leaf").write_text(f"leaf {d}")
+        os.symlink("../f00.bin", sub / "deep" / "ln")
+    (src / "top.txt").write_text("top")
+    (src / "CVS").mkdir()
+    (src / "CVS" / "Entries").write_text("x")
+    got, want = tmp_path / "got", tmp_path / "want"
+    build.copyToBuildDir(str(src), str(got))
+    oracle.copy_to_build_dir(str(src), str(want))
+    a, b = snapshot(got), snapshot(want)
+    assert a == b and len(a) == 40 * (25 + 5) + 1
+    assert all(v[3] for v in a.values() if v[0] == "f")    # every file hard-linked
+    if os.geteuid() != 0:                                  # root reads everything
+        os.chmod(src / "d017" / "deep", 0)
+        try:
+            with pytest.raises(OSError) as e1:
+                build.copyToBuildDir(str(src), str(tmp_path / "g2"))
+            with pytest.raises(OSError) as e2:
+                oracle.copy_to_build_dir(str(src), str(tmp_path / "w2"))
+            assert "d017/deep" in str(e1.value) and "d017/deep" in str(e2.value)
+        finally:
+            os.chmod(src / "d017" / "deep", 0o755)
