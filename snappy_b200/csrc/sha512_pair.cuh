@@ -1,0 +1,270 @@
+// sha512_pair.cuh -- the long-file bin, second form: one SHA-512 chain on TWO lanes.
+//
+// sha512_long_kernel (sha512_long.cuh) takes the message schedule off the serial chain; what is
+// left on the consumer's lane is the 80 rounds, ~2250 ALU instructions per block, and a lone
+// warp issues one ALU instruction per 2 clocks however many of its lanes are active.  This
+// kernel halves the round itself across a lane pair, in SIMT: the SHA-2 round is two coupled
+// recurrences,
+//
+//     e' = d + T1,  T1 = h + Sigma1(e) + Ch(e,f,g) + (W+K)        (lane 0 keeps e,f,g,h)
+//     a' = T1 + Sigma0(a) + Maj(a,b,c)                            (lane 1 keeps a,b,c,d)
+//
+// and both have the same shape: new = Sigma(x0) + F(x0,x1,x2) + P (+ D).  One instruction
+// stream serves both lanes with per-lane parameters:
+//   * Sigma in factored form rotr(x ^ rotr(x,p) ^ rotr(x,q), s) with (p,q,s) = (4,27,14) for
+//     Sigma1 and (6,11,28) for Sigma0 -- all below 32, so the same six funnel shifts with the
+//     amounts in registers;
+//   * Maj(a,b,c) = Ch(~(a^b), b, c): t = LOP3(x0, x1, lane-mask) picks x0 or ~(x0^x1), then one
+//     Ch LOP3;
+//   * P = h + (W+K) on lane 0 and T1 on lane 1; D = d on lane 0 and 0 on lane 1.
+// 18 ALU instructions per round for the pair instead of 28 for one lane.  The lanes talk through
+// shared-memory mailboxes read by the very loads that fetch W+K (lane 0's "next W+K" load is
+// lane 1's "T1 of two rounds ago" load; lane 0's "d" load reads what lane 1 stored two iterations
+// earlier), so no select or shuffle sits in the loop.  Lane 1 runs two rounds behind lane 0,
+// which puts a whole iteration between every store and the load that needs it; a block is 82
+// iterations, and lane 1's two idle ones at the start are used to shift its window in: its
+// mailbox is seeded so that they reproduce b and a (the round is solved for T1).
+//
+// Producer warp, ring protocol and descriptors are those of sha512_long_kernel; the ring is
+// laid out [step][file][81 words] so that a round's W+K is at base + 8*t whatever the number of
+// files.
+#pragma once
+#include "sha512_long.cuh"
+
+namespace snapgpu {
+
+constexpr int kPairFilesPerCta = 16;                 // one consumer lane PAIR per file
+constexpr int kPairMailWords = 89;                   // T[-2..86] / A[-2..86] of one file.  Odd, so that a file's T and A
+                                                     // and the T's of neighbouring files (stride 178 = 2 mod 16 words)
+                                                     // fall into different banks for the 16 lanes of a half-warp
+constexpr int kPairRingPad = 8;                      // the last slot's W+K prefetch runs 2 words over
+constexpr size_t kPairRingBytes = (size_t)(kLongRingWords + kPairRingPad) * 8;
+constexpr size_t kPairMailBytes = (size_t)kPairFilesPerCta * 2 * kPairMailWords * 8;
+constexpr size_t kPairZeroBytes = (size_t)kPairMailWords * 8;
+constexpr size_t kPairSmemBytes = kPairRingBytes + kPairMailBytes + 2 * kPairZeroBytes + 16;
+
+// rotr64 by a per-lane amount below 32
+__device__ __forceinline__ u64 rotr64_var(u64 x, u32 r) {
+    u32 lo, hi;
+    unpack64(x, lo, hi);
+    return pack64(__funnelshift_r(lo, hi, r), __funnelshift_r(hi, lo, r));
+}
+// Sigma0 / Sigma1 by lane: rotr(x ^ rotr(x,p) ^ rotr(x,q), s)
+__device__ __forceinline__ u64 pair_sigma(u64 x, u32 p, u32 q, u32 s) {
+    u32 lo, hi, alo, ahi, blo, bhi;
+    unpack64(x, lo, hi);
+    alo = __funnelshift_r(lo, hi, p);
+    ahi = __funnelshift_r(hi, lo, p);
+    blo = __funnelshift_r(lo, hi, q);
+    bhi = __funnelshift_r(hi, lo, q);
+    const u32 ylo = lop3_xor3(lo, alo, blo), yhi = lop3_xor3(hi, ahi, bhi);
+    return pack64(__funnelshift_r(ylo, yhi, s), __funnelshift_r(yhi, ylo, s));
+}
+// lane 0 (mask 0): Ch(x0,x1,x2); lane 1 (mask ~0): Maj(x0,x1,x2) = Ch(~(x0^x1), x1, x2)
+__device__ __forceinline__ u32 pair_f32(u32 x0, u32 x1, u32 x2, u32 mask) {
+    u32 t;
+    asm("lop3.b32 %0, %1, %2, %3, 0xD2;" : "=r"(t) : "r"(x0), "r"(x1), "r"(mask));   // m ? ~(a^b) : a
+    return lop3_ch(t, x1, x2);
+}
+__device__ __forceinline__ u64 pair_f(u64 x0, u64 x1, u64 x2, u32 mask) {
+    u32 a0, a1, b0, b1, c0, c1;
+    unpack64(x0, a0, a1);
+    unpack64(x1, b0, b1);
+    unpack64(x2, c0, c1);
+    return pack64(pair_f32(a0, b0, c0, mask), pair_f32(a1, b1, c1, mask));
+}
+// x * mul + y with mul in {0,1}: lane 0 adds its h to W+K, lane 1 takes T1 as it is.  The two
+// multiplies run on the FMA pipe.
+__device__ __forceinline__ u64 pair_muladd(u64 x, u32 mul, u64 y) {
+    u32 lo, hi;
+    unpack64(x, lo, hi);
+    return pack64(lo * mul, hi * mul) + y;
+}
+
+template <bool kAligned16>
+__global__ void __launch_bounds__(kLongThreads, 1)
+sha512_pair_kernel(const uint8_t *__restrict__ data, const SegDesc *__restrict__ descs, u32 nsegs,
+                   uint8_t *__restrict__ digests) {
+    extern __shared__ __align__(16) uint8_t pair_smem[];
+    u64 *ring = reinterpret_cast<u64 *>(pair_smem);
+    u64 *mail = reinterpret_cast<u64 *>(pair_smem + kPairRingBytes);
+    u64 *zero = reinterpret_cast<u64 *>(pair_smem + kPairRingBytes + kPairMailBytes);
+    u64 *junk = zero + kPairMailWords;
+    u32 *produced = reinterpret_cast<u32 *>(pair_smem + kPairRingBytes + kPairMailBytes + 2 * kPairZeroBytes);
+    u32 *consumed = produced + 1;
+
+    const u32 lane = threadIdx.x & 31;
+    const u32 warp = threadIdx.x >> 5;
+    const u32 first = blockIdx.x * kPairFilesPerCta;
+    const u32 count = min((u32)kPairFilesPerCta, nsegs - first);
+
+    if (threadIdx.x == 0) {
+        st_volatile_shared(produced, 0);
+        st_volatile_shared(consumed, 0);
+    }
+    for (u32 i = threadIdx.x; i < (u32)kPairMailWords; i += kLongThreads) zero[i] = 0;
+    __syncthreads();
+
+    const u32 nf = count;                                  // files of this CTA (1..16)
+    const u32 ring_steps = 256 / nf;                       // block steps the ring holds
+
+    if (warp == 0) {
+        // ---------------- consumer: lane pair (2f, 2f+1) runs the rounds of file f ----------------
+        const u32 file = lane >> 1, role = lane & 1;       // role 0: e,f,g,h   role 1: a,b,c,d
+        const bool have = file < count;
+        SegDesc sd;
+        sd.off = 0; sd.len = 0; sd.prefix = 0; sd.out_idx = 0; sd.flags = kSegNoFinal;
+        if (have) sd = descs[first + file];
+        const u32 my_blocks = have ? (u32)seg_blocks(sd.len, sd.flags) : 0u;
+        const u32 steps = __reduce_max_sync(0xffffffffu, my_blocks);
+        uint8_t *out_digest = digests + (size_t)sd.out_idx * 64 + (role ? 0 : 32);
+        u64 st[4];                                         // role 1: H0..H3, role 0: H4..H7
+        if (have && (sd.flags & kSegContinue)) {
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(out_digest);
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                uint4 v = s4[i];
+                st[2 * i] = be64_from_le_words(v.x, v.y);
+                st[2 * i + 1] = be64_from_le_words(v.z, v.w);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) st[i] = kIV512[(role ? 0 : 4) + i];
+        }
+        // per-lane parameters of the shared instruction stream
+        const u32 rp = role ? 6u : 4u, rq = role ? 11u : 27u, rs = role ? 28u : 14u;
+        const u32 mask = role ? 0xffffffffu : 0u, mul = role ? 0u : 1u;
+        volatile u64 *Tm = mail + (size_t)(2 * min(file, (u32)kPairFilesPerCta - 1)) * kPairMailWords;   // T[k] = Tm[k+2]
+        volatile u64 *Am = Tm + kPairMailWords;                                                     // A[k] = Am[k+2]
+        volatile u64 *const out = (role ? Am : Tm) + 2;    // iteration i stores T1_i / a_(i-1)
+        volatile u64 *const din = role ? zero : Am;        // iteration i adds A[i-2] = a_(i-3) / 0
+        volatile u64 *const seed_a = role ? Am : junk;     // prologue: A[-2], A[-1]
+        volatile u64 *const seed_t = role ? Tm : junk + 4; // prologue: T[-2], T[-1]
+
+        u32 ready = 0, slot_index = 0;
+        for (u32 b = 0; b < steps; b++) {
+            if (b >= ready) {
+                do ready = ld_volatile_shared(produced); while (b >= ready);
+                __threadfence_block();
+            }
+            volatile u64 *const kin = role ? Tm : ring + ((size_t)slot_index * nf + min(file, nf - 1)) * kLongSlotWords;
+            slot_index = slot_index + 1 == ring_steps ? 0 : slot_index + 1;
+
+            // prologue.  role 1 publishes d, c and the two seeds that make its idle iterations
+            // 0 and 1 produce b and a; its window starts as (c, d, 0).
+            u64 S0 = role ? st[2] : st[0], S1 = role ? st[3] : st[1], S2 = role ? 0 : st[2], S3 = role ? 0 : st[3];
+            seed_a[0] = st[3];
+            seed_a[1] = st[2];
+            seed_t[0] = st[1] - pair_sigma(st[2], rp, rq, rs) - pair_f(st[2], st[3], 0, mask);
+            seed_t[1] = st[0] - pair_sigma(st[1], rp, rq, rs) - pair_f(st[1], st[2], st[3], mask);
+            __syncwarp();
+            u64 D = din[0];
+            u64 PD = pair_muladd(S3, mul, kin[0]) + D;     // h + (W+K) + d  |  T1
+
+#define SNAPGPU_PAIR_ITER(KIN, DIN, OUT, I)                                                   \
+    {                                                                                            \
+        const u64 kwn = (KIN)[(I) + 1];                                                          \
+        const u64 dn = (DIN)[(I) + 1];                                                           \
+        const u64 e = pair_sigma(S0, rp, rq, rs) + pair_f(S0, S1, S2, mask) + PD;                \
+        (OUT)[(I)] = e - D;                                                                      \
+        PD = pair_muladd(S2, mul, kwn) + dn;                                                     \
+        D = dn;                                                                                  \
+        S3 = S2; S2 = S1; S1 = S0; S0 = e;                                                       \
+    }
+#pragma unroll 1
+            for (int grp = 0; grp < 5; grp++) {
+                volatile u64 *const k = kin + 16 * grp, *const d = din + 16 * grp, *const o = out + 16 * grp;
+                SNAPGPU_PAIR_ITER(k, d, o, 0)  SNAPGPU_PAIR_ITER(k, d, o, 1)
+                SNAPGPU_PAIR_ITER(k, d, o, 2)  SNAPGPU_PAIR_ITER(k, d, o, 3)
+                SNAPGPU_PAIR_ITER(k, d, o, 4)  SNAPGPU_PAIR_ITER(k, d, o, 5)
+                SNAPGPU_PAIR_ITER(k, d, o, 6)  SNAPGPU_PAIR_ITER(k, d, o, 7)
+                SNAPGPU_PAIR_ITER(k, d, o, 8)  SNAPGPU_PAIR_ITER(k, d, o, 9)
+                SNAPGPU_PAIR_ITER(k, d, o, 10) SNAPGPU_PAIR_ITER(k, d, o, 11)
+                SNAPGPU_PAIR_ITER(k, d, o, 12) SNAPGPU_PAIR_ITER(k, d, o, 13)
+                SNAPGPU_PAIR_ITER(k, d, o, 14) SNAPGPU_PAIR_ITER(k, d, o, 15)
+            }
+            // role 0 is done after iteration 79; role 1 needs two more
+            const u64 e0 = S0, e1 = S1, e2 = S2, e3 = S3;
+            {
+                volatile u64 *const k = kin + 80, *const d = din + 80, *const o = out + 80;
+                SNAPGPU_PAIR_ITER(k, d, o, 0)  SNAPGPU_PAIR_ITER(k, d, o, 1)
+            }
+#undef SNAPGPU_PAIR_ITER
+            if (b < my_blocks) {
+                st[0] += role ? S0 : e0;
+                st[1] += role ? S1 : e1;
+                st[2] += role ? S2 : e2;
+                st[3] += role ? S3 : e3;
+            }
+            // this step's slot may be overwritten once every lane has read it
+            __syncwarp();
+            if (lane == 0) st_volatile_shared(consumed, b + 1);
+        }
+        if (have) {
+            uint4 *o4 = reinterpret_cast<uint4 *>(out_digest);
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                u32 a_lo, a_hi, b_lo, b_hi;
+                unpack64(st[2 * i], a_lo, a_hi);
+                unpack64(st[2 * i + 1], b_lo, b_hi);
+                o4[i] = make_uint4(bswap32(a_hi), bswap32(a_lo), bswap32(b_hi), bswap32(b_lo));
+            }
+        }
+    } else {
+        // ---------------- producer: W[t] + K[t] of 32 (file, block) pairs per round ----------------
+        // every lane needs the step count: the longest file of the CTA
+        u32 blocks_of = 0;
+        if (lane < count) {
+            const SegDesc *d = descs + first + lane;
+            blocks_of = (u32)seg_blocks(d->len, d->flags);
+        }
+        const u32 steps = __reduce_max_sync(0xffffffffu, blocks_of);
+        // lane -> (file = lane % nf, step offset = lane / nf); a round covers `per` consecutive steps
+        const u32 per = 32 / nf;                           // steps per round (>= 2); ring_steps >= 8 * per
+        const u32 pf = lane % nf, ps = lane / nf;
+        const bool worker = ps < per;                      // 32 % nf leftover lanes idle
+        const SegDesc sd = descs[first + pf];
+        const u32 f_blocks = (u32)seg_blocks(sd.len, sd.flags);
+        const bool final_seg = !(sd.flags & kSegNoFinal);
+        const u64 total_len = sd.prefix + sd.len;
+        u32 done = 0;                                      // steps published so far
+        while (done < steps) {
+            const u32 upto = min(steps, done + per);
+            u32 freed;
+            while (freed = ld_volatile_shared(consumed), upto > freed + ring_steps) __nanosleep(200);
+            __threadfence_block();
+            const u32 b = done + ps;
+            if (worker && b < upto) {
+                u64 w[16];
+                if (b < f_blocks) {
+                    const long long rem = (long long)sd.len - (long long)b * 128;
+                    u32 raw[32];
+                    load_block<kAligned16>(data + sd.off + (size_t)b * 128, rem, raw);
+#pragma unroll
+                    for (int j = 0; j < 16; j++) w[j] = be64_from_le_words(raw[2 * j], raw[2 * j + 1]);
+                    if (rem < 128) pad_block(w, rem, final_seg && (b + 1 == f_blocks), total_len);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) w[j] = 0;       // past this file's end: result is discarded
+                }
+                u64 *slot = ring + ((size_t)(b % ring_steps) * nf + pf) * kLongSlotWords;
+#pragma unroll 1
+                for (int grp = 0; grp < 5; grp++) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) slot[grp * 16 + i] = w[i] + c_K512[grp * 16 + i];
+                    if (grp < 4) {
+#pragma unroll
+                        for (int i = 0; i < 16; i++)
+                            w[i] = small_sigma1(w[(i + 14) & 15]) + w[(i + 9) & 15] + small_sigma0(w[(i + 1) & 15]) + w[i];
+                    }
+                }
+            }
+            __threadfence_block();
+            __syncwarp();
+            done = upto;
+            if (lane == 0) st_volatile_shared(produced, done);
+        }
+    }
+}
+
+}  // namespace snapgpu

@@ -23,6 +23,7 @@
 #include "runtime.hpp"
 #include "sha512_kernels.cuh"
 #include "sha512_long.cuh"
+#include "sha512_pair.cuh"
 
 namespace snapgpu {
 
@@ -132,7 +133,7 @@ struct Options {
     std::atomic<long long> sha_variant{0};
     std::atomic<long long> cmp_ctas_per_sm{0};
     std::atomic<long long> time_kernels{1};
-    std::atomic<long long> long_kernel{1};
+    std::atomic<long long> long_kernel{2};      // 0 off, 1 one lane per file, 2 a lane pair per file
 };
 
 struct Runtime {
@@ -206,6 +207,8 @@ static int init_device(Device &D, int ordinal) {
     SG_CUDA(cudaStreamCreateWithFlags(&D.long_stream, cudaStreamNonBlocking));
     SG_CUDA(cudaFuncSetAttribute(sha512_long_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytes));
     SG_CUDA(cudaFuncSetAttribute(sha512_long_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytes));
+    SG_CUDA(cudaFuncSetAttribute(sha512_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes));
+    SG_CUDA(cudaFuncSetAttribute(sha512_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes));
     for (auto &s : D.slots) {
         SG_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         SG_CUDA(cudaEventCreate(&s.uploaded));
@@ -538,13 +541,23 @@ static int launch_sha512(Device &D, cudaStream_t stream, const uint8_t *d_data, 
         // everything `stream` has been asked to do so far (the data, a chaining value) comes first
         SG_CUDA(cudaEventRecord(slot->fork, stream));
         SG_CUDA(cudaStreamWaitEvent(D.long_stream, slot->fork, 0));
-        const u32 long_grid = (u32)((n_long + kLongFilesPerCta - 1) / kLongFilesPerCta);
-        if (aligned)
-            sha512_long_kernel<true><<<long_grid, kLongThreads, kLongSmemBytes, D.long_stream>>>(d_data, plan.long_descs,
-                                                                                                 (u32)n_long, d_digests);
-        else
-            sha512_long_kernel<false><<<long_grid, kLongThreads, kLongSmemBytes, D.long_stream>>>(d_data, plan.long_descs,
-                                                                                                  (u32)n_long, d_digests);
+        if (R.opt.long_kernel.load() >= 2) {                // one chain per lane pair (sha512_pair.cuh)
+            const u32 long_grid = (u32)((n_long + kPairFilesPerCta - 1) / kPairFilesPerCta);
+            if (aligned)
+                sha512_pair_kernel<true><<<long_grid, kLongThreads, kPairSmemBytes, D.long_stream>>>(
+                    d_data, plan.long_descs, (u32)n_long, d_digests);
+            else
+                sha512_pair_kernel<false><<<long_grid, kLongThreads, kPairSmemBytes, D.long_stream>>>(
+                    d_data, plan.long_descs, (u32)n_long, d_digests);
+        } else {                                            // one chain per lane (sha512_long.cuh)
+            const u32 long_grid = (u32)((n_long + kLongFilesPerCta - 1) / kLongFilesPerCta);
+            if (aligned)
+                sha512_long_kernel<true><<<long_grid, kLongThreads, kLongSmemBytes, D.long_stream>>>(
+                    d_data, plan.long_descs, (u32)n_long, d_digests);
+            else
+                sha512_long_kernel<false><<<long_grid, kLongThreads, kLongSmemBytes, D.long_stream>>>(
+                    d_data, plan.long_descs, (u32)n_long, d_digests);
+        }
         SG_CUDA(cudaGetLastError());
         SG_CUDA(cudaEventRecord(slot->join, D.long_stream));
         R.kernel_launches++;
@@ -1174,7 +1187,8 @@ int snapgpu_set_option(const char *key, long long value) {
     } else if (k == "time_kernels") {
         o.time_kernels = value ? 1 : 0;
     } else if (k == "long_kernel") {
-        o.long_kernel = value ? 1 : 0;
+        if (value < 0 || value > 2) return fail(SNAPGPU_EINVAL, "long_kernel: 0 off, 1 one lane per file, 2 lane pair per file");
+        o.long_kernel = value;
     } else {
         return fail(SNAPGPU_EINVAL, "unknown option %s", key);
     }

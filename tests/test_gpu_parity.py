@@ -18,7 +18,7 @@ def default_options(gpu):
     gpu.set_option("staging_bytes", 256 << 20)
     gpu.set_option("sha_variant", 0)
     gpu.set_option("sha_warps_per_sm", 0)
-    gpu.set_option("long_kernel", 1)
+    gpu.set_option("long_kernel", 2)
     yield
 
 
@@ -223,10 +223,13 @@ def test_long_file_chain(gpu):
     assert dg[1].tobytes() == hashlib.sha512(synth.file_bytes(1, 100)).digest()
 
 
-def test_long_file_kernel(gpu, oracle):
-    """The long-file bin (sha512_long.cuh): files of >= 2 MiB leave the batched kernel when a launch
-    has at most 256 of them.  Same digests with the bin switched off, and both equal the oracle."""
+@pytest.mark.parametrize("mode", [1, 2])
+def test_long_file_kernel(gpu, oracle, mode):
+    """The long-file bin: files whose chain would dominate a launch leave the batched kernel when a
+    launch has at most 256 of them -- mode 1 one lane per file (sha512_long.cuh), mode 2 a lane pair
+    per file (sha512_pair.cuh).  Same digests with the bin switched off, and both equal the oracle."""
     from snappy_b200 import helpers
+    gpu.set_option("long_kernel", mode)
     rng = np.random.default_rng(21)
     MiB = 1 << 20
     cases = [
@@ -235,17 +238,20 @@ def test_long_file_kernel(gpu, oracle):
         list(rng.integers(0, 9000, 300)) + [4 * MiB + 1, 2 * MiB + 128, 0, 7 * MiB],
         [2 * MiB + 64 * i + (i % 3) for i in range(33)],                 # 33 long files: two CTAs, 32 + 1
         [2 * MiB + 1024 * i for i in range(5)] + list(rng.integers(1, 70000, 64)),   # 5 files: 32 % 5 idle lanes
+        [2 * MiB + 128 * i + (i % 5) for i in range(17)],                # 17 long files: 16 + 1 lane pairs
+        [2 * MiB + 777 * i for i in range(16)] + [1, 2, 3],              # exactly 16
+        [MiB + 4096 * i for i in range(11)],                             # 11 files: ring of 23 steps, 2 per round
     ]
     for lengths in cases:
         data, off, ln = pack(lengths, rng)
         want = oracle.sha512_batch(data, off, ln, 8)
         gpu.reset_stats()
-        gpu.set_option("long_kernel", 1)
+        gpu.set_option("long_kernel", mode)
         got = helpers.sha512_batch(data, off, ln)
         launches_with = gpu.stats().kernel_launches
         gpu.set_option("long_kernel", 0)
         plain = helpers.sha512_batch(data, off, ln)
-        gpu.set_option("long_kernel", 1)
+        gpu.set_option("long_kernel", mode)
         assert np.array_equal(got, want), lengths[-4:]
         assert np.array_equal(plain, want)
         assert launches_with >= 1
@@ -642,7 +648,7 @@ def test_config3_shape_at_reduced_size(gpu):
     _spot_check(dg, lengths, [50_000, 50_001, 50_002, 50_003, 0, 49_999, 123, 31_337])
     gpu.set_option("long_kernel", 0)
     small = device.sha512_batch_device(d, off[:50_000], lengths[:50_000]).cpu().numpy()
-    gpu.set_option("long_kernel", 1)
+    gpu.set_option("long_kernel", 2)
     assert np.array_equal(small, dg[:50_000])
 
 
