@@ -150,16 +150,17 @@ sha512_pair_kernel(const uint8_t *__restrict__ data, const SegDesc *__restrict__
             volatile u64 *const kin = role ? Tm : ring + ((size_t)slot_index * nf + min(file, nf - 1)) * kLongSlotWords;
             slot_index = slot_index + 1 == ring_steps ? 0 : slot_index + 1;
 
-            // prologue.  role 1 publishes d, c and the two seeds that make its idle iterations
-            // 0 and 1 produce b and a; its window starts as (c, d, 0).
-            u64 S0 = role ? st[2] : st[0], S1 = role ? st[3] : st[1], S2 = role ? 0 : st[2], S3 = role ? 0 : st[3];
+            // prologue.  role 1 publishes d and c, and the seed that makes its second idle iteration
+            // produce a (the first one's, which produces b, it keeps in a register); its window
+            // starts as (c, d, 0).  Ordered so that every load sits well behind the store it needs.
+            const u64 kw0 = kin[0];
             seed_a[0] = st[3];
             seed_a[1] = st[2];
-            seed_t[0] = st[1] - pair_sigma(st[2], rp, rq, rs) - pair_f(st[2], st[3], 0, mask);
-            seed_t[1] = st[0] - pair_sigma(st[1], rp, rq, rs) - pair_f(st[1], st[2], st[3], mask);
-            __syncwarp();
+            const u64 seed0 = st[1] - pair_sigma(st[2], rp, rq, rs) - pair_f(st[2], st[3], 0, mask);
             u64 D = din[0];
-            u64 PD = pair_muladd(S3, mul, kin[0]) + D;     // h + (W+K) + d  |  T1
+            seed_t[1] = st[0] - pair_sigma(st[1], rp, rq, rs) - pair_f(st[1], st[2], st[3], mask);
+            u64 S0 = role ? st[2] : st[0], S1 = role ? st[3] : st[1], S2 = role ? 0 : st[2], S3 = role ? 0 : st[3];
+            u64 PD = role ? seed0 : st[3] + kw0 + D;       // T1 that yields b  |  h + (W+K) + d
 
 #define SNAPGPU_PAIR_ITER(KIN, DIN, OUT, I)                                                   \
     {                                                                                            \
