@@ -121,12 +121,11 @@ inline size_t align_up(size_t x) { return (x + kAlign - 1) & ~(kAlign - 1); }
 // One file streamed through `buf` in pieces that are multiples of 128 bytes: the io.Copy loop
 // of helpers.Sha512sum (helpers/helpers.go:195-196) with the chaining value carried between
 // GPU calls.  Used for files larger than a batch and for files that grew while being packed.
-int stream_file(const std::string &path, uint8_t *buf, size_t cap, uint8_t digest[64]) {
-    int fd = ::open(path.c_str(), O_RDONLY | O_CLOEXEC);
-    if (fd < 0) return fail(SNAPGPU_EIO, "%s", go_path_error("open", path, errno).c_str());
-    uint64_t prefix = 0;
+// `prefix` bytes of the message have been hashed already (their chaining value is in `digest`)
+// when prefix > 0; the descriptor is read from its current position to EOF and closed.
+int stream_fd(int fd, const std::string &path, uint8_t *buf, size_t cap, uint8_t digest[64], uint64_t prefix = 0) {
     size_t len = 0;
-    bool first = true;
+    bool first = prefix == 0;
     int rc = 0;
     for (;;) {
         ssize_t r = read_full(fd, buf + len, cap - len);
@@ -148,6 +147,12 @@ int stream_file(const std::string &path, uint8_t *buf, size_t cap, uint8_t diges
     }
     ::close(fd);
     return rc;
+}
+
+int stream_file(const std::string &path, uint8_t *buf, size_t cap, uint8_t digest[64]) {
+    int fd = ::open(path.c_str(), O_RDONLY | O_CLOEXEC);
+    if (fd < 0) return fail(SNAPGPU_EIO, "%s", go_path_error("open", path, errno).c_str());
+    return stream_fd(fd, path, buf, cap, digest);
 }
 
 // What the packer did with one file of a batch.
@@ -216,14 +221,42 @@ unsigned packer_threads(size_t nfiles) {
 // the file did not go through a batch (larger than a batch, or it grew): the sink copies it itself.
 typedef std::function<int(size_t index, const uint8_t *bytes, uint64_t len)> FileSink;
 
+// One more, long file hashed ALONGSIDE a list (writeHashes' data.tar.gz): a single SHA-512
+// chain runs at ~70 MB/s on the GPU however idle the rest of it is, so instead of sitting in
+// one batch and stretching that batch's GPU call, the file rides along in slices -- every
+// batch's launch carries the next slice as a continuation segment (the long-file kernel hashes
+// it beside the batched kernel), sized to what the packer needs for the next batch anyway.
+// What is left after the last batch is streamed at the end.
+struct Rider {
+    std::string path;
+    uint8_t digest[64] = {0};
+};
+
 int hash_files(const std::vector<std::string> &paths, std::vector<uint8_t> &digests,
-               const std::vector<int64_t> *size_hint = nullptr, const FileSink *sink = nullptr) {
+               const std::vector<int64_t> *size_hint = nullptr, const FileSink *sink = nullptr,
+               Rider *rider = nullptr) {
     digests.assign(paths.size() * 64, 0);
-    if (paths.empty()) return 0;
+    if (paths.empty() && !rider) return 0;
     int rc = ensure_init();
     if (rc) return rc;
     Staging &S = staging();
     std::lock_guard<std::mutex> lock(S.mu);
+    // the rider is opened first: like build.go:222-226 a missing archive is the first error
+    int rider_fd = -1;
+    if (rider) {
+        rider_fd = ::open(rider->path.c_str(), O_RDONLY | O_CLOEXEC);
+        if (rider_fd < 0) return fail(SNAPGPU_EIO, "%s", go_path_error("open", rider->path, errno).c_str());
+    }
+    struct FdGuard {
+        int &fd;
+        ~FdGuard() { if (fd >= 0) ::close(fd); }
+    } rider_guard{rider_fd};
+    if (paths.empty()) {
+        if ((rc = ring_acquire(S, (size_t)16 << 20))) return rc;
+        const int fd = rider_fd;
+        rider_fd = -1;                                       // stream_fd closes it
+        return stream_fd(fd, rider->path, S.ring[0], S.ring_cap, rider->digest);
+    }
     const size_t n = paths.size();
     const unsigned nthreads = packer_threads(n);
 
@@ -270,7 +303,14 @@ int hash_files(const std::vector<std::string> &paths, std::vector<uint8_t> &dige
     // a batch of its own and is streamed
     struct Batch { size_t first, count; bool streamed; };
     std::vector<Batch> batches;
-    const size_t room = cap - 256;
+    // the rider's slice sits at the start of each buffer, so that it is part of the first chunk the
+    // GPU call uploads and its chain starts at once: 1/384 of the buffer (~0.7 MiB of a 256 MiB
+    // batch is ~10 ms of chain, what packing the next batch takes anyway), a multiple of 128 bytes
+    const size_t slice = rider ? std::min<size_t>(std::max<size_t>(cap / 384, (size_t)128 << 10), (size_t)1 << 20) & ~(size_t)127 : 0;
+    const size_t rider_off = 0;
+    const size_t room = cap - 256 - slice;
+    struct RiderPiece { size_t len = 0; bool eof = false; int err = 0; } piece[2];
+    bool rider_eof_read = false;                             // touched by the (sequential) fills only
     for (size_t i = 0; i < n;) {
         if (planned[i] + 1 > room) {
             batches.push_back(Batch{i, 1, true});
@@ -291,8 +331,9 @@ int hash_files(const std::vector<std::string> &paths, std::vector<uint8_t> &dige
         const Batch &B = batches[bi];
         std::vector<PackedFile> &pf = packed[bi & 1];
         pf.clear();
+        piece[bi & 1] = RiderPiece();
         if (B.streamed) return;
-        size_t used = 0;
+        size_t used = slice;                                 // files follow the rider's slice
         for (size_t k = 0; k < B.count; k++) {
             used = align_up(used);
             PackedFile f;
@@ -303,12 +344,28 @@ int hash_files(const std::vector<std::string> &paths, std::vector<uint8_t> &dige
             used += f.planned + 1;
         }
         uint8_t *buf = S.ring[bi & 1];
+        std::thread rider_reader;
+        if (rider && !rider_eof_read)                        // the next slice, read beside the packers
+            rider_reader = std::thread([&, buf, bi]() {
+                RiderPiece &rp = piece[bi & 1];
+                const ssize_t r = read_full(rider_fd, buf + rider_off, slice);
+                if (r < 0) {
+                    rp.err = errno;
+                    rider_eof_read = true;
+                    return;
+                }
+                rp.len = (size_t)r;
+                rp.eof = rider_eof_read = (size_t)r < slice;
+            });
         parallel_for(pf.size(), [&](size_t k) { pack_one(paths[pf[k].index], buf, pf[k]); });
+        if (rider_reader.joinable()) rider_reader.join();
     };
 
     std::vector<HostSeg> segs;
     std::vector<uint8_t> out;
     std::thread prefetch;
+    uint64_t rider_prefix = 0;
+    bool rider_done = false;
     fill(0);
     for (size_t bi = 0; bi < batches.size() && !rc; bi++) {
         const double tb0 = wall_ms();
@@ -329,9 +386,21 @@ int hash_files(const std::vector<std::string> &paths, std::vector<uint8_t> &dige
                 break;
             }
         if (rc) break;
+        const RiderPiece rp = piece[bi & 1];
+        if (rp.err) {
+            rc = fail(SNAPGPU_EIO, "%s", go_path_error("read", rider->path, rp.err).c_str());
+            break;
+        }
+        // segment 0 is the rider's slice (when there is one), the files follow
+        const bool ride = rider && !rider_done && (rp.len > 0 || rp.eof);
+        const size_t base = ride ? 1 : 0;
         segs.clear();
+        if (ride)
+            segs.push_back(HostSeg{rider_off, rp.len, rider_prefix,
+                                   (rider_prefix ? kHostSegContinue : 0u) | (rp.eof ? 0u : kHostSegNoFinal)});
         for (const PackedFile &f : pf) segs.push_back(HostSeg{f.off, f.grew ? 0 : f.len, 0, 0});
         out.resize(segs.size() * 64);
+        if (ride) memcpy(&out[0], rider->digest, 64);                    // the chaining value so far
         // the sink reads the same pinned bytes the GPU copy engine reads: it runs beside the GPU call
         std::vector<int> sink_rc;
         std::vector<std::string> sink_err;
@@ -370,11 +439,21 @@ int hash_files(const std::vector<std::string> &paths, std::vector<uint8_t> &dige
         if (getenv("SNAPGPU_TRACE"))
             fprintf(stderr, "[snapgpu] batch %zu: %zu files, waited %.2f ms for the packer, GPU call %.2f ms\n", bi, pf.size(),
                     tb1 - tb0, wall_ms() - tb1);
-        for (size_t k = 0; k < pf.size(); k++) memcpy(&digests[64 * pf[k].index], &out[64 * k], 64);
+        for (size_t k = 0; k < pf.size(); k++) memcpy(&digests[64 * pf[k].index], &out[64 * (k + base)], 64);
+        if (ride) {
+            memcpy(rider->digest, &out[0], 64);
+            rider_prefix += rp.len;
+            rider_done = rp.eof;
+        }
         for (const PackedFile &f : pf)                        // rare: the file grew after its stat
             if (f.grew && (rc = stream_file(paths[f.index], buf, cap, &digests[64 * f.index]))) break;
     }
     if (prefetch.joinable()) prefetch.join();
+    if (!rc && rider && !rider_done) {                        // what the batches did not carry
+        const int fd = rider_fd;
+        rider_fd = -1;                                        // stream_fd closes it
+        rc = stream_fd(fd, rider->path, S.ring[0], cap, rider->digest, rider_prefix);
+    }
     return rc;
 }
 
@@ -1314,11 +1393,6 @@ int build_hashes_yaml(const std::string &build_dir, const std::string *data_tar_
     std::vector<std::string> paths;
     std::vector<int64_t> sizes;
     std::vector<size_t> slot_of;                         // digest slot of paths[k]
-    if (data_tar_opt) {
-        paths.push_back(data_tar);                       // archive-sha512 first (build.go:222)
-        sizes.push_back(-1);
-        slot_of.push_back(0);
-    }
     size_t slot = 1;
     for (const TreeEntry &e : entries)
         if (e.regular) {
@@ -1330,14 +1404,18 @@ int build_hashes_yaml(const std::string &build_dir, const std::string *data_tar_
             slot++;
         }
     std::vector<uint8_t> fresh;
+    // archive-sha512 (build.go:222): one long chain, hashed in slices beside the tree's batches
+    Rider archive;
+    archive.path = data_tar;
     const double t1 = wall_ms();
-    if ((rc = hash_files(paths, fresh, &sizes))) return rc;
+    if ((rc = hash_files(paths, fresh, &sizes, nullptr, data_tar_opt ? &archive : nullptr))) return rc;
+    if (data_tar_opt) memcpy(&digests[0], archive.digest, 64);
     for (size_t k = 0; k < paths.size(); k++) memcpy(&digests[64 * slot_of[k]], &fresh[64 * k], 64);
     const double t2 = wall_ms();
     rc = emit_hashes_yaml(entries, digests.data(), nreg + 1, yaml);
     if (getenv("SNAPGPU_TRACE"))
         fprintf(stderr, "[snapgpu] writeHashes: walk %.2f ms (%zu entries), pack+hash %.2f ms (%zu files, %zu from the digest cache), yaml %.2f ms\n",
-                t1 - t0, entries.size(), t2 - t1, paths.size(), nreg + (data_tar_opt ? 1 : 0) - paths.size(), wall_ms() - t2);
+                t1 - t0, entries.size(), t2 - t1, paths.size() + (data_tar_opt ? 1 : 0), nreg - paths.size(), wall_ms() - t2);
     return rc;
 }
 

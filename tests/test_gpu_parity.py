@@ -343,6 +343,39 @@ def test_tree_larger_than_host_staging(gpu, oracle, tmp_path):
     assert got == oracle.write_hashes(str(tree), str(tar))
 
 
+def test_archive_rides_along_in_slices(gpu, tmp_path):
+    """writeHashes hashes data.tar.gz (archive-sha512, snappy/build.go:222) in slices carried by the
+    tree's batches, the rest streamed at the end: every archive size around the slice boundaries gives
+    hashlib's digest, for a tree of several batches, of one batch, and with no regular file at all."""
+    from snappy_b200 import build
+    rng = np.random.default_rng(33)
+    gpu.set_option("staging_bytes", 1 << 20)            # 1 MiB batches, 128 KiB slices
+    big = tmp_path / "big"
+    big.mkdir()
+    for i in range(60):
+        (big / f"f{i:03d}").write_bytes(rng.integers(0, 256, int(rng.integers(20_000, 90_000)), dtype=np.uint8).tobytes())
+    small = tmp_path / "small"
+    small.mkdir()
+    (small / "one").write_bytes(b"1")
+    empty = tmp_path / "empty"
+    (empty / "sub").mkdir(parents=True)
+    K = 128 << 10
+    sizes = [0, 1, 127, 128, K - 1, K, K + 1, 2 * K, 3 * K + 77, 5 * K, 9 * K + 128, (1 << 20) + 5, 3_000_001]
+    for tree in (big, small, empty):
+        for n in sizes:
+            tar = tmp_path / "data.tar.gz"
+            payload = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+            tar.write_bytes(payload)
+            doc = build.hashes_yaml(str(tree), str(tar))
+            first = doc.split(b"\n", 1)[0]
+            assert first == b"archive-sha512: " + hashlib.sha512(payload).hexdigest().encode(), (tree.name, n)
+            if tree is big:
+                assert doc.count(b"- name: ") == 60
+    # a missing archive is the first error, before anything is hashed (build.go:222-226)
+    with pytest.raises(OSError):
+        build.hashes_yaml(str(big), str(tmp_path / "nope.tar.gz"))
+
+
 # ---- cmp -----------------------------------------------------------------------------------------
 
 def test_cmp_reference_truth_tables(gpu, tmp_path):
