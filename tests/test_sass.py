@@ -94,3 +94,37 @@ def test_cmp_kernel_uses_128_bit_loads(sass):
 def test_probe_kernels_issue_what_they_claim(sass, kind, opcode, least):
     c = find(sass, "pipe_probe_kernel", f"ILi{kind}E")
     assert count(c, opcode) >= least, c.most_common(6)
+
+
+def test_pair_kernel_round_loop(native):
+    """sha512_pair_kernel: the 16-round loop of the consumer has ~17 ALU instructions per round (28 in the
+    one-lane consumer), talks through shared memory only (two LDS.64 + one STS.64 per round, no shuffle,
+    no divergence check) and does not spill."""
+    text = subprocess.run(["cuobjdump", "-sass", str(native.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    body = [p for p in text.split("Function : ") if p.startswith("_ZN7snapgpu18sha512_pair_kernelILb1E")]
+    assert len(body) == 1
+    insts = []
+    for line in body[0].splitlines():
+        m = re.match(r"\s+/\*([0-9a-f]{4,6})\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)(.*?);", line)
+        if m:
+            insts.append((int(m.group(1), 16), m.group(2), m.group(3)))
+    assert not any(op.startswith(("LDL", "STL")) for _, op, _ in insts)
+    # loops = backward branches; the round loop is the one whose body holds 16 STS.64 and 32 LDS.64
+    loops = []
+    for addr, op, rest in insts:
+        if op.startswith("BRA"):
+            m = re.search(r"0x([0-9a-f]+)", rest)
+            if m and int(m.group(1), 16) < addr:
+                loops.append((int(m.group(1), 16), addr))
+    alu = re.compile(r"^(IADD3|LOP3|SHF|PRMT|SEL|ISETP|VIADD|LEA|MOV|IMNMX|VIMNMX)")
+    found = False
+    for lo, hi in loops:
+        ops = [op for a, op, _ in insts if lo <= a <= hi]
+        if (sum(op.startswith("STS.64") for op in ops) == 16 and sum(op.startswith("LDS.64") for op in ops) == 32
+                and len(ops) < 500):
+            found = True
+            assert sum(op.startswith("SHF.R.W") for op in ops) == 16 * 6
+            assert not any(op.startswith(("SHFL", "BRA.DIV", "WARPSYNC", "BAR")) for op in ops)
+            n_alu = sum(bool(alu.match(op)) for op in ops)
+            assert n_alu <= 16 * 17.5, n_alu
+    assert found

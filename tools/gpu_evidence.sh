@@ -28,6 +28,11 @@ ncu --set full --clock-control none --import-source on -k regex:cmp_pairs -s 4 -
     python bench.py --steps 3 --no-cpu --no-e2e --no-tail > ${o}_ncu_bench_cmp.log 2>&1; echo "ncu bench cmp exit $?"
 SNAPGPU_TRACE=1 python tools/tree_bench.py ${o}_tree.jsonl > ${o}_tree.log 2> ${o}_tree_trace.log; echo "tree exit $?"; cat ${o}_tree.log
 grep "writeHashes:" ${o}_tree_trace.log | tail -3; grep "batch " ${o}_tree_trace.log | tail -6
+python tools/long_probe.py 16 > ${o}_long_probe.jsonl 2> ${o}_long_probe.err; echo "long probe exit $?"; grep '"files": 1,' ${o}_long_probe.jsonl
+python tools/stress.py 60 2 > ${o}_stress.json 2> ${o}_stress.err; echo "stress exit $?"; tail -1 ${o}_stress.json
+python tools/ncu_long_target.py 4 > ${o}_pair_plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:sha512_pair -c 1 -o ${o}_pair -f \
+    python tools/ncu_long_target.py 4 > ${o}_ncu_pair.log 2>&1; echo "ncu pair exit $?"
 if [ -z "$skip" ]; then
   timeout 900 python tools/cfg3_tail.py ${o}_cfg3.json 1024 > ${o}_cfg3.log 2>&1; echo "cfg3 exit $?"; tail -1 ${o}_cfg3.log
 fi

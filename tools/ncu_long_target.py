@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""ncu target: one 2 MiB+ file alone -> sha512_long_kernel (argv[1] = MiB, default 4)."""
+"""ncu target: one 2 MiB+ file alone -> the long-file bin (sha512_pair_kernel by default; argv[1] = MiB, default 4)."""
 import sys
 from pathlib import Path
 
