@@ -440,19 +440,29 @@ def main():
         dt_ = torch.empty(ttotal, dtype=torch.uint8, device=dev)
         device.synth_fill_device(dt_, to, tl)
         dgt = torch.empty((1, 64), dtype=torch.uint8, device=dev)
-        device.sha512_batch_device(dt_, to, tl, dgt)
-        torch.cuda.synchronize()
-        N.reset_stats()
-        device.sha512_batch_device(dt_, to, tl, dgt)
-        torch.cuda.synchronize()
-        tms = N.stats().sha512_kernel_ms_sum
-        launches += 2
+        # through the default long-file bin (2: a lane pair per chain), its one-lane form (1) and,
+        # with the bin off (0), the batched kernel -- the two comparison points
+        by_mode = {}
+        for mode in (2, 1, 0):
+            N.set_option("long_kernel", mode)
+            device.sha512_batch_device(dt_, to, tl, dgt)
+            torch.cuda.synchronize()
+            N.reset_stats()
+            device.sha512_batch_device(dt_, to, tl, dgt)
+            torch.cuda.synchronize()
+            by_mode[mode] = N.stats().sha512_kernel_ms_sum
+            launches += 2
+        N.set_option("long_kernel", 2)
+        tms = by_mode[2]
         tblocks = int(synth.blocks(tl)[0])
         tail = {"what": "one 16 MiB file alone on the GPU: a single SHA-512 chain cannot be split, so this is the "
                         "latency floor of the longest file of a batch",
+                "kernel": "sha512_pair_kernel (one chain on a lane pair)",
                 "file_bytes": int(tl[0]), "blocks": tblocks, "kernel_ms": tms, "us_per_block": tms * 1e3 / tblocks,
                 "mb_per_s_per_stream": int(tl[0]) / (tms * 1e-3) / 1e6,
                 "extrapolated_s_per_GiB": tms * 1e-3 * (1 << 30) / int(tl[0]),
+                "one_lane_kernel_us_per_block": by_mode[1] * 1e3 / tblocks,
+                "batched_kernel_us_per_block": by_mode[0] * 1e3 / tblocks,
                 "sha512_hex_prefix": dgt.cpu().numpy().tobytes().hex()[:16]}
         del dt_
 
