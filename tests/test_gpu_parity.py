@@ -50,6 +50,21 @@ def test_reference_kats_through_files(gpu, golden_dir, tmp_path):
     assert "no such file or directory" in str(e.value).lower()
 
 
+def test_reference_kats_through_the_hasher(gpu, golden_dir):
+    """The other crypto/sha512 call shape in the reference: sha512.New(); Write; hex(Sum(nil))
+    (SystemImagePart.Hash, snappy/systemimage.go:122-128; its KAT is snappy/systemimage_test.go:104,117)."""
+    from snappy_b200 import helpers
+    for k in json.loads((golden_dir / "sha512_kats.json").read_text()):
+        h = helpers.Sha512Stream()
+        h.Write(k["message"].encode())
+        assert h.Sum().hex() == k["sha512"], k["source"]
+        msg = k["message"].encode()                      # the same in two writes
+        h2 = helpers.Sha512Stream()
+        h2.Write(msg[: len(msg) // 2])
+        h2.Write(msg[len(msg) // 2:])
+        assert h2.Sum().hex() == k["sha512"]
+
+
 def test_every_length_0_to_300(gpu, oracle):
     from snappy_b200 import helpers
     rng = np.random.default_rng(11)
