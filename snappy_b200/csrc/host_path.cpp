@@ -1382,9 +1382,17 @@ int build_hashes_yaml(const std::string &build_dir, const std::string *data_tar_
                       bool make_debian) {
     std::vector<TreeEntry> entries;
     const double t0 = wall_ms();
+    const std::string data_tar = data_tar_opt ? *data_tar_opt : std::string();
+    if (data_tar_opt) {
+        // build.go:218-226: DEBIAN/ is made, then the archive is hashed, and only then the tree is
+        // walked -- an archive that cannot be opened is reported before any error of the walk
+        if (make_debian) mkdir_all(build_dir + "/DEBIAN", 0755);
+        const int fd = ::open(data_tar.c_str(), O_RDONLY | O_CLOEXEC);
+        if (fd < 0) return fail(SNAPGPU_EIO, "%s", go_path_error("open", data_tar, errno).c_str());
+        ::close(fd);
+    }
     int rc = collect_tree(build_dir, entries, make_debian);
     if (rc) return rc;
-    const std::string data_tar = data_tar_opt ? *data_tar_opt : std::string();
     // digests: archive first, then one per regular entry in walk order; entries this library
     // copied into place itself (copyToBuildDir) come from the digest cache, the rest are hashed
     size_t nreg = 0;

@@ -295,3 +295,19 @@ def test_copy_to_build_dir_wide_tree_parallel_walk(native, oracle, tmp_path):
             assert "d017/deep" in str(e1.value) and "d017/deep" in str(e2.value)
         finally:
             os.chmod(src / "d017" / "deep", 0o755)
+
+
+def test_missing_archive_is_reported_before_anything_else(native, oracle, tmp_path):
+    """writeHashes makes DEBIAN/, hashes the archive, then walks (snappy/build.go:218-228): with no
+    archive the open error comes first -- before a walk error, before the GPU is touched -- and
+    DEBIAN/ exists afterwards in both implementations."""
+    from snappy_b200 import build
+    for impl in (lambda t, a: build.writeHashes(t, a), lambda t, a: oracle.write_hashes(t, a)):
+        tree = tmp_path / f"t{id(impl)}"
+        tree.mkdir()
+        os.mkfifo(tree / "pipe", 0o644)                    # would be "Unknown file mode" during the walk
+        with pytest.raises(OSError) as e:
+            impl(str(tree), str(tmp_path / "no-such.tar.gz"))
+        assert "no-such.tar.gz" in str(e.value)
+        assert (tree / "DEBIAN").is_dir()
+        assert not (tree / "DEBIAN" / "hashes.yaml").exists()
