@@ -45,7 +45,8 @@ const char *snapgpu_version(void);
 
 /* Tunables (all optional).  Known keys: "staging_bytes" (per-device H2D chunk, default
  * 1 GiB, two buffers), "sha_warps_per_sm" (0 = auto), "sha_variant" (0 = default kernel),
- * "cmp_ctas_per_sm", "time_kernels", "long_kernel" (the long-file bin: 0 off, 1 one lane per
+ * "cmp_ctas_per_sm", "time_kernels", "feeders" (host threads per device that bounce pageable
+ * input into pinned memory, 0 = auto), "long_kernel" (the long-file bin: 0 off, 1 one lane per
  * file, 2 a lane pair per file = default). */
 int snapgpu_set_option(const char *key, long long value);
 

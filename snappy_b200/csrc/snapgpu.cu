@@ -75,7 +75,7 @@ std::string hex_lower(const uint8_t *p, size_t n) {
 // ------------------------------------------------------------------------------------------
 
 constexpr int kPlanSlots = 4;
-constexpr int kFeeders = 4;                     // host threads that move pageable memory into pinned bounce buffers
+constexpr int kFeeders = 8;                     // at most this many host threads move pageable memory into pinned bounce buffers
 constexpr size_t kBounceBytes = 4u << 20;
 constexpr size_t kMaxChunkItems = 1u << 20;
 constexpr uint64_t kMaxSegBytes = 1ULL << 39;   // block counts stay below 2^32
@@ -133,6 +133,7 @@ struct Options {
     std::atomic<long long> sha_variant{0};
     std::atomic<long long> cmp_ctas_per_sm{0};
     std::atomic<long long> time_kernels{1};
+    std::atomic<long long> feeders{0};          // bounce-buffer threads per device for pageable input, 0 = auto
     std::atomic<long long> long_kernel{2};      // 0 off, 1 one lane per file, 2 a lane pair per file
 };
 
@@ -722,12 +723,20 @@ static int h2d_span(Device &D, uint8_t *dst, const uint8_t *src, size_t bytes, b
     SG_CUDA(cudaEventRecord(D.feeder_fork, D.copy_stream));
     for (int f = 0; f < kFeeders; f++) SG_CUDA(cudaStreamWaitEvent(D.feeder_stream[f], D.feeder_fork, 0));
     const size_t pieces = (bytes + kBounceBytes - 1) / kBounceBytes;
+    // threads: one memcpy runs at ~10 GB/s, the link takes ~55; half the cores, shared between the
+    // bound devices (each has its own set of feeders when a call is sharded over several)
+    int nfeed = (int)rt().opt.feeders.load();
+    if (nfeed <= 0) {
+        const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
+        nfeed = (int)(hw / 2 / std::max<size_t>(1, rt().devs.size()));
+    }
+    nfeed = std::max(1, std::min<int>({nfeed, kFeeders, (int)pieces}));
     int rcs[kFeeders] = {};
     std::string errs[kFeeders];
     auto feed = [&](int f) {
         if (cudaSetDevice(D.ordinal) != cudaSuccess) { rcs[f] = SNAPGPU_ECUDA; errs[f] = "cudaSetDevice failed"; return; }
         int use = 0;
-        for (size_t p = (size_t)f; p < pieces; p += kFeeders, use ^= 1) {
+        for (size_t p = (size_t)f; p < pieces; p += (size_t)nfeed, use ^= 1) {
             const size_t off = p * kBounceBytes, len = std::min(kBounceBytes, bytes - off);
             cudaError_t e = cudaEventSynchronize(D.bounce_free[f][use]);       // its previous DMA has drained
             if (e == cudaSuccess) {
@@ -743,7 +752,7 @@ static int h2d_span(Device &D, uint8_t *dst, const uint8_t *src, size_t bytes, b
         }
     };
     std::vector<std::thread> th;
-    for (int f = 1; f < kFeeders; f++) th.emplace_back(feed, f);
+    for (int f = 1; f < nfeed; f++) th.emplace_back(feed, f);
     feed(0);
     for (auto &t : th) t.join();
     for (int f = 0; f < kFeeders; f++)
@@ -1186,6 +1195,9 @@ int snapgpu_set_option(const char *key, long long value) {
         o.cmp_ctas_per_sm = value;
     } else if (k == "time_kernels") {
         o.time_kernels = value ? 1 : 0;
+    } else if (k == "feeders") {
+        if (value < 0 || value > kFeeders) return fail(SNAPGPU_EINVAL, "feeders out of range");
+        o.feeders = value;
     } else if (k == "long_kernel") {
         if (value < 0 || value > 2) return fail(SNAPGPU_EINVAL, "long_kernel: 0 off, 1 one lane per file, 2 lane pair per file");
         o.long_kernel = value;
