@@ -274,9 +274,18 @@ def test_long_file_kernel(gpu, oracle, mode):
     data, off, ln = pack([3 * MiB + 5, 100, 2 * MiB + 1, 17], rng, align=1, jitter=True)
     assert (off % 16 != 0).any()
     assert np.array_equal(helpers.sha512_batch(data, off, ln), oracle.sha512_batch(data, off, ln, 4))
-    # more long files than the bin takes: all stay in the batched kernel
+    # 260 long files: more than the one-lane form takes (all stay in the batched kernel), 17 CTAs of the pair form
     lengths = [2 * MiB] * 260
     data, off, ln = pack(lengths, rng)
+    assert np.array_equal(helpers.sha512_batch(data, off, ln), oracle.sha512_batch(data, off, ln, 16))
+    # more long files than one CTA per SM of the pair form takes (148 x 16): the batched kernel keeps them all
+    lengths = [130 * 1024 + 128 * (i % 9) for i in range(2400)]
+    data, off, ln = pack(lengths, rng)
+    gpu.reset_stats()
+    got = helpers.sha512_batch(data, off, ln)
+    assert np.array_equal(got, oracle.sha512_batch(data, off, ln, 16))
+    # ... and just below that limit they all go to the bin (mode 2)
+    data, off, ln = pack(lengths[:2300], rng)
     assert np.array_equal(helpers.sha512_batch(data, off, ln), oracle.sha512_batch(data, off, ln, 16))
     # a long message streamed in pieces (continuation segments go through the long kernel too)
     msg = rng.integers(0, 256, 9 * MiB + 77, dtype=np.uint8).tobytes()

@@ -16,7 +16,7 @@ from snappy_b200 import device, synth         # noqa: E402
 
 mib = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 N.init([0])
-for nfiles in (1, 4, 16, 17, 64):
+for nfiles in (1, 4, 16, 17, 64, 500):
     lengths = np.array([(mib << 20) + 128 * i + (i % 7) for i in range(nfiles)], dtype=np.uint64)
     off, total = synth.layout(lengths)
     d = torch.empty(total, dtype=torch.uint8, device="cuda:0")
