@@ -327,8 +327,8 @@ constexpr int kShaVariants = 6;
 // variant 5: compact loop, every add as IMAD.WIDE + IMAD on the FMA pipe.  ALU instructions per
 //            block drop from 3425 to ~2700, yet it measured 19-29 % slower (and every partial mix
 //            between 0 and 5 fell in between, profiles/r01_sweep_fma_add_variants.txt): IMAD.WIDE
-//            issues at a quarter of the ALU rate and stalls the issue port it shares.
-// Input that is not 16-byte aligned always takes the register-load kernel (any alignment).
+//            issues at half the ALU rate and holds up the ALU instructions issued next to it (a 1:1 mix
+//            of LOP3 and IMAD.WIDE runs at 0.75 + 0.75 per clock per SM, pipe_microbench.cuh).
 static ShaKernel sha_kernel_for(int variant, bool aligned) {
     if (!aligned) {
         // any byte alignment: the staged kernel reading from each file's own phase; variant 2
@@ -713,7 +713,16 @@ static int h2d_span(Device &D, uint8_t *dst, const uint8_t *src, size_t bytes, b
         SG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, D.copy_stream));
         return 0;
     }
-    for (int f = 0; f < kFeeders; f++) {
+    const size_t pieces = (bytes + kBounceBytes - 1) / kBounceBytes;
+    // threads: one memcpy runs at ~10 GB/s, the link takes ~55; half the cores, shared between the
+    // bound devices (each has its own set of feeders when a call is sharded over several)
+    int nfeed = (int)rt().opt.feeders.load();
+    if (nfeed <= 0) {
+        const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
+        nfeed = (int)(hw / 2 / std::max<size_t>(1, rt().devs.size()));
+    }
+    nfeed = std::max(1, std::min<int>({nfeed, kFeeders, (int)pieces}));
+    for (int f = 0; f < nfeed; f++) {
         if (D.feeder_stream[f]) continue;
         SG_CUDA(cudaStreamCreateWithFlags(&D.feeder_stream[f], cudaStreamNonBlocking));
         SG_CUDA(cudaEventCreateWithFlags(&D.feeder_done[f], cudaEventDisableTiming));
@@ -726,16 +735,7 @@ static int h2d_span(Device &D, uint8_t *dst, const uint8_t *src, size_t bytes, b
     // may still be reading the same staging buffer's neighbour; plan uploads): fork from it
     if (!D.feeder_fork) SG_CUDA(cudaEventCreateWithFlags(&D.feeder_fork, cudaEventDisableTiming));
     SG_CUDA(cudaEventRecord(D.feeder_fork, D.copy_stream));
-    for (int f = 0; f < kFeeders; f++) SG_CUDA(cudaStreamWaitEvent(D.feeder_stream[f], D.feeder_fork, 0));
-    const size_t pieces = (bytes + kBounceBytes - 1) / kBounceBytes;
-    // threads: one memcpy runs at ~10 GB/s, the link takes ~55; half the cores, shared between the
-    // bound devices (each has its own set of feeders when a call is sharded over several)
-    int nfeed = (int)rt().opt.feeders.load();
-    if (nfeed <= 0) {
-        const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
-        nfeed = (int)(hw / 2 / std::max<size_t>(1, rt().devs.size()));
-    }
-    nfeed = std::max(1, std::min<int>({nfeed, kFeeders, (int)pieces}));
+    for (int f = 0; f < nfeed; f++) SG_CUDA(cudaStreamWaitEvent(D.feeder_stream[f], D.feeder_fork, 0));
     int rcs[kFeeders] = {};
     std::string errs[kFeeders];
     auto feed = [&](int f) {
@@ -760,9 +760,9 @@ static int h2d_span(Device &D, uint8_t *dst, const uint8_t *src, size_t bytes, b
     for (int f = 1; f < nfeed; f++) th.emplace_back(feed, f);
     feed(0);
     for (auto &t : th) t.join();
-    for (int f = 0; f < kFeeders; f++)
+    for (int f = 0; f < nfeed; f++)
         if (rcs[f]) return fail(rcs[f], "host-to-device copy through the bounce buffers failed: %s", errs[f].c_str());
-    for (int f = 0; f < kFeeders; f++) {                      // join: the copy stream continues after all pieces
+    for (int f = 0; f < nfeed; f++) {                         // join: the copy stream continues after all pieces
         SG_CUDA(cudaEventRecord(D.feeder_done[f], D.feeder_stream[f]));
         SG_CUDA(cudaStreamWaitEvent(D.copy_stream, D.feeder_done[f], 0));
     }
