@@ -1093,6 +1093,46 @@ static int run_on_devices(const std::vector<std::vector<WorkItem>> &shards,
     return 0;
 }
 
+// The common multi-device call -- plain files, none heavy enough to need placing on its own --
+// needs no item copies at all: the caller's arrays are cut into ndev contiguous index ranges of
+// equal weight and every device works on its range in place.  Returns false when an item weighs
+// more than 1/(4 ndev) of the job (shard_items then places those first).
+template <class Weight>
+static bool split_contiguous(const uint64_t *lengths, size_t n, size_t ndev, Weight weight_of, std::vector<size_t> &cut) {
+    uint64_t total = 0;
+    for (size_t i = 0; i < n; i++) total += weight_of(lengths[i]);
+    const uint64_t big = std::max<uint64_t>(total / (4 * (uint64_t)ndev), 1);
+    cut.assign(ndev + 1, n);
+    cut[0] = 0;
+    uint64_t acc = 0;
+    size_t d = 1;
+    for (size_t i = 0; i < n; i++) {
+        const uint64_t w = weight_of(lengths[i]);
+        if (w > big) return false;
+        while (d < ndev && acc >= total * d / ndev) cut[d++] = i;
+        acc += w;
+    }
+    return true;
+}
+
+static int run_on_ranges(const std::vector<size_t> &cut, const std::function<int(Device &, size_t lo, size_t hi)> &fn) {
+    auto &R = rt();
+    const size_t ndev = R.devs.size();
+    std::vector<int> rcs(ndev, 0);
+    std::vector<std::string> errs(ndev);
+    std::vector<std::thread> threads;
+    for (size_t d = 0; d < ndev; d++)
+        threads.emplace_back([&, d]() {
+            if (cut[d] == cut[d + 1]) return;
+            rcs[d] = fn(*R.devs[d], cut[d], cut[d + 1]);
+            if (rcs[d]) errs[d] = g_last_error;
+        });
+    for (auto &t : threads) t.join();
+    for (size_t d = 0; d < ndev; d++)
+        if (rcs[d]) return fail(rcs[d], "device %zu: %s", d, errs[d].c_str());
+    return 0;
+}
+
 static int sha512_host_items(const uint8_t *data, const std::vector<WorkItem> &all, uint8_t *digests);
 
 int sha512_host_segments(const uint8_t *data, const HostSeg *segs, size_t n, uint8_t *digests) {
@@ -1240,6 +1280,11 @@ int snapgpu_sha512_batch(const uint8_t *data, const uint64_t *offsets, const uin
     if (!runtime_ready()) return fail(SNAPGPU_ENOINIT, "snapgpu_init has not been called (or failed)");
     if (rt().devs.size() == 1)       // one device: the caller's arrays are the item list
         return sha512_shard(*rt().devs[0], data, ItemList(offsets, lengths, nfiles), digests);
+    std::vector<size_t> cut;
+    if (split_contiguous(lengths, nfiles, rt().devs.size(), [](uint64_t len) { return seg_blocks(len, 0) + 1; }, cut))
+        return run_on_ranges(cut, [&](Device &D, size_t lo, size_t hi) {
+            return sha512_shard(D, data, ItemList(offsets + lo, lengths + lo, hi - lo), digests + 64 * lo);
+        });
     std::vector<WorkItem> all(nfiles);
     for (size_t i = 0; i < nfiles; i++) {
         if (lengths[i] >= kMaxSegBytes) return fail(SNAPGPU_EINVAL, "file %zu too large", i);
@@ -1265,6 +1310,11 @@ int snapgpu_cmp_batch(const uint8_t *a, const uint8_t *b, const uint64_t *offset
     if (!a || !b || !offsets || !lengths || !equal) return fail(SNAPGPU_EINVAL, "null argument");
     memset(equal, 1, npairs);
     if (rt().devs.size() == 1) return cmp_shard(*rt().devs[0], a, b, ItemList(offsets, lengths, npairs), equal);
+    std::vector<size_t> cut;
+    if (split_contiguous(lengths, npairs, rt().devs.size(), [](uint64_t len) { return len + 64; }, cut))
+        return run_on_ranges(cut, [&](Device &D, size_t lo, size_t hi) {
+            return cmp_shard(D, a, b, ItemList(offsets + lo, lengths + lo, hi - lo), equal + lo);
+        });
     std::vector<WorkItem> all(npairs);
     std::vector<uint64_t> weight(npairs);
     for (size_t i = 0; i < npairs; i++) {

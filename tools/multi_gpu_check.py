@@ -42,4 +42,24 @@ for nd in [n for n in (1, 2, 4, 8) if n <= ngpu]:
     print(json.dumps({"what": "in-process sharding, host buffers (config 2 batch)", "devices": nd, "ms": best * 1e3,
                       "gb_per_s": nbytes / best / 1e9, "bit_exact_with_oracle": True}), flush=True)
     N.lib().snapgpu_free_pinned(p)
+    if nd > 1 and "--weak" in sys.argv:
+        # weak scaling: one config 2 batch PER DEVICE in one pinned buffer, one call
+        big_ln = np.tile(ln, nd)
+        big_off = np.concatenate([off + np.uint64(k * len(data)) for k in range(nd)])
+        p = N.lib().snapgpu_alloc_pinned(len(data) * nd)
+        host = np.frombuffer((ctypes.c_uint8 * (len(data) * nd)).from_address(p), dtype=np.uint8)
+        for k in range(nd):
+            host[k * len(data):(k + 1) * len(data)] = data
+        got = helpers.sha512_batch(host, big_off, big_ln)
+        assert np.array_equal(got, np.tile(want, (nd, 1))), f"{nd} devices, weak: digests differ from the oracle"
+        best = 1e9
+        for _ in range(4):
+            t0 = time.perf_counter()
+            helpers.sha512_batch(host, big_off, big_ln, out=got)
+            best = min(best, time.perf_counter() - t0)
+        print(json.dumps({"what": "in-process sharding, host buffers, one config 2 batch per device (weak)", "devices": nd,
+                          "files": int(len(big_ln)), "ms": best * 1e3, "gb_per_s": nbytes * nd / best / 1e9,
+                          "bit_exact_with_oracle": True}), flush=True)
+        del host
+        N.lib().snapgpu_free_pinned(p)
     N.lib().snapgpu_shutdown()
