@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Randomised parity stress: random batches x random options (kernel variant, launch shape, long-file
 bin form, staging size, alignment, pinned/pageable, device-resident/host path) against the oracle.
-usage: stress.py [seconds] [seed]   -- prints one JSON summary line; exits 1 on the first mismatch."""
+usage: stress.py [seconds] [seed] [devices]   -- prints one JSON summary line; exits 1 on the first mismatch.
+With devices > 1 the host-buffer calls are sharded over that many GPUs in this one process."""
 import ctypes
 import json
 import sys
@@ -19,8 +20,9 @@ from snappy_b200 import device, helpers       # noqa: E402
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+ndev = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 rng = np.random.default_rng(seed)
-N.init([0])
+N.init(list(range(ndev)))
 O.build()
 KiB, MiB = 1 << 10, 1 << 20
 
@@ -104,5 +106,5 @@ while time.time() < t_end:
                               "got": np.nonzero(eq == 0)[0].tolist()[:10]}), flush=True)
             mism += 1
             break
-print(json.dumps({"what": "randomised parity stress", "seed": seed, "seconds": budget, "cases": cases, "mismatches": mism}))
+print(json.dumps({"what": "randomised parity stress", "devices": ndev, "seed": seed, "seconds": budget, "cases": cases, "mismatches": mism}))
 sys.exit(1 if mism else 0)
