@@ -163,6 +163,13 @@ void snapgpu_digest_cache_stats(size_t *entries, uint64_t *hits);
 int snapgpu_verify_hashes(const char *root, const char *yaml_path, const char *data_tar, char **report,
                           size_t *count);
 
+/* The reader side, as the reference uses it: NewSnapPartFromYaml reads meta/hashes.yaml and keeps
+ * archive-sha512 as the part's hash (snappy/snapp.go:466-478).  Like yaml.Unmarshal into hashesYaml
+ * this decodes every entry's mode (yamlFileMode.UnmarshalYAML, snappy/hashes.go:59-88): a mode that
+ * does not start with d, f or l fails the read with SNAPGPU_EMODE "Unknown file mode ...".  Host
+ * logic only (no GPU).  hexdigest gets the NUL-terminated value (129 bytes hold a SHA-512). */
+int snapgpu_read_archive_sha512(const char *yaml_path, char *hexdigest, size_t cap);
+
 void snapgpu_free(void *p);
 
 /* ---- synthetic inputs and instrumentation (bench/test support, not product API) ------ */

@@ -70,6 +70,7 @@ SIGNATURES = {
     "snapgpu_apparmor_delta": (_i, [_cp, _cp, _cp, _pp, _psz, _pp, _psz]),
     "snapgpu_free": (None, [_vp]),
     "snapgpu_verify_hashes": (_i, [_cp, _cp, _cp, _pp, _psz]),
+    "snapgpu_read_archive_sha512": (_i, [_cp, _cp, _sz]),
     "snapgpu_hasher_new": (_vp, []),
     "snapgpu_hasher_write": (_i, [_vp, _vp, _sz]),
     "snapgpu_hasher_sum": (_i, [_vp, _vp]),

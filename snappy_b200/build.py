@@ -52,6 +52,14 @@ def verifyHashes(root: str, yamlPath: str, dataTar: str | None = None) -> list[s
     return _names(ptr, count)
 
 
+def readArchiveSha512(yamlPath: str) -> str:
+    """``part.hash`` of NewSnapPartFromYaml (snappy/snapp.go:466-478): archive-sha512 of a hashes.yaml,
+    after decoding every entry's mode like yaml.Unmarshal does (UnknownFileMode on a bad one)."""
+    buf = ctypes.create_string_buffer(256)
+    _raise(N.lib().snapgpu_read_archive_sha512(N.fs(yamlPath), buf, 256))
+    return buf.value.decode()
+
+
 def digest_cache_stats() -> tuple[int, int]:
     entries, hits = ctypes.c_size_t(), ctypes.c_uint64()
     N.lib().snapgpu_digest_cache_stats(ctypes.byref(entries), ctypes.byref(hits))

@@ -1547,6 +1547,62 @@ int verify_hashes(const std::string &root, const std::string &yaml_path, const s
     return 0;
 }
 
+// The reader side of the format, as the reference uses it: NewSnapPartFromYaml reads
+// meta/hashes.yaml, yaml.Unmarshal's it into hashesYaml and keeps ArchiveSha512 as the part's
+// hash (snappy/snapp.go:466-478).  Unmarshalling decodes every entry's mode through
+// yamlFileMode.UnmarshalYAML (snappy/hashes.go:59-88), so a mode string that does not start with
+// d, f or l fails the whole read with "Unknown file mode ...".  The document is cut textually
+// (split_hashes_yaml); a scalar in double or single quotes is unquoted.
+std::string unquote_simple(std::string v) {
+    size_t b = v.find_first_not_of(' ');
+    v = b == std::string::npos ? std::string() : v.substr(b);
+    if (v.size() >= 2 && ((v.front() == '"' && v.back() == '"') || (v.front() == '\'' && v.back() == '\'')))
+        v = v.substr(1, v.size() - 2);
+    return v;
+}
+
+int read_archive_sha512(const std::string &yaml_path, std::string *hex) {
+    std::string doc;
+    {
+        int fd = ::open(yaml_path.c_str(), O_RDONLY | O_CLOEXEC);
+        if (fd < 0) return fail(SNAPGPU_EIO, "%s", go_path_error("open", yaml_path, errno).c_str());
+        char buf[1 << 16];
+        for (;;) {
+            ssize_t r = ::read(fd, buf, sizeof buf);
+            if (r < 0 && errno == EINTR) continue;
+            if (r < 0) {
+                const int e = errno;
+                ::close(fd);
+                return fail(SNAPGPU_EIO, "%s", go_path_error("read", yaml_path, e).c_str());
+            }
+            if (r == 0) break;
+            doc.append(buf, (size_t)r);
+        }
+        ::close(fd);
+    }
+    // an empty document and the empty flow mapping "{}" (what the reference's test fixtures write,
+    // snappy/common_test.go:77) unmarshal to the zero value: no hash
+    {
+        size_t b = doc.find_first_not_of(" \t\r\n"), e = doc.find_last_not_of(" \t\r\n");
+        const std::string body = b == std::string::npos ? std::string() : doc.substr(b, e - b + 1);
+        if (body.empty() || body == "{}" || body == "---") {
+            hex->clear();
+            return 0;
+        }
+    }
+    std::string archive;
+    std::vector<YamlEntryBlock> blocks;
+    int rc = split_hashes_yaml(doc, &archive, &blocks);
+    if (rc) return rc;
+    for (const YamlEntryBlock &b : blocks) {
+        const std::string m = unquote_simple(b.mode);
+        if (m.empty() || (m[0] != 'd' && m[0] != 'f' && m[0] != 'l'))
+            return fail(SNAPGPU_EMODE, "Unknown file mode %s", m.c_str());
+    }
+    *hex = unquote_simple(archive);
+    return 0;
+}
+
 int write_file_0644(const std::string &path, const std::string &content) {
     int fd = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0644);
     if (fd < 0) return fail(SNAPGPU_EIO, "%s", go_path_error("open", path, errno).c_str());
@@ -2018,6 +2074,16 @@ int snapgpu_verify_hashes(const char *root, const char *yaml_path, const char *d
     int rc = verify_hashes(clean_dir(root), yaml_path, data_tar ? &tar : nullptr, &lines);
     if (rc) return rc;
     return pack_names(lines, report, count);
+}
+
+int snapgpu_read_archive_sha512(const char *yaml_path, char *hexdigest, size_t cap) {
+    if (!yaml_path || !hexdigest || cap == 0) return fail(SNAPGPU_EINVAL, "null argument");
+    std::string hex;
+    int rc = read_archive_sha512(yaml_path, &hex);
+    if (rc) return rc;
+    if (hex.size() + 1 > cap) return fail(SNAPGPU_EINVAL, "archive-sha512 does not fit %zu bytes", cap);
+    memcpy(hexdigest, hex.c_str(), hex.size() + 1);
+    return 0;
 }
 
 snapgpu_hasher *snapgpu_hasher_new(void) {

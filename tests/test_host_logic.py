@@ -311,3 +311,27 @@ def test_missing_archive_is_reported_before_anything_else(native, oracle, tmp_pa
         assert "no-such.tar.gz" in str(e.value)
         assert (tree / "DEBIAN").is_dir()
         assert not (tree / "DEBIAN" / "hashes.yaml").exists()
+
+
+def test_read_archive_sha512_like_new_snap_part(native, golden_dir, tmp_path):
+    """The reader side (snappy/snapp.go:466-478): TestLocalSnapHash (snappy/snapp_test.go:159-170), the
+    "{}" fixture of makeInstalledMockSnap (snappy/common_test.go:77), the golden document, and the mode
+    decoding of yamlFileMode.UnmarshalYAML (snappy/hashes.go:59-88)."""
+    from snappy_b200 import build
+    f = tmp_path / "hashes.yaml"
+    f.write_bytes(b"archive-sha512: F00F00")                     # no trailing newline, as the reference writes it
+    assert build.readArchiveSha512(str(f)) == "F00F00"
+    f.write_bytes(b"{}")
+    assert build.readArchiveSha512(str(f)) == ""
+    f.write_bytes(b"")
+    assert build.readArchiveSha512(str(f)) == ""
+    assert build.readArchiveSha512(str(golden_dir / "hashes_simple.yaml")) == (
+        "cf83e1357eefb8bdf1542850d66d8007d620e4050b5715dc83f4a921d36ce9ce47d0d13c5d85f2b0ff8318d2877eec2f63b931bd47417a81a538327af927da3e")
+    f.write_bytes(b'archive-sha512: "12345"\nfiles:\n- name: a\n  mode: drwxr-xr-x\n- name: b\n  size: 0\n  sha512: 00\n  mode: frw-r--r--\n')
+    assert build.readArchiveSha512(str(f)) == "12345"           # a quoted (number-like) scalar is unquoted
+    f.write_bytes(b"archive-sha512: ab\nfiles:\n- name: a\n  mode: prw-r--r--\n")
+    with pytest.raises(build.UnknownFileMode) as e:
+        build.readArchiveSha512(str(f))
+    assert "Unknown file mode prw-r--r--" in str(e.value)
+    with pytest.raises(OSError):
+        build.readArchiveSha512(str(tmp_path / "missing.yaml"))
