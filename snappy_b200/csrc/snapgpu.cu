@@ -523,8 +523,12 @@ static int launch_sha512(Device &D, cudaStream_t stream, const uint8_t *d_data, 
     int per_sm = (int)R.opt.sha_warps_per_sm.load();
     if (per_sm <= 0) {
         const uint64_t lanes = (uint64_t)D.sm_count * kShaThreads;
+        // depth = how many times the longest file fits into a lane's share of the launch.  Below 2
+        // the longest chain is the makespan and must have its sub-partition to itself; three
+        // warps only pay off for deep launches (measured over seven length distributions,
+        // profiles/r01_shape_probe.jsonl: with depth 3..5 two warps are 1-10 % faster than three)
         const uint64_t depth = max_blocks ? total_blocks / (lanes * max_blocks) : 1;
-        per_sm = (int)std::min<uint64_t>(std::max<uint64_t>(depth, 1), 3);
+        per_sm = depth < 2 ? 1 : depth < 6 ? 2 : 3;
     }
     per_sm = std::min(per_sm, kShaCtasPerSmMax);
     const u32 nunits = (u32)((n + 31) / 32);

@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""Which launch shape (CTAs per SM) is best for which length distribution: kernel-only, device-resident."""
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from snappy_b200 import _native as N          # noqa: E402
+from snappy_b200 import device, synth         # noqa: E402
+
+N.init([0])
+PEAK = 148 * 64 * 1.965e9
+rng = np.random.default_rng(5)
+n = 400_000
+cases = {
+    "lognormal s=1.0 (cfg2 x4)": synth.lognormal_sizes(n),
+    "lognormal s=0.5": np.clip(np.round(np.exp(rng.normal(np.log(8192), 0.5, n))), 1024, 65536).astype(np.uint64),
+    "lognormal s=0.25": np.clip(np.round(np.exp(rng.normal(np.log(8192), 0.25, n))), 1024, 65536).astype(np.uint64),
+    "uniform 0..64K": rng.integers(0, 65536, n // 2).astype(np.uint64),
+    "uniform 8K..16K": rng.integers(8192, 16384, n).astype(np.uint64),
+    "half 4K half 64K": np.concatenate([np.full(n // 4, 4096), np.full(n // 8, 65536)]).astype(np.uint64),
+    "uniform 4K": np.full(n, 4096, dtype=np.uint64),
+}
+for name, lengths in cases.items():
+    off, total = synth.layout(lengths)
+    d = torch.empty(total, dtype=torch.uint8, device="cuda:0")
+    device.synth_fill_device(d, off, lengths)
+    blocks = synth.blocks(lengths)
+    row = {"lengths": name, "files": len(lengths), "max_over_mean_blocks": round(float(blocks.max() / blocks.mean()), 2),
+           "depth": round(float(blocks.sum() / (148 * 128 * blocks.max())), 2)}
+    for r in (0, 1, 2, 3):
+        N.set_option("sha_warps_per_sm", r)
+        dg = torch.empty((len(lengths), 64), dtype=torch.uint8, device="cuda:0")
+        for _ in range(2):
+            device.sha512_batch_device(d, off, lengths, dg)
+        torch.cuda.synchronize()
+        N.reset_stats()
+        for _ in range(10):
+            device.sha512_batch_device(d, off, lengths, dg)
+        torch.cuda.synchronize()
+        s = N.stats()
+        ms = s.sha512_kernel_ms_sum / s.sha512_kernel_timed
+        row["auto" if r == 0 else f"R{r}"] = round(int(blocks.sum()) * 3568 / (ms * 1e-3) / PEAK, 4)
+    print(json.dumps(row), flush=True)
+    del d
