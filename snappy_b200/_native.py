@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libsnapgpu.so"
+LIB_PATH = Path(os.environ.get("SNAPGPU_LIB") or _HERE / "libsnapgpu.so")    # SNAPGPU_LIB: an experimental build
 
 OK, ECUDA, EINVAL, EIO, EMODE, ENAME, ENOINIT = 0, -1, -2, -3, -4, -5, -6
 

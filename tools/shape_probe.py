@@ -17,6 +17,8 @@ PEAK = 148 * 64 * 1.965e9
 rng = np.random.default_rng(5)
 n = 400_000
 cases = {
+    "config 2 (100k lognormal s=1.0)": synth.lognormal_sizes(100_000),
+    "config 5 shard (250k x 64K)": np.full(250_000, 65536, dtype=np.uint64),
     "lognormal s=1.0 (cfg2 x4)": synth.lognormal_sizes(n),
     "lognormal s=0.5": np.clip(np.round(np.exp(rng.normal(np.log(8192), 0.5, n))), 1024, 65536).astype(np.uint64),
     "lognormal s=0.25": np.clip(np.round(np.exp(rng.normal(np.log(8192), 0.25, n))), 1024, 65536).astype(np.uint64),
