@@ -75,6 +75,7 @@ std::string hex_lower(const uint8_t *p, size_t n) {
 // ------------------------------------------------------------------------------------------
 
 constexpr int kPlanSlots = 4;
+constexpr size_t kCounterBytes = 64 + 8 * (2 + 4 * 256);   // unit counter | balance[2 + sub-partitions] (up to 256 SMs)
 constexpr int kFeeders = 8;                     // at most this many host threads move pageable memory into pinned bounce buffers
 constexpr size_t kBounceBytes = 4u << 20;
 constexpr size_t kMaxChunkItems = 1u << 20;
@@ -133,6 +134,8 @@ struct Options {
     std::atomic<long long> sha_variant{0};
     std::atomic<long long> cmp_ctas_per_sm{0};
     std::atomic<long long> time_kernels{1};
+    std::atomic<long long> balance{0};          // balance claims between SM sub-partitions when CTAs share an SM
+                                                // (experimental)
     std::atomic<long long> feeders{0};          // bounce-buffer threads per device for pageable input, 0 = auto
     std::atomic<long long> long_kernel{2};      // 0 off, 1 one lane per file, 2 a lane pair per file
 };
@@ -215,7 +218,7 @@ static int init_device(Device &D, int ordinal) {
         SG_CUDA(cudaEventCreate(&s.uploaded));
         SG_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
         SG_CUDA(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
-        SG_CUDA(cudaMalloc(&s.d_counter, 256));
+        SG_CUDA(cudaMalloc(&s.d_counter, kCounterBytes));
     }
     for (int b = 0; b < 2; b++) {
         SG_CUDA(cudaEventCreateWithFlags(&D.ev_copied[b], cudaEventDisableTiming));
@@ -311,7 +314,7 @@ static bool trace_on() {
     return on;
 }
 
-typedef void (*ShaKernel)(const uint8_t *, const SegDesc *, const u32 *, u32, uint8_t *, u32 *, u32);
+typedef void (*ShaKernel)(const uint8_t *, const SegDesc *, const u32 *, u32, uint8_t *, u32 *, u32, unsigned long long *, u32);
 
 constexpr int kShaCtasPerSmMax = 3;   // 168 registers per thread: no spills with the one-block-ahead prefetch
 constexpr int kShaVariants = 6;
@@ -513,7 +516,7 @@ static int launch_sha512(Device &D, cudaStream_t stream, const uint8_t *d_data, 
     // still hashing; the hashing kernel waits for the finished plan
     SG_CUDA(cudaMemcpyAsync(slot->d_buf, slot->h_buf, (n + n_long) * sizeof(SegDesc), cudaMemcpyHostToDevice,
                             D.copy_stream));
-    SG_CUDA(cudaMemsetAsync(slot->d_counter, 0, sizeof(u32), D.copy_stream));
+    SG_CUDA(cudaMemsetAsync(slot->d_counter, 0, kCounterBytes, D.copy_stream));
     if (n_main && (rc = enqueue_length_binning(D, D.copy_stream, plan, n, max_blocks))) return rc;
     SG_CUDA(cudaEventRecord(slot->uploaded, D.copy_stream));
     SG_CUDA(cudaStreamWaitEvent(stream, slot->uploaded, 0));
@@ -574,7 +577,12 @@ static int launch_sha512(Device &D, cudaStream_t stream, const uint8_t *d_data, 
         R.sha_long_launches++;
     }
     if (n_main) {
-        k<<<grid, kShaThreads, 0, stream>>>(d_data, plan.descs, plan.order, (u32)n, d_digests, slot->d_counter, 1u);
+        // several CTAs per SM: claims are balanced between SM sub-partitions (sha512_kernels.cuh)
+        unsigned long long *balance = nullptr;
+        if (grid > (u32)D.sm_count && D.sm_count <= 256 && R.opt.balance.load())
+            balance = reinterpret_cast<unsigned long long *>(reinterpret_cast<uint8_t *>(slot->d_counter) + 64);
+        k<<<grid, kShaThreads, 0, stream>>>(d_data, plan.descs, plan.order, (u32)n, d_digests, slot->d_counter, 1u, balance,
+                                            (u32)D.sm_count * 4);
         SG_CUDA(cudaGetLastError());
         R.kernel_launches++;
     }
@@ -1226,6 +1234,19 @@ void snapgpu_shutdown(void) {
 
 int snapgpu_num_devices(void) { return (int)rt().devs.size(); }
 
+#ifdef SNAPGPU_TRACE_WARPS
+// experimental build only: the per-warp records of the last SHA-512 launch on device `dev`
+int snapgpu_test_warp_trace(int dev, unsigned long long *out, size_t nwarps) {
+    Device *D = nullptr;
+    int rc = get_device(dev, &D);
+    if (rc) return rc;
+    SG_CUDA(cudaSetDevice(D->ordinal));
+    SG_CUDA(cudaDeviceSynchronize());
+    SG_CUDA(cudaMemcpyFromSymbol(out, g_warp_trace, std::min<size_t>(nwarps, 8192) * 4 * sizeof(unsigned long long)));
+    return 0;
+}
+#endif
+
 int snapgpu_set_option(const char *key, long long value) {
     if (!key) return fail(SNAPGPU_EINVAL, "null key");
     auto &o = rt().opt;
@@ -1244,6 +1265,8 @@ int snapgpu_set_option(const char *key, long long value) {
         o.cmp_ctas_per_sm = value;
     } else if (k == "time_kernels") {
         o.time_kernels = value ? 1 : 0;
+    } else if (k == "balance") {
+        o.balance = value ? 1 : 0;
     } else if (k == "feeders") {
         if (value < 0 || value > kFeeders) return fail(SNAPGPU_EINVAL, "feeders out of range");
         o.feeders = value;

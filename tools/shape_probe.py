@@ -27,25 +27,33 @@ cases = {
     "half 4K half 64K": np.concatenate([np.full(n // 4, 4096), np.full(n // 8, 65536)]).astype(np.uint64),
     "uniform 4K": np.full(n, 4096, dtype=np.uint64),
 }
+only = sys.argv[1] if len(sys.argv) > 1 else ""
 for name, lengths in cases.items():
+    if only and only not in name:
+        continue
     off, total = synth.layout(lengths)
     d = torch.empty(total, dtype=torch.uint8, device="cuda:0")
     device.synth_fill_device(d, off, lengths)
     blocks = synth.blocks(lengths)
     row = {"lengths": name, "files": len(lengths), "max_over_mean_blocks": round(float(blocks.max() / blocks.mean()), 2),
            "depth": round(float(blocks.sum() / (148 * 128 * blocks.max())), 2)}
-    for r in (0, 1, 2, 3):
-        N.set_option("sha_warps_per_sm", r)
-        dg = torch.empty((len(lengths), 64), dtype=torch.uint8, device="cuda:0")
-        for _ in range(2):
-            device.sha512_batch_device(d, off, lengths, dg)
-        torch.cuda.synchronize()
-        N.reset_stats()
-        for _ in range(10):
-            device.sha512_batch_device(d, off, lengths, dg)
-        torch.cuda.synchronize()
-        s = N.stats()
-        ms = s.sha512_kernel_ms_sum / s.sha512_kernel_timed
-        row["auto" if r == 0 else f"R{r}"] = round(int(blocks.sum()) * 3568 / (ms * 1e-3) / PEAK, 4)
+    for bal in (1, 0):
+        N.set_option("balance", bal)
+        for r in ((0, 1, 2, 3) if bal else (2, 3)):
+            N.set_option("sha_warps_per_sm", r)
+            dg = torch.empty((len(lengths), 64), dtype=torch.uint8, device="cuda:0")
+            for _ in range(2):
+                device.sha512_batch_device(d, off, lengths, dg)
+            torch.cuda.synchronize()
+            N.reset_stats()
+            for _ in range(10):
+                device.sha512_batch_device(d, off, lengths, dg)
+            torch.cuda.synchronize()
+            s = N.stats()
+            ms = s.sha512_kernel_ms_sum / s.sha512_kernel_timed
+            key = ("auto" if r == 0 else f"R{r}") + ("" if bal else " unbalanced")
+            row[key] = round(int(blocks.sum()) * 3568 / (ms * 1e-3) / PEAK, 4)
+            print("   ", name, key, row[key], file=sys.stderr, flush=True)
+    N.set_option("balance", 0)
     print(json.dumps(row), flush=True)
     del d
