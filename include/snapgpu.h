@@ -211,6 +211,7 @@ int snapgpu_pipe_microbench(int dev, int kind, int warps_per_sm, double *inst_pe
 int snapgpu_test_yaml_from_digests(const char *build_dir, const uint8_t *digests, size_t ndigests,
                                    char **out, size_t *out_len);
 int snapgpu_test_shard(const uint64_t *weights, size_t n, int ndev, int *device_of);
+int snapgpu_test_split(const uint64_t *lengths, size_t n, int ndev, size_t *cut);   /* 1 = cut in place, 0 = too heavy an item */
 long long snapgpu_test_chunks(const uint64_t *offsets, const uint64_t *lengths, size_t n,
                               uint64_t cap, int is_sha, uint64_t *rows, size_t max_rows);
 /* the order the device-side length binning gives files of these lengths (needs a GPU) */

@@ -86,6 +86,7 @@ SIGNATURES = {
     "snapgpu_test_yaml_from_digests": (_i, [_cp, _vp, _sz, _pp, _psz]),
     "snapgpu_test_plan_order": (_i, [_vp, _sz, _vp]),
     "snapgpu_test_shard": (_i, [_vp, _sz, _i, _vp]),
+    "snapgpu_test_split": (_i, [_vp, _sz, _i, _vp]),
     "snapgpu_test_chunks": (ctypes.c_longlong, [_vp, _vp, _sz, _u64, _i, _vp, _sz]),
 }
 

@@ -1498,6 +1498,18 @@ int snapgpu_test_shard(const uint64_t *weights, size_t n, int ndev, int *device_
     return 0;
 }
 
+// The in-place multi-device split of a plain file list (split_contiguous): cut[0..ndev] are the
+// index boundaries.  Returns 1 when the list can be cut this way, 0 when an item is too heavy
+// (shard_items then places the heavy ones first), negative on a bad argument.
+int snapgpu_test_split(const uint64_t *lengths, size_t n, int ndev, size_t *cut) {
+    if (!lengths || !cut || ndev < 1) return fail(SNAPGPU_EINVAL, "bad argument");
+    std::vector<size_t> c;
+    const bool ok = split_contiguous(lengths, n, (size_t)ndev, [](uint64_t len) { return seg_blocks(len, 0) + 1; }, c);
+    if (!ok) return 0;
+    for (int d = 0; d <= ndev; d++) cut[d] = c[(size_t)d];
+    return 1;
+}
+
 // Chunking of a host batch for a staging buffer of `cap` bytes.  Writes one row of six u64
 // per produced item: user index, off, len, prefix, flags, chunk number.  Returns the number
 // of rows (or a negative error); rows beyond max_rows are counted but not written.

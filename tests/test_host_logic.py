@@ -148,6 +148,33 @@ def test_sharder_balances_and_covers(native):
             assert np.all(np.diff(d_small) >= 0)
 
 
+def test_contiguous_split_for_several_devices(native):
+    """The in-place multi-device split of a plain file list: contiguous index ranges that cover the list,
+    weights (blocks + 1) within one file of equal, and a refusal when one file is too heavy to be cut around."""
+    rng = np.random.default_rng(9)
+    blocks = lambda ln: (ln + 144) // 128 + 1
+    for ndev in (2, 4, 8):
+        for lengths in (np.full(2000, 65536, dtype=np.uint64), rng.integers(0, 70_000, 20_000).astype(np.uint64),
+                        np.clip(np.round(np.exp(rng.normal(np.log(8192), 1.0, 100_000))), 1024, 65536).astype(np.uint64),
+                        np.zeros(50, dtype=np.uint64), np.array([5, 5, 5], dtype=np.uint64)):
+            cut = np.zeros(ndev + 1, dtype=np.uint64)
+            rc = native.lib().snapgpu_test_split(lengths.ctypes.data, len(lengths), ndev, cut.ctypes.data)
+            w = blocks(lengths.astype(np.int64))
+            if rc == 0:                                   # only when a single file outweighs 1/(4 ndev) of the job
+                assert w.max() > max(w.sum() // (4 * ndev), 1)
+                continue
+            assert rc == 1
+            c = cut.astype(np.int64)
+            assert c[0] == 0 and c[-1] == len(lengths) and np.all(np.diff(c) >= 0)
+            loads = np.array([w[c[d]:c[d + 1]].sum() for d in range(ndev)])
+            assert loads.sum() == w.sum()
+            if len(lengths) >= 100 * ndev:
+                assert loads.max() - loads.min() <= 2 * w.max() + 2, (ndev, loads)
+        heavy = np.concatenate([rng.integers(0, 5000, 1000), [1 << 30]]).astype(np.uint64)
+        cut = np.zeros(ndev + 1, dtype=np.uint64)
+        assert native.lib().snapgpu_test_split(heavy.ctypes.data, len(heavy), ndev, cut.ctypes.data) == 0
+
+
 def test_chunker_covers_every_byte_once(native):
     rng = np.random.default_rng(5)
     lengths = np.concatenate([rng.integers(0, 40000, 300), [1_500_000, 0, 999_999, 128, 1_048_576]]).astype(np.uint64)
