@@ -113,3 +113,66 @@ def test_pair_schedule_matches_hashlib():
     for n in (0, 1, 3, 111, 112, 127, 128, 129, 1000, 4096, 5001):
         m = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
         assert sha512_pair(m) == hashlib.sha512(m).digest(), n
+
+
+# ---- design check for the next step: no pipeline refill between blocks ----------------
+
+def sha512_pair_continuous(msg):
+    """Lane 1 stays two rounds behind lane 0 ACROSS block boundaries: 80 iterations per block instead of 82,
+    no seeds.  Each lane feeds forward at its own time (lane 0 before iteration 80 n, lane 1 before 80 n + 2);
+    in its last four rounds of a block lane 1 publishes a + H (what lane 0 needs as d in rounds 0..3 of the
+    next block) by loading -H where it otherwise loads 0; lane 1's own sum leaves that load out (dn * mul)."""
+    n = len(msg)
+    msg = msg + b"\x80" + b"\0" * ((111 - n) % 128) + (8 * n).to_bytes(16, "big")
+    total = 80 * (len(msg) // 128)
+    ring = []
+    for o in range(0, len(msg), 128):
+        ring += producer(msg[o:o + 128])
+    H = [list(IV[4:8]), list(IV[0:4])]
+    T, A = {}, {}
+    a, b, c, d = H[1]
+    A[-2], A[-1] = d, c
+    T[-1] = (a - pair_sigma(b, 1) - pair_f(b, c, d, 1)) & M
+    seed0 = (b - pair_sigma(c, 1) - pair_f(c, d, 0, 1)) & M          # once per message, not per block
+    win = [list(H[0]), [c, d, 0, 0]]
+
+    def kin(lane, g):
+        return (ring[g] if g < total else 0) if lane == 0 else T[g - 2]
+
+    def din(lane, g):
+        if lane == 0:
+            return A[g - 2]
+        t1 = (g - 2) % 80
+        return (-H[1][3 - (t1 - 76)]) & M if g >= 2 and t1 >= 76 else 0   # rounds 76..79: -Hd, -Hc, -Hb, -Ha
+
+    D = [din(0, 0), din(1, 0)]
+    PD = [(win[0][3] + kin(0, 0) + D[0]) & M, seed0]
+    for g in range(total + 2):
+        if g % 80 == 0 and g > 0:                                   # lane 0 crosses a block boundary
+            old_h = H[0][3]
+            win[0] = [(x + y) & M for x, y in zip(win[0], H[0])]
+            H[0] = list(win[0])
+            PD[0] = (PD[0] + old_h) & M                             # PD had been built from the un-fed h
+        if (g - 2) % 80 == 0 and g > 2:                             # lane 1 does, two iterations later
+            win[1] = [(x + y) & M for x, y in zip(win[1], H[1])]
+            H[1] = list(win[1])
+        nxt = [(kin(l, g + 1), din(l, g + 1)) if g + 1 < total + 2 else (0, 0) for l in (0, 1)]
+        out = []
+        for l in (0, 1):
+            s0, s1, s2, s3 = win[l]
+            e = (pair_sigma(s0, l) + pair_f(s0, s1, s2, l) + PD[l]) & M
+            out.append((e - D[l]) & M)
+            PD[l] = (s2 * MUL[l] + nxt[l][0] + nxt[l][1] * MUL[l]) & M
+            D[l] = nxt[l][1]
+            if not (l == 0 and g >= total):                         # lane 0 is done after its last block
+                win[l] = [e, s0, s1, s2]
+        T[g], A[g] = out
+    win[1] = [(x + y) & M for x, y in zip(win[1], H[1])]
+    return b"".join(x.to_bytes(8, "big") for x in win[1] + H[0])
+
+
+def test_continuous_pair_schedule_matches_hashlib():
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 111, 112, 128, 129, 1000, 4096, 5001, 20000):
+        m = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert sha512_pair_continuous(m) == hashlib.sha512(m).digest(), n
