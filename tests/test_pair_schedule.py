@@ -119,9 +119,10 @@ def test_pair_schedule_matches_hashlib():
 
 def sha512_pair_continuous(msg):
     """Lane 1 stays two rounds behind lane 0 ACROSS block boundaries: 80 iterations per block instead of 82,
-    no seeds.  Each lane feeds forward at its own time (lane 0 before iteration 80 n, lane 1 before 80 n + 2);
-    in its last four rounds of a block lane 1 publishes a + H (what lane 0 needs as d in rounds 0..3 of the
-    next block) by loading -H where it otherwise loads 0; lane 1's own sum leaves that load out (dn * mul)."""
+    no seeds after the first block.  Each lane feeds forward at its own time (lane 0 before iteration 80 n,
+    lane 1 before 80 n + 2).  Lane 1 always publishes the plain a; what lane 0 needs as d in rounds 0..3 of a
+    block is a + H of lane 1's previous block, so lane 0 adds Hd, Hc, Hb, Ha (handed over by lane 1) to its
+    PD of those four rounds."""
     n = len(msg)
     msg = msg + b"\x80" + b"\0" * ((111 - n) % 128) + (8 * n).to_bytes(16, "big")
     total = 80 * (len(msg) // 128)
@@ -135,35 +136,46 @@ def sha512_pair_continuous(msg):
     T[-1] = (a - pair_sigma(b, 1) - pair_f(b, c, d, 1)) & M
     seed0 = (b - pair_sigma(c, 1) - pair_f(c, d, 0, 1)) & M          # once per message, not per block
     win = [list(H[0]), [c, d, 0, 0]]
+    handed = [0, 0, 0, 0]                                            # lane 1's H (a,b,c,d) as lane 0 last read it
+    published = list(H[1])                                           # what lane 1 wrote into the hand-over words
 
     def kin(lane, g):
         return (ring[g] if g < total else 0) if lane == 0 else T[g - 2]
 
     def din(lane, g):
-        if lane == 0:
-            return A[g - 2]
-        t1 = (g - 2) % 80
-        return (-H[1][3 - (t1 - 76)]) & M if g >= 2 and t1 >= 76 else 0   # rounds 76..79: -Hd, -Hc, -Hb, -Ha
+        return A[g - 2] if lane == 0 else 0
+
+    def fix(g):
+        """H word lane 0 adds to the PD of round g (rounds 0..3 of every block but the first)."""
+        t = g % 80
+        return handed[3 - t] if g >= 80 and t < 4 and g < total else 0   # t = 0: Hd, 1: Hc, 2: Hb, 3: Ha
 
     D = [din(0, 0), din(1, 0)]
     PD = [(win[0][3] + kin(0, 0) + D[0]) & M, seed0]
     for g in range(total + 2):
         if g % 80 == 0 and g > 0:                                   # lane 0 crosses a block boundary
+            handed = list(published)                                # lane 1 wrote them 78 iterations ago
             old_h = H[0][3]
             win[0] = [(x + y) & M for x, y in zip(win[0], H[0])]
             H[0] = list(win[0])
-            PD[0] = (PD[0] + old_h) & M                             # PD had been built from the un-fed h
+            PD[0] = (PD[0] + old_h + fix(g)) & M                    # PD had been built from the un-fed h and the plain d
+            D[0] = (D[0] + fix(g)) & M                              # ... and so had D, which is subtracted to publish T1
         if (g - 2) % 80 == 0 and g > 2:                             # lane 1 does, two iterations later
             win[1] = [(x + y) & M for x, y in zip(win[1], H[1])]
             H[1] = list(win[1])
+            published = list(H[1])
         nxt = [(kin(l, g + 1), din(l, g + 1)) if g + 1 < total + 2 else (0, 0) for l in (0, 1)]
         out = []
         for l in (0, 1):
             s0, s1, s2, s3 = win[l]
             e = (pair_sigma(s0, l) + pair_f(s0, s1, s2, l) + PD[l]) & M
             out.append((e - D[l]) & M)
-            PD[l] = (s2 * MUL[l] + nxt[l][0] + nxt[l][1] * MUL[l]) & M
+            PD[l] = (s2 * MUL[l] + nxt[l][0] + nxt[l][1]) & M
+            if l == 0 and (g + 1) % 80 in (1, 2, 3):
+                PD[l] = (PD[l] + fix(g + 1)) & M                    # rounds 1..3: in the peeled iterations 0..2
             D[l] = nxt[l][1]
+            if l == 0 and (g + 1) % 80 in (1, 2, 3):
+                D[l] = (D[l] + fix(g + 1)) & M
             if not (l == 0 and g >= total):                         # lane 0 is done after its last block
                 win[l] = [e, s0, s1, s2]
         T[g], A[g] = out
