@@ -122,6 +122,21 @@ int snapgpu_write_hashes(const char *build_dir, const char *data_tar);
  * verification mode. */
 int snapgpu_hashes_yaml(const char *build_dir, const char *data_tar, char **out, size_t *out_len);
 
+/* Phases of the most recent snapgpu_write_hashes / snapgpu_hashes_yaml / snapgpu_verify_hashes
+ * made by the calling thread (bench support).  Directory scan, file reads, host-to-device
+ * copies and kernels overlap inside pack_ms; the tails are what was left to wait for after the
+ * last file had been read. */
+typedef struct snapgpu_tree_stats_t {
+    double total_ms;
+    double pack_ms;         /* scan + open/read/close of every file (GPU batches run underneath) */
+    double gpu_tail_ms;     /* waiting for the last batches after the last file was packed */
+    double chain_tail_ms;   /* waiting for the archive's (and other long files') chain after that */
+    double yaml_ms;         /* walk-order assembly + document */
+    uint64_t entries, files_hashed, files_cached, batches, yaml_bytes;
+    unsigned pack_threads;
+} snapgpu_tree_stats_t;
+int snapgpu_tree_stats(snapgpu_tree_stats_t *out);
+
 /* helpers.FilesAreEqual (helpers/cmp.go:31): 1 equal, 0 not equal OR any error. */
 int snapgpu_files_are_equal(const char *a, const char *b);
 
@@ -210,6 +225,9 @@ int snapgpu_pipe_microbench(int dev, int kind, int warps_per_sm, double *inst_pe
 /* host logic only, usable without a GPU */
 int snapgpu_test_yaml_from_digests(const char *build_dir, const uint8_t *digests, size_t ndigests,
                                    char **out, size_t *out_len);
+/* one fileHash as yaml.v2 renders it (snappy/hashes_test.go:30-33); size < 0 / sha512_hex NULL = omitted */
+int snapgpu_test_filehash_yaml(const char *name, long long size, const char *sha512_hex, unsigned mode,
+                               char **out, size_t *out_len);
 int snapgpu_test_shard(const uint64_t *weights, size_t n, int ndev, int *device_of);
 int snapgpu_test_split(const uint64_t *lengths, size_t n, int ndev, size_t *cut);   /* 1 = cut in place, 0 = too heavy an item */
 long long snapgpu_test_chunks(const uint64_t *offsets, const uint64_t *lengths, size_t n,

@@ -39,6 +39,22 @@ class Stats(ctypes.Structure):
     ]
 
 
+class TreeStats(ctypes.Structure):
+    _fields_ = [
+        ("total_ms", ctypes.c_double),
+        ("pack_ms", ctypes.c_double),
+        ("gpu_tail_ms", ctypes.c_double),
+        ("chain_tail_ms", ctypes.c_double),
+        ("yaml_ms", ctypes.c_double),
+        ("entries", ctypes.c_uint64),
+        ("files_hashed", ctypes.c_uint64),
+        ("files_cached", ctypes.c_uint64),
+        ("batches", ctypes.c_uint64),
+        ("yaml_bytes", ctypes.c_uint64),
+        ("pack_threads", ctypes.c_uint),
+    ]
+
+
 _lib = None
 
 _vp, _sz, _u64, _i = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_int
@@ -65,6 +81,7 @@ SIGNATURES = {
     "snapgpu_sha512sum_file": (_i, [_cp, _cp]),
     "snapgpu_write_hashes": (_i, [_cp, _cp]),
     "snapgpu_hashes_yaml": (_i, [_cp, _cp, _pp, _psz]),
+    "snapgpu_tree_stats": (_i, [ctypes.POINTER(TreeStats)]),
     "snapgpu_files_are_equal": (_i, [_cp, _cp]),
     "snapgpu_dir_updated": (_i, [_cp, _cp, _cp, _pp, _psz]),
     "snapgpu_apparmor_delta": (_i, [_cp, _cp, _cp, _pp, _psz, _pp, _psz]),
@@ -84,6 +101,7 @@ SIGNATURES = {
     "snapgpu_reset_stats": (None, []),
     "snapgpu_pipe_microbench": (_i, [_i, _i, _i, _pd, _pd, _pd]),
     "snapgpu_test_yaml_from_digests": (_i, [_cp, _vp, _sz, _pp, _psz]),
+    "snapgpu_test_filehash_yaml": (_i, [_cp, ctypes.c_longlong, _cp, ctypes.c_uint, _pp, _psz]),
     "snapgpu_test_plan_order": (_i, [_vp, _sz, _vp]),
     "snapgpu_test_shard": (_i, [_vp, _sz, _i, _vp]),
     "snapgpu_test_split": (_i, [_vp, _sz, _i, _vp]),
@@ -140,6 +158,13 @@ def stats() -> Stats:
     s = Stats()
     check(lib().snapgpu_get_stats(ctypes.byref(s)))
     return s
+
+
+def tree_stats() -> dict:
+    """Phases of the calling thread's most recent write_hashes / hashes_yaml."""
+    s = TreeStats()
+    check(lib().snapgpu_tree_stats(ctypes.byref(s)))
+    return {k: getattr(s, k) for k, _ in TreeStats._fields_}
 
 
 def reset_stats() -> None:

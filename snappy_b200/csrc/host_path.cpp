@@ -24,6 +24,7 @@
 #include <errno.h>
 #include <fcntl.h>
 #include <sys/stat.h>
+#include <sys/syscall.h>
 #include <time.h>
 #include <unistd.h>
 
@@ -33,6 +34,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <condition_variable>
+#include <deque>
 #include <functional>
 #include <map>
 #include <mutex>
@@ -877,6 +880,7 @@ private:
         column_++;
     }
 
+public:
     // see string_value: the texts whose plain rendering is the text itself
     static bool plain_safe(const std::string &s) {
         const size_t n = s.size();
@@ -898,6 +902,7 @@ private:
         return true;
     }
 
+private:
     // write_plain for ASCII text without spaces: nothing to fold
     void write_plain_ascii(const char *p, size_t n) {
         if (!whitespace_) put(' ');
@@ -1119,31 +1124,24 @@ int yaml_file_mode(mode_t m, std::string *out) {
     return 0;
 }
 
-struct TreeEntry {
-    std::string name;       // path relative to the build dir
-    std::string path;
-    mode_t mode;
-    off_t size;
-    bool regular;
-    dev_t dev = 0;          // identity of the file at lstat time (digest cache key)
-    ino_t ino = 0;
-    struct timespec mtime = {0, 0};
-};
-
 // ------------------------------------------------------------------------------------------
 // digest cache: SHA-512 of files this library wrote itself (copyToBuildDir reads every copied
-// file once, for the copy and for the hash); writeHashes takes a cached digest only if device,
-// inode, size and mtime of the file are still what they were when it was written.
+// file once, for the copy and for the hash).  writeHashes takes a cached digest only if device,
+// inode, size, mtime AND ctime of the file are still what they were when it was written: mtime
+// can be set back with utimensat and is tick-granular, ctime moves with every write, truncate,
+// utimensat or rename over the inode and cannot be set.  The cache serves the ONE writeHashes
+// that follows the copy: a writeHashes run empties it.
 // ------------------------------------------------------------------------------------------
 
 struct CachedDigest {
     off_t size;
-    struct timespec mtime;
+    struct timespec mtime, ctime;
     uint8_t digest[64];
 };
 struct DigestCache {
     std::mutex mu;
     std::map<std::pair<dev_t, ino_t>, CachedDigest> map;
+    std::atomic<size_t> entries{0};
     uint64_t hits = 0;
 };
 DigestCache &digest_cache() {
@@ -1154,106 +1152,33 @@ void cache_put(const struct stat &st, const uint8_t digest[64]) {
     CachedDigest d;
     d.size = st.st_size;
     d.mtime = st.st_mtim;
+    d.ctime = st.st_ctim;
     memcpy(d.digest, digest, 64);
     DigestCache &C = digest_cache();
     std::lock_guard<std::mutex> lock(C.mu);
     if (C.map.size() >= ((size_t)1 << 22)) C.map.clear();      // bounded: a build stages one tree at a time
     C.map[std::make_pair(st.st_dev, st.st_ino)] = d;
+    C.entries = C.map.size();
 }
-bool cache_get(const TreeEntry &e, uint8_t digest[64]) {
+bool cache_get(const struct stat &st, uint8_t digest[64]) {
     DigestCache &C = digest_cache();
+    if (C.entries.load(std::memory_order_relaxed) == 0) return false;     // the usual case, without the lock
     std::lock_guard<std::mutex> lock(C.mu);
-    auto it = C.map.find(std::make_pair(e.dev, e.ino));
+    auto it = C.map.find(std::make_pair(st.st_dev, st.st_ino));
     if (it == C.map.end()) return false;
     const CachedDigest &d = it->second;
-    if (d.size != e.size || d.mtime.tv_sec != e.mtime.tv_sec || d.mtime.tv_nsec != e.mtime.tv_nsec) return false;
+    if (d.size != st.st_size || d.mtime.tv_sec != st.st_mtim.tv_sec || d.mtime.tv_nsec != st.st_mtim.tv_nsec ||
+        d.ctime.tv_sec != st.st_ctim.tv_sec || d.ctime.tv_nsec != st.st_ctim.tv_nsec)
+        return false;
     memcpy(digest, d.digest, 64);
     C.hits++;
     return true;
 }
-
-// filepath.Walk: pre-order, names of each directory sorted bytewise, Lstat.
-// The children of one directory are lstat'ed through its descriptor (fstatat), and at the top
-// level the subtrees of the root's sub-directories are walked by several threads and stitched
-// back together in Walk order.
-int walk_children(const std::string &dir, const std::string &rel, mode_t dir_mode, off_t dir_size,
-                  std::vector<TreeEntry> &out, bool top_level = false) {
-    DIR *d = opendir(dir.c_str());
-    if (!d) {
-        // Go reports the directory to the callback a second time with the error, and
-        // writeHashes ignores that error (build.go:228,241): the entry appears twice.
-        if (!rel.empty() && rel.compare(0, 7, "/DEBIAN") != 0)
-            out.push_back(TreeEntry{rel.substr(1), dir, dir_mode, dir_size, false});
-        return 0;
-    }
-    std::vector<std::string> names;
-    while (struct dirent *e = readdir(d)) {
-        if (!strcmp(e->d_name, ".") || !strcmp(e->d_name, "..")) continue;
-        names.emplace_back(e->d_name);
-    }
-    std::sort(names.begin(), names.end());
-    const int dfd = dirfd(d);
-    std::vector<struct stat> sts(names.size());
-    for (size_t i = 0; i < names.size(); i++)
-        if (fstatat(dfd, names[i].c_str(), &sts[i], AT_SYMLINK_NOFOLLOW) != 0) {
-            const int e = errno;
-            closedir(d);
-            return fail(SNAPGPU_EIO, "%s", go_path_error("lstat", dir + "/" + names[i], e).c_str());
-        }
-    closedir(d);
-
-    // sub-directories of the root: walked in parallel, each into its own list
-    std::vector<std::vector<TreeEntry>> sub;
-    std::vector<int> sub_rc;
-    std::vector<std::string> sub_err;
-    std::vector<size_t> subdirs;
-    if (top_level) {
-        for (size_t i = 0; i < names.size(); i++)
-            if (S_ISDIR(sts[i].st_mode)) subdirs.push_back(i);
-        const unsigned nthreads = std::min<unsigned>(packer_threads(16 * subdirs.size()), (unsigned)subdirs.size());
-        if (nthreads >= 2) {
-            sub.resize(subdirs.size());
-            sub_rc.assign(subdirs.size(), 0);
-            sub_err.resize(subdirs.size());
-            std::atomic<size_t> next{0};
-            auto work = [&]() {
-                for (size_t k; (k = next.fetch_add(1)) < subdirs.size();) {
-                    const size_t i = subdirs[k];
-                    sub_rc[k] = walk_children(dir + "/" + names[i], rel + "/" + names[i], sts[i].st_mode, sts[i].st_size, sub[k]);
-                    if (sub_rc[k]) sub_err[k] = snapgpu_last_error();
-                }
-            };
-            std::vector<std::thread> th;
-            for (unsigned t = 1; t < nthreads; t++) th.emplace_back(work);
-            work();
-            for (auto &x : th) x.join();
-        }
-    }
-
-    size_t k = 0;
-    for (size_t i = 0; i < names.size(); i++) {
-        const std::string child = dir + "/" + names[i];
-        const std::string crel = rel + "/" + names[i];
-        const struct stat &st = sts[i];
-        const bool skip = crel.compare(0, 7, "/DEBIAN") == 0;     // prefix test (build.go:229)
-        if (!skip) {
-            out.push_back(TreeEntry{crel.substr(1), child, st.st_mode, st.st_size, S_ISREG(st.st_mode)});
-            out.back().dev = st.st_dev;
-            out.back().ino = st.st_ino;
-            out.back().mtime = st.st_mtim;
-        }
-        if (S_ISDIR(st.st_mode)) {
-            if (!sub.empty()) {
-                if (sub_rc[k]) return fail(sub_rc[k], "%s", sub_err[k].c_str());
-                out.insert(out.end(), std::make_move_iterator(sub[k].begin()), std::make_move_iterator(sub[k].end()));
-                k++;
-            } else {
-                int rc = walk_children(child, crel, st.st_mode, st.st_size, out);
-                if (rc) return rc;
-            }
-        }
-    }
-    return 0;
+void cache_clear_entries() {
+    DigestCache &C = digest_cache();
+    std::lock_guard<std::mutex> lock(C.mu);
+    C.map.clear();
+    C.entries = 0;
 }
 
 std::string clean_dir(const char *p) {
@@ -1276,159 +1201,305 @@ int mkdir_all(const std::string &path, mode_t mode) {
     return (stat(path.c_str(), &st) == 0 && S_ISDIR(st.st_mode)) ? 0 : -1;
 }
 
-int collect_tree(const std::string &build_dir, std::vector<TreeEntry> &entries, bool make_debian = true) {
-    if (make_debian) mkdir_all(build_dir + "/DEBIAN", 0755);   // error ignored, like build.go:218-219
-    entries.clear();
-    struct stat root;
-    if (lstat(build_dir.c_str(), &root) == 0 && S_ISDIR(root.st_mode))
-        return walk_children(build_dir, "", root.st_mode, root.st_size, entries, true);
+#include "tree_hasher.hpp"
+
+bool TreeHasher::cache_lookup(const struct stat &st, uint8_t digest[64]) { return cache_get(st, digest); }
+
+// ------------------------------------------------------------------------------------------
+// yaml.Marshal(hashesYaml{...}) (build.go:264), written by the pool in one parallel pass.
+//
+// In what yaml.v2 emits for hashesYaml every sequence item is a run of lines of its own, so the
+// document is header + one text per entry, and an entry's text does not depend on its
+// neighbours.  Entries whose name is a run of [A-Za-z0-9_./+-] that yaml.v2 would not resolve
+// to a bool/int/float/null -- every entry of a real tree -- have a fixed layout
+//     "\n- name: N" ["\n  size: S\n  sha512: H"] "\n  mode: M"
+// whose length is known without writing it; anything else goes through the general emitter
+// (YamlEmitter) entry by entry.  Pass 1 sizes the entries, a prefix sum places them, pass 2
+// writes each into its place of the one output buffer.
+// ------------------------------------------------------------------------------------------
+
+struct TreeDoc {
+    char *buf = nullptr;       // malloc'd, NUL-terminated
+    size_t len = 0;
+};
+
+inline int mode_char(mode_t m) {          // yamlFileMode.MarshalYAML (snappy/hashes.go:36-45)
+    if (S_ISDIR(m)) return 'd';
+    if (S_ISLNK(m)) return 'l';
+    if (S_ISREG(m)) return 'f';
     return 0;
 }
 
-// yaml.Marshal(hashesYaml{...}) (build.go:264).  digests: archive first, then one per regular
-// entry in walk order.
-int emit_hashes_yaml(const std::vector<TreeEntry> &entries, const uint8_t *digests, size_t ndigests,
-                     std::string *yaml) {
-    size_t nreg = 0;
-    for (const TreeEntry &e : entries) nreg += e.regular;
-    if (ndigests != nreg + 1) return fail(SNAPGPU_EINVAL, "expected %zu digests, got %zu", nreg + 1, ndigests);
+// the hex of a digest consists of digits and 'e' only: the one shape of 128 hex characters that
+// could read as a number to yaml.v2 (it then goes through the general emitter, which decides)
+inline bool digest_hex_may_resolve(const uint8_t *d) {
+    for (int i = 0; i < 64; i++) {
+        const unsigned hi = d[i] >> 4, lo = d[i] & 15;
+        if ((hi > 9 && hi != 14) || (lo > 9 && lo != 14)) return false;
+    }
+    return true;
+}
+
+inline size_t decimal_digits(uint64_t v) {
+    size_t n = 1;
+    while (v >= 10) {
+        v /= 10;
+        n++;
+    }
+    return n;
+}
+
+inline char *put_hex(char *p, const uint8_t *d) {
+    static const char hx[] = "0123456789abcdef";
+    for (int i = 0; i < 64; i++) {
+        *p++ = hx[d[i] >> 4];
+        *p++ = hx[d[i] & 15];
+    }
+    return p;
+}
+
+// digests_in: nullptr = every regular entry carries its own digest (TEntry::digest); otherwise
+// the digests of the regular entries in walk order (the test hook's), 64 bytes each.
+int emit_tree_yaml(const std::vector<FlatEntry> &flat, const uint8_t archive_digest[64], const uint8_t *digests_in,
+                   TreeDoc *doc) {
+    const size_t n = flat.size();
+    YamlEmitter head;
     int rc;
-    YamlEmitter em;
-    em.out.reserve(256 + entries.size() * 224);           // ~200 bytes per regular entry
-    std::string hex(128, '0'), mode, num;
-    auto hex_into = [&hex](const uint8_t *p) {
-        static const char d[] = "0123456789abcdef";
-        for (int i = 0; i < 64; i++) {
-            hex[2 * i] = d[p[i] >> 4];
-            hex[2 * i + 1] = d[p[i] & 15];
+    head.key("archive-sha512");
+    if ((rc = head.string_value(hex_lower(archive_digest, 64)))) return rc;
+    head.key("files");
+    if (n == 0) {
+        head.empty_flow_sequence();
+        head.end_document();
+        doc->len = head.out.size();
+        doc->buf = static_cast<char *>(malloc(doc->len + 1));
+        if (!doc->buf) return fail(SNAPGPU_EINVAL, "out of memory");
+        memcpy(doc->buf, head.out.data(), doc->len + 1);
+        return 0;
+    }
+    IoPool &pool = IoPool::instance();
+    const unsigned nw = (unsigned)std::max<size_t>(1, std::min<size_t>(pool.size(), n / 2048));
+    std::vector<uint32_t> len(n);
+    std::vector<size_t> first_digest(nw + 1, 0);          // digests_in: index of the first regular entry of each range
+    if (digests_in)
+        for (unsigned t = 0; t < nw; t++) {
+            size_t regs = 0;
+            for (size_t k = n * t / nw; k < n * (t + 1) / nw; k++) regs += flat[k].e->kind == 1;
+            first_digest[t + 1] = first_digest[t] + regs;
+        }
+    struct Slow {
+        size_t index;
+        std::string text;
+    };
+    std::vector<std::vector<Slow>> slow(nw);
+    struct Err {
+        size_t index = ~(size_t)0;
+        int rc = 0;
+        std::string text;
+    };
+    std::vector<Err> errs(nw);
+
+    auto digest_of = [&](size_t k, size_t &di) -> const uint8_t * {
+        return digests_in ? digests_in + 64 * di++ : flat[k].e->digest;
+    };
+    auto size_pass = [&](unsigned t) {
+        std::string name, md;
+        size_t di = first_digest[t];
+        for (size_t k = n * t / nw; k < n * (t + 1) / nw; k++) {
+            const TDir *d = flat[k].dir;
+            const TEntry &e = *flat[k].e;
+            const int mc = mode_char(e.mode);
+            if (!mc) {                                       // the first one in walk order is the error (hashes.go:44)
+                if (errs[t].index == ~(size_t)0) {
+                    errs[t].index = k;
+                    errs[t].rc = SNAPGPU_EMODE;
+                    errs[t].text = "Unknown file mode " + go_mode_string(e.mode);
+                }
+                continue;
+            }
+            name.assign(d->rel);
+            name.append(d->names, e.name_off, e.name_len);
+            const bool regular = e.kind == 1;
+            const uint8_t *dg = regular ? digest_of(k, di) : nullptr;
+            const bool fast = YamlEmitter::plain_safe(name) && !resolves_to_non_string(name) && !is_base60_float(name) &&
+                              !(regular && digest_hex_may_resolve(dg));
+            if (fast) {
+                len[k] = (uint32_t)(9 + name.size() + (regular ? 9 + decimal_digits((uint64_t)e.size) + 11 + 128 : 0) + 9 + 10);
+                continue;
+            }
+            YamlEmitter em;
+            em.continue_after_line();
+            int r = yaml_file_mode(e.mode, &md);
+            em.begin_sequence_item();
+            em.key("name", true);
+            if (!r) r = em.string_value(name);
+            if (!r && regular) {
+                em.key("size");
+                em.plain_value(std::to_string((long long)e.size));
+                em.key("sha512");
+                r = em.string_value(hex_lower(dg, 64));
+            }
+            if (!r) {
+                em.key("mode");
+                r = em.string_value(md);
+            }
+            em.end_sequence_item();
+            if (r) {
+                if (errs[t].index == ~(size_t)0) {
+                    errs[t].index = k;
+                    errs[t].rc = r;
+                    errs[t].text = snapgpu_last_error();
+                }
+                continue;
+            }
+            len[k] = (uint32_t)em.out.size();
+            slow[t].push_back(Slow{k, std::move(em.out)});
         }
     };
-    em.key("archive-sha512");
-    hex_into(&digests[0]);
-    if ((rc = em.string_value(hex))) return rc;
-    em.key("files");
-    if (entries.empty()) {
-        em.empty_flow_sequence();
-    } else {
-        // one run of entries: the sequence items entries[lo, hi), digests from slot di on
-        auto emit_run = [&entries, digests](YamlEmitter &out, size_t lo, size_t hi, size_t di) -> int {
-            std::string hx(128, '0'), md, nm;
-            static const char dd[] = "0123456789abcdef";
-            int r;
-            for (size_t k = lo; k < hi; k++) {
-                const TreeEntry &e = entries[k];
-                if ((r = yaml_file_mode(e.mode, &md))) return r;
-                out.begin_sequence_item();
-                out.key("name", true);
-                if ((r = out.string_value(e.name))) return r;
-                if (e.regular) {
-                    out.key("size");
-                    nm = std::to_string((long long)e.size);
-                    out.plain_value(nm);
-                    out.key("sha512");
-                    const uint8_t *p = &digests[64 * di++];
-                    for (int i = 0; i < 64; i++) {
-                        hx[2 * i] = dd[p[i] >> 4];
-                        hx[2 * i + 1] = dd[p[i] & 15];
-                    }
-                    if ((r = out.string_value(hx))) return r;
-                }
-                out.key("mode");
-                if ((r = out.string_value(md))) return r;
-                out.end_sequence_item();
-            }
-            return 0;
-        };
-        const unsigned nthreads = std::min<unsigned>(packer_threads(entries.size() / 256), 8);
-        if (nthreads < 2) {
-            if ((rc = emit_run(em, 0, entries.size(), 1))) return rc;
-        } else {
-            // large trees: consecutive runs of entries are written by several threads, each into
-            // its own emitter that starts "after a line"; the pieces are concatenated in order
-            std::vector<size_t> lo(nthreads + 1), first_digest(nthreads + 1, 1);
-            for (unsigned t = 0; t <= nthreads; t++) lo[t] = entries.size() * t / nthreads;
-            for (unsigned t = 0; t < nthreads; t++) {
-                size_t regs = 0;
-                for (size_t k = lo[t]; k < lo[t + 1]; k++) regs += entries[k].regular;
-                first_digest[t + 1] = first_digest[t] + regs;
-            }
-            std::vector<YamlEmitter> part(nthreads);
-            std::vector<int> rcs(nthreads, 0);
-            std::vector<std::string> errs(nthreads);
-            auto work = [&](unsigned t) {
-                part[t].out.reserve((lo[t + 1] - lo[t]) * 224);
-                part[t].continue_after_line();
-                rcs[t] = emit_run(part[t], lo[t], lo[t + 1], first_digest[t]);
-                if (rcs[t]) errs[t] = snapgpu_last_error();
-            };
-            std::vector<std::thread> th;
-            for (unsigned t = 1; t < nthreads; t++) th.emplace_back(work, t);
-            work(0);
-            for (auto &x : th) x.join();
-            for (unsigned t = 0; t < nthreads; t++) {          // the first failing entry in walk order
-                if (rcs[t]) return fail(rcs[t], "%s", errs[t].c_str());
-                em.out += part[t].out;
-            }
-        }
+    const double ty0 = wall_ms();
+    pool.run(nw, size_pass);
+    const double ty1 = wall_ms();
+    for (unsigned t = 0; t < nw; t++)
+        if (errs[t].rc) return fail(errs[t].rc, "%s", errs[t].text.c_str());
+
+    std::vector<size_t> range_off(nw + 1);
+    size_t total = head.out.size();
+    for (unsigned t = 0; t < nw; t++) {
+        range_off[t] = total;
+        for (size_t k = n * t / nw; k < n * (t + 1) / nw; k++) total += len[k];
     }
-    em.end_document();
-    *yaml = std::move(em.out);
+    range_off[nw] = total;
+    total += 1;                                              // the document's final line break
+    char *buf = static_cast<char *>(malloc(total + 1));
+    if (!buf) return fail(SNAPGPU_EINVAL, "out of memory");
+    memcpy(buf, head.out.data(), head.out.size());
+    buf[total - 1] = '\n';
+    buf[total] = 0;
+
+    auto write_pass = [&](unsigned t) {
+        char *p = buf + range_off[t];
+        size_t di = first_digest[t];
+        size_t next_slow = 0;
+        char num[24];
+        for (size_t k = n * t / nw; k < n * (t + 1) / nw; k++) {
+            const TDir *d = flat[k].dir;
+            const TEntry &e = *flat[k].e;
+            const bool regular = e.kind == 1;
+            const uint8_t *dg = regular ? digest_of(k, di) : nullptr;
+            if (next_slow < slow[t].size() && slow[t][next_slow].index == k) {
+                const std::string &text = slow[t][next_slow++].text;
+                memcpy(p, text.data(), text.size());
+                p += text.size();
+                continue;
+            }
+            memcpy(p, "\n- name: ", 9);
+            p += 9;
+            memcpy(p, d->rel.data(), d->rel.size());
+            p += d->rel.size();
+            memcpy(p, d->names.data() + e.name_off, e.name_len);
+            p += e.name_len;
+            if (regular) {
+                memcpy(p, "\n  size: ", 9);
+                p += 9;
+                uint64_t v = (uint64_t)e.size;
+                int nd = 0;
+                do {
+                    num[nd++] = (char)('0' + v % 10);
+                    v /= 10;
+                } while (v);
+                while (nd) *p++ = num[--nd];
+                memcpy(p, "\n  sha512: ", 11);
+                p += 11;
+                p = put_hex(p, dg);
+            }
+            memcpy(p, "\n  mode: ", 9);
+            p += 9;
+            *p++ = (char)mode_char(e.mode);
+            static const char rwx[] = "rwxrwxrwx";
+            for (int i = 0; i < 9; i++) *p++ = (e.mode & (1u << (8 - i))) ? rwx[i] : '-';
+        }
+    };
+    const double ty2 = wall_ms();
+    pool.run(nw, write_pass);
+    if (getenv("SNAPGPU_TRACE"))
+        fprintf(stderr, "[snapgpu] yaml: size pass %.2f ms, layout+malloc %.2f ms, write pass %.2f ms (%u threads)\n", ty1 - ty0,
+                ty2 - ty1, wall_ms() - ty2, nw);
+    doc->buf = buf;
+    doc->len = total;
     return 0;
 }
+
+// Phases of the last build_tree_doc of this thread, for the bench and the trace.
+struct TreeStats {
+    double total_ms = 0, pack_ms = 0, gpu_tail_ms = 0, chain_tail_ms = 0, yaml_ms = 0;
+    uint64_t entries = 0, files_hashed = 0, files_cached = 0, batches = 0, yaml_bytes = 0;
+};
+thread_local TreeStats g_tree_stats;
 
 // data_tar == nullptr (verification without the archive): the archive digest is left zero.
 // make_debian: create DEBIAN/ first as writeHashes does (build.go:218-219); verification does not.
-int build_hashes_yaml(const std::string &build_dir, const std::string *data_tar_opt, std::string *yaml,
-                      bool make_debian) {
-    std::vector<TreeEntry> entries;
+int build_tree_doc(const std::string &build_dir, const std::string *data_tar, bool make_debian, TreeDoc *doc) {
     const double t0 = wall_ms();
-    const std::string data_tar = data_tar_opt ? *data_tar_opt : std::string();
-    if (data_tar_opt) {
-        // build.go:218-226: DEBIAN/ is made, then the archive is hashed, and only then the tree is
-        // walked -- an archive that cannot be opened is reported before any error of the walk
-        if (make_debian) mkdir_all(build_dir + "/DEBIAN", 0755);
-        const int fd = ::open(data_tar.c_str(), O_RDONLY | O_CLOEXEC);
-        if (fd < 0) return fail(SNAPGPU_EIO, "%s", go_path_error("open", data_tar, errno).c_str());
+    // build.go:218-226: DEBIAN/ is made, then the archive is hashed, and only then the tree is
+    // walked -- an archive that cannot be opened is reported before any error of the walk (and
+    // before the GPU is touched).  Here its chain starts first and the whole tree is hashed
+    // underneath it.
+    if (make_debian) mkdir_all(build_dir + "/DEBIAN", 0755);   // error ignored, like build.go:218-219
+    if (data_tar) {
+        const int fd = ::open(data_tar->c_str(), O_RDONLY | O_CLOEXEC);
+        if (fd < 0) return fail(SNAPGPU_EIO, "%s", go_path_error("open", *data_tar, errno).c_str());
         ::close(fd);
     }
-    int rc = collect_tree(build_dir, entries, make_debian);
+    int rc = ensure_init();
     if (rc) return rc;
-    // digests: archive first, then one per regular entry in walk order; entries this library
-    // copied into place itself (copyToBuildDir) come from the digest cache, the rest are hashed
-    size_t nreg = 0;
-    for (const TreeEntry &e : entries) nreg += e.regular;
-    std::vector<uint8_t> digests((nreg + 1) * 64, 0);
-    std::vector<std::string> paths;
-    std::vector<int64_t> sizes;
-    std::vector<size_t> slot_of;                         // digest slot of paths[k]
-    size_t slot = 1;
-    for (const TreeEntry &e : entries)
-        if (e.regular) {
-            if (!cache_get(e, &digests[64 * slot])) {
-                paths.push_back(e.path);
-                sizes.push_back((int64_t)e.size);        // the walk's lstat: no second stat
-                slot_of.push_back(slot);
-            }
-            slot++;
-        }
-    std::vector<uint8_t> fresh;
-    // archive-sha512 (build.go:222): one long chain, hashed in slices beside the tree's batches
-    Rider archive;
-    archive.path = data_tar;
+    uint8_t archive_digest[64] = {0};
+    int archive_err = 0;
+    uint8_t archive_op = 0;
+    TreeHasher tree(build_dir, true);
+    tree.chains.start();
+    if (data_tar) tree.chains.add(*data_tar, archive_digest, &archive_err, &archive_op);
+    rc = tree.run();
     const double t1 = wall_ms();
-    if ((rc = hash_files(paths, fresh, &sizes, nullptr, data_tar_opt ? &archive : nullptr))) return rc;
-    if (data_tar_opt) memcpy(&digests[0], archive.digest, 64);
-    for (size_t k = 0; k < paths.size(); k++) memcpy(&digests[64 * slot_of[k]], &fresh[64 * k], 64);
+    const int chain_rc = tree.chains.finish();
+    const std::string chain_err = chain_rc ? snapgpu_last_error() : "";
     const double t2 = wall_ms();
-    rc = emit_hashes_yaml(entries, digests.data(), nreg + 1, yaml);
+    if (make_debian) cache_clear_entries();                  // the digest cache serves one writeHashes
+    if (archive_err)
+        return fail(SNAPGPU_EIO, "%s", go_path_error(archive_op == 2 ? "open" : "read", *data_tar, archive_err).c_str());
+    if (rc) return rc;
+    if (chain_rc) return fail(chain_rc, "%s", chain_err.c_str());
+    std::vector<FlatEntry> flat;
+    tree.flatten(flat);
+    if ((rc = tree.first_error(flat))) return rc;
+    const double t3 = wall_ms();
+    rc = emit_tree_yaml(flat, archive_digest, nullptr, doc);
+    const double t4 = wall_ms();
+    TreeStats &S = g_tree_stats;
+    S.total_ms = t4 - t0;
+    S.pack_ms = tree.pack_ms() - tree.drain_ms();
+    S.gpu_tail_ms = tree.drain_ms();
+    S.chain_tail_ms = t2 - t1;
+    S.yaml_ms = t4 - t2;
+    S.entries = flat.size();
+    S.files_hashed = tree.files_hashed();
+    S.files_cached = tree.files_cached();
+    S.batches = tree.batches();
+    S.yaml_bytes = rc ? 0 : doc->len;
     if (getenv("SNAPGPU_TRACE"))
-        fprintf(stderr, "[snapgpu] writeHashes: walk %.2f ms (%zu entries), pack+hash %.2f ms (%zu files, %zu from the digest cache), yaml %.2f ms\n",
-                t1 - t0, entries.size(), t2 - t1, paths.size() + (data_tar_opt ? 1 : 0), nreg - paths.size(), wall_ms() - t2);
+        fprintf(stderr, "[snapgpu] writeHashes: %zu entries; scan+pack %.2f ms (%zu files in %zu batches, %zu from the digest cache), "
+                        "GPU tail %.2f ms, chains tail %.2f ms, flatten %.2f ms, yaml %.2f ms; total %.2f ms\n",
+                flat.size(), S.pack_ms, tree.files_hashed(), tree.batches(), tree.files_cached(), S.gpu_tail_ms, S.chain_tail_ms,
+                t3 - t2, t4 - t3, S.total_ms);
     return rc;
 }
 
-int build_hashes_yaml(const std::string &build_dir, const std::string &data_tar, std::string *yaml) {
-    return build_hashes_yaml(build_dir, &data_tar, yaml, true);
+int build_hashes_yaml(const std::string &build_dir, const std::string *data_tar_opt, std::string *yaml, bool make_debian) {
+    TreeDoc doc;
+    int rc = build_tree_doc(build_dir, data_tar_opt, make_debian, &doc);
+    if (rc) return rc;
+    yaml->assign(doc.buf, doc.len);
+    free(doc.buf);
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1603,12 +1674,12 @@ int read_archive_sha512(const std::string &yaml_path, std::string *hex) {
     return 0;
 }
 
-int write_file_0644(const std::string &path, const std::string &content) {
+int write_file_0644(const std::string &path, const char *content, size_t size) {
     int fd = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0644);
     if (fd < 0) return fail(SNAPGPU_EIO, "%s", go_path_error("open", path, errno).c_str());
     size_t done = 0;
-    while (done < content.size()) {
-        ssize_t w = ::write(fd, content.data() + done, content.size() - done);
+    while (done < size) {
+        ssize_t w = ::write(fd, content + done, size - done);
         if (w < 0) {
             if (errno == EINTR) continue;
             int e = errno;
@@ -1998,15 +2069,29 @@ int snapgpu_sha512sum_file(const char *infile, char hexdigest[129]) {
 
 int snapgpu_hashes_yaml(const char *build_dir, const char *data_tar, char **out, size_t *out_len) {
     if (!build_dir || !data_tar || !out || !out_len) return fail(SNAPGPU_EINVAL, "null argument");
-    std::string yaml;
-    int rc = build_hashes_yaml(clean_dir(build_dir), data_tar, &yaml);
+    const std::string tar = data_tar;
+    TreeDoc doc;
+    int rc = build_tree_doc(clean_dir(build_dir), &tar, true, &doc);
     if (rc) return rc;
-    char *buf = static_cast<char *>(malloc(yaml.size() + 1));
-    if (!buf) return fail(SNAPGPU_EINVAL, "out of memory");
-    memcpy(buf, yaml.data(), yaml.size());
-    buf[yaml.size()] = 0;
-    *out = buf;
-    *out_len = yaml.size();
+    *out = doc.buf;
+    *out_len = doc.len;
+    return 0;
+}
+
+int snapgpu_tree_stats(snapgpu_tree_stats_t *out) {
+    if (!out) return fail(SNAPGPU_EINVAL, "null argument");
+    const TreeStats &S = g_tree_stats;
+    out->total_ms = S.total_ms;
+    out->pack_ms = S.pack_ms;
+    out->gpu_tail_ms = S.gpu_tail_ms;
+    out->chain_tail_ms = S.chain_tail_ms;
+    out->yaml_ms = S.yaml_ms;
+    out->entries = S.entries;
+    out->files_hashed = S.files_hashed;
+    out->files_cached = S.files_cached;
+    out->batches = S.batches;
+    out->yaml_bytes = S.yaml_bytes;
+    out->pack_threads = IoPool::instance().size();
     return 0;
 }
 
@@ -2016,38 +2101,74 @@ int snapgpu_hashes_yaml(const char *build_dir, const char *data_tar, char **out,
 int snapgpu_test_yaml_from_digests(const char *build_dir, const uint8_t *digests, size_t ndigests, char **out,
                                    size_t *out_len) {
     if (!build_dir || !out_len) return fail(SNAPGPU_EINVAL, "null argument");
-    std::vector<TreeEntry> entries;
+    const std::string dir = clean_dir(build_dir);
     const double t0 = wall_ms();
-    int rc = collect_tree(clean_dir(build_dir), entries);
+    mkdir_all(dir + "/DEBIAN", 0755);                        // error ignored, like build.go:218-219
+    TreeHasher tree(dir, false);                             // scan and lstat only: no GPU
+    int rc = tree.run();
     if (rc) return rc;
+    std::vector<FlatEntry> flat;
+    tree.flatten(flat);
+    if ((rc = tree.first_error(flat))) return rc;
     const double t1 = wall_ms();
+    size_t nreg = 0;
+    for (const FlatEntry &f : flat) nreg += f.e->kind == 1;
     if (!digests) {
-        size_t nreg = 0;
-        for (const TreeEntry &e : entries) nreg += e.regular;
         *out_len = nreg + 1;
         return 0;
     }
     if (!out) return fail(SNAPGPU_EINVAL, "null argument");
-    std::string yaml;
-    if ((rc = emit_hashes_yaml(entries, digests, ndigests, &yaml))) return rc;
+    if (ndigests != nreg + 1) return fail(SNAPGPU_EINVAL, "expected %zu digests, got %zu", nreg + 1, ndigests);
+    TreeDoc doc;
+    if ((rc = emit_tree_yaml(flat, digests, digests + 64, &doc))) return rc;
     if (getenv("SNAPGPU_TRACE"))
-        fprintf(stderr, "[snapgpu] walk of %zu entries %.2f ms, yaml emit %.2f ms\n", entries.size(), t1 - t0, wall_ms() - t1);
-    char *buf = static_cast<char *>(malloc(yaml.size() + 1));
+        fprintf(stderr, "[snapgpu] walk of %zu entries %.2f ms, yaml emit %.2f ms\n", flat.size(), t1 - t0, wall_ms() - t1);
+    *out = doc.buf;
+    *out_len = doc.len;
+    return 0;
+}
+
+// Test hook (no GPU): the yaml.v2 rendering of one fileHash (snappy/hashes.go:93-101) as a
+// one-item sequence, the shape of TestHashesYamlMarshal (snappy/hashes_test.go:30-55): size < 0
+// and sha512_hex == NULL stand for the nil pointer and the empty string that omitempty drops.
+int snapgpu_test_filehash_yaml(const char *name, long long size, const char *sha512_hex, unsigned mode, char **out,
+                               size_t *out_len) {
+    if (!name || !out || !out_len) return fail(SNAPGPU_EINVAL, "null argument");
+    std::string md;
+    int rc = yaml_file_mode((mode_t)mode, &md);
+    if (rc) return rc;
+    YamlEmitter em;
+    em.key("name");
+    if ((rc = em.string_value(name))) return rc;
+    if (size >= 0) {
+        em.key("size");
+        em.plain_value(std::to_string(size));
+    }
+    if (sha512_hex && *sha512_hex) {
+        em.key("sha512");
+        if ((rc = em.string_value(sha512_hex))) return rc;
+    }
+    em.key("mode");
+    if ((rc = em.string_value(md))) return rc;
+    em.end_document();
+    char *buf = static_cast<char *>(malloc(em.out.size() + 1));
     if (!buf) return fail(SNAPGPU_EINVAL, "out of memory");
-    memcpy(buf, yaml.data(), yaml.size());
-    buf[yaml.size()] = 0;
+    memcpy(buf, em.out.data(), em.out.size() + 1);
     *out = buf;
-    *out_len = yaml.size();
+    *out_len = em.out.size();
     return 0;
 }
 
 int snapgpu_write_hashes(const char *build_dir, const char *data_tar) {
     if (!build_dir || !data_tar) return fail(SNAPGPU_EINVAL, "null argument");
     const std::string dir = clean_dir(build_dir);
-    std::string yaml;
-    int rc = build_hashes_yaml(dir, data_tar, &yaml);
+    const std::string tar = data_tar;
+    TreeDoc doc;
+    int rc = build_tree_doc(dir, &tar, true, &doc);
     if (rc) return rc;
-    return write_file_0644(dir + "/DEBIAN/hashes.yaml", yaml);
+    rc = write_file_0644(dir + "/DEBIAN/hashes.yaml", doc.buf, doc.len);
+    free(doc.buf);
+    return rc;
 }
 
 int snapgpu_files_are_equal(const char *a, const char *b) {

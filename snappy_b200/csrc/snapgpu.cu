@@ -8,12 +8,14 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <memory>
 #include <mutex>
+#include <shared_mutex>
 #include <thread>
 #include <time.h>
 
@@ -75,6 +77,7 @@ std::string hex_lower(const uint8_t *p, size_t n) {
 // ------------------------------------------------------------------------------------------
 
 constexpr int kPlanSlots = 4;
+constexpr int kStageBufs = 3;
 constexpr size_t kCounterBytes = 64 + 8 * (2 + 4 * 256);   // unit counter | balance[2 + sub-partitions] (up to 256 SMs)
 constexpr int kFeeders = 8;                     // at most this many host threads move pageable memory into pinned bounce buffers
 constexpr size_t kBounceBytes = 4u << 20;
@@ -101,7 +104,11 @@ struct TimedLaunch {
     bool recorded = false;
 };
 
-struct Device {
+// One pipeline on one GPU: streams, plan slots, staging and result buffers, timing ring.  A device
+// has kPipes of them so that concurrent callers (goroutines through cgo, the archive's chain
+// beside the tree's batches) overlap one's copies with another's kernels instead of queueing
+// behind a per-device lock.  Everything in a Pipe is used under its own mutex only.
+struct Pipe {
     int ordinal = -1;
     int sm_count = 0;
     std::mutex mu;
@@ -109,12 +116,14 @@ struct Device {
     PlanSlot slots[kPlanSlots];
     int next_slot = 0;
     // host-buffer pipeline (allocated on first use)
-    uint8_t *d_stage[2] = {nullptr, nullptr};
+    uint8_t *d_stage[kStageBufs] = {};   // the batch calls use two, a batch session all of them
     size_t stage_cap = 0;
-    uint8_t *d_out[2] = {nullptr, nullptr};
-    uint8_t *h_out[2] = {nullptr, nullptr};
+    int stage_n = 0;          // buffers allocated at stage_cap
+    uint8_t *d_out[kStageBufs] = {};
+    uint8_t *h_out[kStageBufs] = {};
     size_t out_cap = 0;       // bytes
-    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    int out_n = 0;
+    cudaEvent_t ev_copied[kStageBufs] = {}, ev_done[kStageBufs] = {};
     // bounce buffers for callers whose host buffer is ordinary pageable memory (allocated on first use)
     uint8_t *bounce[kFeeders][2] = {};
     cudaEvent_t bounce_free[kFeeders][2] = {};
@@ -126,6 +135,59 @@ struct Device {
     int sha_ti = 0, cmp_ti = 0;
     double sha_ms_sum = 0, cmp_ms_sum = 0, sha_ms_last = 0, cmp_ms_last = 0;
     uint64_t sha_ms_n = 0, cmp_ms_n = 0;
+};
+
+constexpr int kPipes = 3;
+
+struct Device {
+    int ordinal = -1;
+    int sm_count = 0;
+    std::unique_ptr<Pipe> pipes[kPipes];
+    std::mutex lease_mu;                  // guards busy[] and sessions
+    std::condition_variable lease_cv;
+    bool busy[kPipes] = {};
+    int sessions = 0;
+};
+
+// A caller's hold on one pipe of a device: the lowest-numbered free one (a lone caller always
+// gets pipe 0 and its warm buffers); when all are taken it waits for whichever is released
+// first.  A batch session keeps its pipe for a long time and its owner makes short calls of its
+// own meanwhile (the archive's chain), so sessions may hold at most kPipes - 1 pipes of a
+// device: one is always left to the calls that come and go.
+struct PipeLease {
+    Device &dev;
+    Pipe *pipe = nullptr;
+    int index = -1;
+    const bool session;
+    explicit PipeLease(Device &d, bool for_session = false) : dev(d), session(for_session) {
+        {
+            std::unique_lock<std::mutex> lk(dev.lease_mu);
+            dev.lease_cv.wait(lk, [&] {
+                if (session && dev.sessions >= kPipes - 1) return false;
+                for (int i = 0; i < kPipes; i++)
+                    if (!dev.busy[i]) {
+                        index = i;
+                        return true;
+                    }
+                return false;
+            });
+            dev.busy[index] = true;
+            if (session) dev.sessions++;
+        }
+        pipe = dev.pipes[index].get();
+        pipe->mu.lock();                  // contended only by the statistics readers
+    }
+    ~PipeLease() {
+        pipe->mu.unlock();
+        {
+            std::lock_guard<std::mutex> lk(dev.lease_mu);
+            dev.busy[index] = false;
+            if (session) dev.sessions--;
+        }
+        dev.lease_cv.notify_all();
+    }
+    PipeLease(const PipeLease &) = delete;
+    PipeLease &operator=(const PipeLease &) = delete;
 };
 
 struct Options {
@@ -140,8 +202,13 @@ struct Options {
     std::atomic<long long> long_kernel{2};      // 0 off, 1 one lane per file, 2 a lane pair per file
 };
 
+// devs is written only by snapgpu_init / snapgpu_shutdown, under mu AND devs_mu held exclusively;
+// every entry point that touches a device holds devs_mu shared for the duration of its call, so
+// a first call racing with snapgpu_init sees either no devices or all of them, and a re-init or
+// shutdown waits for the calls in flight instead of destroying pipes under them.
 struct Runtime {
     std::mutex mu;
+    std::shared_mutex devs_mu;
     std::vector<std::unique_ptr<Device>> devs;
     Options opt;
     std::atomic<uint64_t> kernel_launches{0}, sha_launches{0}, sha_long_launches{0}, cmp_launches{0}, h2d_bytes{0},
@@ -153,10 +220,15 @@ static Runtime &rt() {
     return r;
 }
 
-bool runtime_ready() { return !rt().devs.empty(); }
+typedef std::shared_lock<std::shared_mutex> DevsInUse;
+
+bool runtime_ready() {
+    DevsInUse use(rt().devs_mu);
+    return !rt().devs.empty();
+}
 size_t staging_bytes() { return (size_t)rt().opt.staging_bytes.load(); }
 
-static void destroy_device(Device &D) {
+static void destroy_pipe(Pipe &D) {
     if (D.ordinal < 0) return;
     cudaSetDevice(D.ordinal);
     cudaDeviceSynchronize();
@@ -169,7 +241,7 @@ static void destroy_device(Device &D) {
         if (s.fork) cudaEventDestroy(s.fork);
         if (s.join) cudaEventDestroy(s.join);
     }
-    for (int b = 0; b < 2; b++) {
+    for (int b = 0; b < kStageBufs; b++) {
         if (D.d_stage[b]) cudaFree(D.d_stage[b]);
         if (D.d_out[b]) cudaFree(D.d_out[b]);
         if (D.h_out[b]) cudaFreeHost(D.h_out[b]);
@@ -197,22 +269,13 @@ static void destroy_device(Device &D) {
     D.ordinal = -1;
 }
 
-static int init_device(Device &D, int ordinal) {
+static int init_pipe(Pipe &D, int ordinal, int sm_count) {
     D.ordinal = ordinal;
+    D.sm_count = sm_count;
     SG_CUDA(cudaSetDevice(ordinal));
-    cudaDeviceProp prop;
-    SG_CUDA(cudaGetDeviceProperties(&prop, ordinal));
-    D.sm_count = prop.multiProcessorCount;
-    if (prop.major < 10)
-        return fail(SNAPGPU_ECUDA, "device %d is sm_%d%d; libsnapgpu is built for sm_100a only", ordinal,
-                    prop.major, prop.minor);
     SG_CUDA(cudaStreamCreateWithFlags(&D.copy_stream, cudaStreamNonBlocking));
     SG_CUDA(cudaStreamCreateWithFlags(&D.compute_stream, cudaStreamNonBlocking));
     SG_CUDA(cudaStreamCreateWithFlags(&D.long_stream, cudaStreamNonBlocking));
-    SG_CUDA(cudaFuncSetAttribute(sha512_long_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytes));
-    SG_CUDA(cudaFuncSetAttribute(sha512_long_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytes));
-    SG_CUDA(cudaFuncSetAttribute(sha512_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes));
-    SG_CUDA(cudaFuncSetAttribute(sha512_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes));
     for (auto &s : D.slots) {
         SG_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         SG_CUDA(cudaEventCreate(&s.uploaded));
@@ -220,12 +283,42 @@ static int init_device(Device &D, int ordinal) {
         SG_CUDA(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
         SG_CUDA(cudaMalloc(&s.d_counter, kCounterBytes));
     }
-    for (int b = 0; b < 2; b++) {
+    for (int b = 0; b < kStageBufs; b++) {
         SG_CUDA(cudaEventCreateWithFlags(&D.ev_copied[b], cudaEventDisableTiming));
         SG_CUDA(cudaEventCreateWithFlags(&D.ev_done[b], cudaEventDisableTiming));
     }
     for (auto &t : D.sha_t) { SG_CUDA(cudaEventCreate(&t.beg)); SG_CUDA(cudaEventCreate(&t.end)); }
     for (auto &t : D.cmp_t) { SG_CUDA(cudaEventCreate(&t.beg)); SG_CUDA(cudaEventCreate(&t.end)); }
+    return 0;
+}
+
+static void destroy_device(Device &dev) {
+    for (auto &p : dev.pipes)
+        if (p) {
+            std::lock_guard<std::mutex> lock(p->mu);
+            destroy_pipe(*p);
+        }
+    dev.ordinal = -1;
+}
+
+static int init_device(Device &dev, int ordinal) {
+    dev.ordinal = ordinal;
+    SG_CUDA(cudaSetDevice(ordinal));
+    cudaDeviceProp prop;
+    SG_CUDA(cudaGetDeviceProperties(&prop, ordinal));
+    dev.sm_count = prop.multiProcessorCount;
+    if (prop.major < 10)
+        return fail(SNAPGPU_ECUDA, "device %d is sm_%d%d; libsnapgpu is built for sm_100a only", ordinal,
+                    prop.major, prop.minor);
+    SG_CUDA(cudaFuncSetAttribute(sha512_long_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytes));
+    SG_CUDA(cudaFuncSetAttribute(sha512_long_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytes));
+    SG_CUDA(cudaFuncSetAttribute(sha512_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes));
+    SG_CUDA(cudaFuncSetAttribute(sha512_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes));
+    for (auto &p : dev.pipes) {
+        p.reset(new Pipe());
+        int rc = init_pipe(*p, ordinal, dev.sm_count);
+        if (rc) return rc;
+    }
     return 0;
 }
 
@@ -245,7 +338,7 @@ int ensure_init() {
 // Reserve a plan slot of at least `bytes`: waits for the launch that used it last.  When a
 // slot has to grow, all of them grow together, so the cost of pinning memory is paid in the
 // first call of a given size and not again three launches later.
-static int acquire_slot(Device &D, size_t bytes, PlanSlot **out) {
+static int acquire_slot(Pipe &D, size_t bytes, PlanSlot **out) {
     PlanSlot &s = D.slots[D.next_slot];
     D.next_slot = (D.next_slot + 1) % kPlanSlots;
     if (s.in_flight) {
@@ -437,7 +530,7 @@ static size_t plan_bytes(size_t n, size_t nbuckets) {
     return (n + kLongMaxFiles) * sizeof(SegDesc) + n * sizeof(u32) + nbuckets * sizeof(u32);
 }
 
-static int enqueue_length_binning(Device &D, cudaStream_t stream, const DevicePlan &p, size_t n, uint64_t max_blocks) {
+static int enqueue_length_binning(Pipe &D, cudaStream_t stream, const DevicePlan &p, size_t n, uint64_t max_blocks) {
     const u32 top = (u32)std::min<uint64_t>(max_blocks, kPlanTopMax);
     const u32 nbuckets = top + 1;
     SG_CUDA(cudaMemsetAsync(p.hist, 0, nbuckets * sizeof(u32), stream));
@@ -454,7 +547,7 @@ static int enqueue_length_binning(Device &D, cudaStream_t stream, const DevicePl
 // Caller holds D.mu.  The plan goes up on the copy stream so that it overlaps whatever the
 // caller's stream is still running.
 template <typename Get>
-static int launch_sha512(Device &D, cudaStream_t stream, const uint8_t *d_data, Get get, size_t n,
+static int launch_sha512(Pipe &D, cudaStream_t stream, const uint8_t *d_data, Get get, size_t n,
                          uint8_t *d_digests) {
     if (n == 0) return 0;
     if (n > 0xfffffff0ull) return fail(SNAPGPU_EINVAL, "too many files in one launch (%zu)", n);
@@ -607,7 +700,7 @@ struct CmpItem {
     uint64_t off, len;
 };
 
-static int launch_cmp(Device &D, cudaStream_t stream, const uint8_t *d_a, const uint8_t *d_b, const CmpItem *items,
+static int launch_cmp(Pipe &D, cudaStream_t stream, const uint8_t *d_a, const uint8_t *d_b, const CmpItem *items,
                       size_t n, uint8_t *d_equal) {
     if (n == 0) return 0;
     if (n > 0xfffffff0ull) return fail(SNAPGPU_EINVAL, "too many pairs in one launch (%zu)", n);
@@ -677,29 +770,31 @@ static int launch_cmp(Device &D, cudaStream_t stream, const uint8_t *d_a, const 
 // host-buffer pipeline: pack spans -> H2D -> kernel -> D2H, double buffered
 // ------------------------------------------------------------------------------------------
 
-static int ensure_staging(Device &D, size_t stage_bytes, size_t out_bytes) {
+// At least `nbuf` staging buffers of stage_bytes and result buffers of out_bytes.  Growing frees
+// the old buffers: the caller makes sure nothing in flight still uses them.
+static int ensure_staging(Pipe &D, size_t stage_bytes, size_t out_bytes, int nbuf = 2) {
     if (D.stage_cap < stage_bytes) {
-        for (int b = 0; b < 2; b++) {
+        for (int b = 0; b < kStageBufs; b++) {
             if (D.d_stage[b]) cudaFree(D.d_stage[b]);
             D.d_stage[b] = nullptr;
         }
         D.stage_cap = 0;
-        for (int b = 0; b < 2; b++) SG_CUDA(cudaMalloc(&D.d_stage[b], stage_bytes + kStageSlack));
+        D.stage_n = 0;
         D.stage_cap = stage_bytes;
     }
+    for (; D.stage_n < nbuf; D.stage_n++) SG_CUDA(cudaMalloc(&D.d_stage[D.stage_n], D.stage_cap + kStageSlack));
     if (D.out_cap < out_bytes) {
-        for (int b = 0; b < 2; b++) {
+        for (int b = 0; b < kStageBufs; b++) {
             if (D.d_out[b]) cudaFree(D.d_out[b]);
             if (D.h_out[b]) cudaFreeHost(D.h_out[b]);
             D.d_out[b] = D.h_out[b] = nullptr;
         }
-        D.out_cap = 0;
-        size_t want = std::max<size_t>(out_bytes + out_bytes / 2, 1u << 16);
-        for (int b = 0; b < 2; b++) {
-            SG_CUDA(cudaMalloc(&D.d_out[b], want));
-            SG_CUDA(cudaHostAlloc(&D.h_out[b], want, cudaHostAllocPortable));
-        }
-        D.out_cap = want;
+        D.out_n = 0;
+        D.out_cap = std::max<size_t>(out_bytes + out_bytes / 2, 1u << 16);
+    }
+    for (; D.out_n < nbuf; D.out_n++) {
+        SG_CUDA(cudaMalloc(&D.d_out[D.out_n], D.out_cap));
+        SG_CUDA(cudaHostAlloc(&D.h_out[D.out_n], D.out_cap, cudaHostAllocPortable));
     }
     return 0;
 }
@@ -719,7 +814,7 @@ static bool host_pointer_is_pinned(const void *p) {
 // cudaMemcpyAsync stage through the driver's single bounce buffer at ~10 GB/s; instead kFeeders
 // host threads copy 4 MiB pieces into pinned bounce buffers of their own (two each, so the memcpy
 // of a piece overlaps the DMA of the previous one) and enqueue the DMAs on their own streams.
-static int h2d_span(Device &D, uint8_t *dst, const uint8_t *src, size_t bytes, bool pinned) {
+static int h2d_span(Pipe &D, uint8_t *dst, const uint8_t *src, size_t bytes, bool pinned) {
     if (bytes == 0) return 0;
     if (pinned || bytes < kBounceBytes) {
         SG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, D.copy_stream));
@@ -915,13 +1010,31 @@ static size_t ramp_cap(size_t chunk_index, size_t cap_max) {
 }
 
 // Runs one device's shard of a host-buffer SHA-512 batch.  digests: caller's n*64 array.
-static int sha512_shard(Device &D, const uint8_t *data, const ItemList &shard, uint8_t *digests) {
+// The staging buffers a shard needs: the configured size, or less when the whole shard is smaller
+// (a concurrent caller hashing a few MiB on a second pipe should not allocate two 1 GiB buffers).
+static size_t staging_for(const ItemList &shard, size_t cap_max) {
+    if (shard.size() > (1u << 16)) return cap_max;
+    uint64_t lo = ~0ull, hi = 0, sum = 0;
+    for (size_t k = 0; k < shard.size(); k++) {
+        const WorkItem w = shard.at(k);
+        lo = std::min(lo, w.off);
+        hi = std::max(hi, w.off + w.len);
+        sum += w.len + 32;
+    }
+    const uint64_t need = std::min<uint64_t>(hi - lo, sum) + 4096;     // dense spans never exceed either
+    size_t cap = (size_t)16 << 20;
+    while (cap < need && cap < cap_max) cap <<= 1;
+    return std::min(cap, cap_max);
+}
+
+static int sha512_shard(Device &dev, const uint8_t *data, const ItemList &shard, uint8_t *digests) {
     if (shard.empty()) return 0;
-    std::lock_guard<std::mutex> lock(D.mu);
+    PipeLease lease(dev);
+    Pipe &D = *lease.pipe;
     SG_CUDA(cudaSetDevice(D.ordinal));
     auto &R = rt();
     const double t_begin = now_ms();
-    const size_t cap = staging_bytes();
+    const size_t cap = std::min(staging_bytes(), std::max(D.stage_cap, staging_for(shard, staging_bytes())));
     ChunkPlan plan;
     ChunkStream stream(shard, true, plan);
     const std::vector<Chunk> &chunks = plan.chunks;      // grows as the stream is consumed
@@ -988,13 +1101,14 @@ static int sha512_shard(Device &D, const uint8_t *data, const ItemList &shard, u
     return 0;
 }
 
-static int cmp_shard(Device &D, const uint8_t *a, const uint8_t *b_host, const ItemList &shard,
+static int cmp_shard(Device &dev, const uint8_t *a, const uint8_t *b_host, const ItemList &shard,
                      uint8_t *equal) {
     if (shard.empty()) return 0;
-    std::lock_guard<std::mutex> lock(D.mu);
+    PipeLease lease(dev);
+    Pipe &D = *lease.pipe;
     SG_CUDA(cudaSetDevice(D.ordinal));
     auto &R = rt();
-    const size_t cap = staging_bytes();
+    const size_t cap = std::min(staging_bytes(), std::max(D.stage_cap, 2 * staging_for(shard, staging_bytes())));
     const size_t half = (cap / 2) & ~(size_t)255;
     ChunkPlan plan;
     ChunkStream stream(shard, false, plan);
@@ -1044,6 +1158,190 @@ static int cmp_shard(Device &D, const uint8_t *a, const uint8_t *b_host, const I
     }
     if ((rc = gather(0))) return rc;
     if ((rc = gather(1))) return rc;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// batch session (runtime.hpp): the same pipeline as sha512_shard, fed batch by batch
+// ------------------------------------------------------------------------------------------
+
+}  // namespace snapgpu
+
+class snapgpu::BatchSession {
+public:
+    struct Slot {
+        bool busy = false, copy_reported = false;
+        uint64_t ticket = 0;
+        std::vector<uint8_t *> dst;
+    };
+    struct Lane {
+        Device *dev = nullptr;
+        std::unique_ptr<PipeLease> lease;
+        Slot slot[kStageBufs];
+        int busy() const {
+            int n = 0;
+            for (const Slot &x : slot) n += x.busy;
+            return n;
+        }
+    };
+    DevsInUse use;
+    std::vector<Lane> lanes;
+    size_t max_batch_bytes = 0;
+    uint64_t next_ticket = 1;
+    size_t in_flight = 0;
+    std::vector<uint64_t> span_base;
+
+    BatchSession() : use(rt().devs_mu) {}
+};
+
+namespace snapgpu {
+
+// Finish what can be finished on one slot.  wait: block for it.
+static int session_retire(BatchSession *s, BatchSession::Lane &L, int b, std::vector<uint64_t> *copied, bool wait) {
+    BatchSession::Slot &S = L.slot[b];
+    if (!S.busy) return 0;
+    Pipe &P = *L.lease->pipe;
+    if (!S.copy_reported) {
+        cudaError_t e = wait ? cudaEventSynchronize(P.ev_copied[b]) : cudaEventQuery(P.ev_copied[b]);
+        if (e == cudaErrorNotReady) return 0;
+        if (e != cudaSuccess) return fail(SNAPGPU_ECUDA, "host-to-device copy failed: %s", cudaGetErrorString(e));
+        S.copy_reported = true;
+        if (copied) copied->push_back(S.ticket);
+    }
+    cudaError_t e = wait ? cudaEventSynchronize(P.ev_done[b]) : cudaEventQuery(P.ev_done[b]);
+    if (e == cudaErrorNotReady) return 0;
+    if (e != cudaSuccess) return fail(SNAPGPU_ECUDA, "SHA-512 batch failed: %s", cudaGetErrorString(e));
+    const uint8_t *src = P.h_out[b];
+    for (size_t i = 0; i < S.dst.size(); i++) memcpy(S.dst[i], src + 64 * i, 64);
+    S.busy = false;
+    s->in_flight--;
+    return 0;
+}
+
+int session_open(BatchSession **out, size_t max_batch_bytes) {
+    *out = nullptr;
+    std::unique_ptr<BatchSession> s(new BatchSession());
+    auto &R = rt();
+    if (R.devs.empty()) return fail(SNAPGPU_ENOINIT, "snapgpu_init has not been called (or failed)");
+    s->max_batch_bytes = std::min(std::max<size_t>(max_batch_bytes, 1u << 20), staging_bytes());
+    s->lanes.resize(R.devs.size());
+    for (size_t d = 0; d < R.devs.size(); d++) {
+        s->lanes[d].dev = R.devs[d].get();
+        s->lanes[d].lease.reset(new PipeLease(*R.devs[d], true));
+    }
+    *out = s.release();
+    return 0;
+}
+
+void session_close(BatchSession *s) {
+    if (!s) return;
+    for (auto &L : s->lanes) {
+        cudaSetDevice(L.dev->ordinal);
+        for (int b = 0; b < kStageBufs; b++)
+            if (L.slot[b].busy) {                    // abandoned after an error: let the GPU finish with the buffers
+                cudaEventSynchronize(L.lease->pipe->ev_done[b]);
+                L.slot[b].busy = false;
+            }
+    }
+    delete s;
+}
+
+size_t session_in_flight(const BatchSession *s) { return s->in_flight; }
+size_t session_capacity(const BatchSession *s) { return kStageBufs * s->lanes.size(); }
+
+int session_poll(BatchSession *s, std::vector<uint64_t> *copied, bool wait_all) {
+    for (auto &L : s->lanes) {
+        if (!L.busy()) continue;
+        SG_CUDA(cudaSetDevice(L.dev->ordinal));
+        // a lane's batches in the order they were enqueued (tickets grow), so that "copied" is
+        // reported in order
+        int order[kStageBufs];
+        for (int k = 0; k < kStageBufs; k++) order[k] = k;
+        std::sort(order, order + kStageBufs, [&](int x, int y) { return L.slot[x].ticket < L.slot[y].ticket; });
+        for (int k = 0; k < kStageBufs; k++) {
+            int rc = session_retire(s, L, order[k], copied, wait_all);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+int session_submit(BatchSession *s, const HostSpan *spans, size_t nspans, const SpanSeg *segs,
+                   uint8_t *const *digest_dst, size_t nsegs, uint64_t *ticket, std::vector<uint64_t> *copied) {
+    if (nsegs == 0) return fail(SNAPGPU_EINVAL, "empty batch");
+    auto &R = rt();
+    // a lane with a free slot, the one with the fewest batches in flight; none: wait for the oldest batch
+    BatchSession::Lane *lane = nullptr;
+    int b = -1;
+    for (int pass = 0; pass < 2 && !lane; pass++) {
+        int best_busy = kStageBufs;
+        for (auto &L : s->lanes) {
+            const int busy = L.busy();
+            if (busy < best_busy) {
+                best_busy = busy;
+                lane = &L;
+            }
+        }
+        if (lane) break;
+        BatchSession::Lane *oldest = nullptr;
+        int ob = 0;
+        for (auto &L : s->lanes)
+            for (int k = 0; k < kStageBufs; k++)
+                if (L.slot[k].busy && (!oldest || L.slot[k].ticket < oldest->slot[ob].ticket)) {
+                    oldest = &L;
+                    ob = k;
+                }
+        SG_CUDA(cudaSetDevice(oldest->dev->ordinal));
+        int rc = session_retire(s, *oldest, ob, copied, true);
+        if (rc) return rc;
+    }
+    Pipe &P = *lane->lease->pipe;
+    SG_CUDA(cudaSetDevice(P.ordinal));
+    for (b = 0; lane->slot[b].busy; b++) {}                  // a free staging buffer of the lane
+
+    s->span_base.resize(nspans);
+    size_t total = 0;
+    for (size_t k = 0; k < nspans; k++) {
+        s->span_base[k] = total;
+        total += (spans[k].bytes + 255) & ~(size_t)255;
+    }
+    if (total > s->max_batch_bytes) return fail(SNAPGPU_EINVAL, "batch of %zu bytes exceeds the session's %zu", total, s->max_batch_bytes);
+    if (P.stage_cap < total || P.out_cap < nsegs * 64 || P.stage_n < kStageBufs || P.out_n < kStageBufs) {
+        // growing frees the old buffers: nothing of this lane may still be using them
+        if (P.stage_cap < total || P.out_cap < nsegs * 64) {
+            for (int k = 0; k < kStageBufs; k++) {
+                int rc = session_retire(s, *lane, k, copied, true);
+                if (rc) return rc;
+            }
+            b = 0;
+        }
+        size_t want = (size_t)16 << 20;
+        while (want < total) want <<= 1;
+        int rc = ensure_staging(P, std::max(P.stage_cap, std::min(want, std::max(s->max_batch_bytes, total))),
+                                std::max(P.out_cap, nsegs * 64), kStageBufs);
+        if (rc) return rc;
+    }
+    for (size_t k = 0; k < nspans; k++)
+        if (spans[k].bytes)
+            SG_CUDA(cudaMemcpyAsync(P.d_stage[b] + s->span_base[k], spans[k].ptr, spans[k].bytes, cudaMemcpyHostToDevice,
+                                    P.copy_stream));
+    R.h2d_bytes += total;
+    SG_CUDA(cudaEventRecord(P.ev_copied[b], P.copy_stream));
+    SG_CUDA(cudaStreamWaitEvent(P.compute_stream, P.ev_copied[b], 0));
+    const uint64_t *base = s->span_base.data();
+    auto get = [segs, base](size_t i) { return SegDesc{base[segs[i].span] + segs[i].off, segs[i].len, 0, (u32)i, 0}; };
+    int rc = launch_sha512(P, P.compute_stream, P.d_stage[b], get, nsegs, P.d_out[b]);
+    if (rc) return rc;
+    SG_CUDA(cudaMemcpyAsync(P.h_out[b], P.d_out[b], nsegs * 64, cudaMemcpyDeviceToHost, P.compute_stream));
+    R.d2h_bytes += nsegs * 64;
+    SG_CUDA(cudaEventRecord(P.ev_done[b], P.compute_stream));
+    BatchSession::Slot &S = lane->slot[b];
+    S.busy = true;
+    S.copy_reported = false;
+    S.ticket = s->next_ticket++;
+    S.dst.assign(digest_dst, digest_dst + nsegs);
+    s->in_flight++;
+    if (ticket) *ticket = S.ticket;
     return 0;
 }
 
@@ -1148,7 +1446,8 @@ static int run_on_ranges(const std::vector<size_t> &cut, const std::function<int
 static int sha512_host_items(const uint8_t *data, const std::vector<WorkItem> &all, uint8_t *digests);
 
 int sha512_host_segments(const uint8_t *data, const HostSeg *segs, size_t n, uint8_t *digests) {
-    if (!runtime_ready()) return fail(SNAPGPU_ENOINIT, "snapgpu_init has not been called (or failed)");
+    DevsInUse use(rt().devs_mu);
+    if (rt().devs.empty()) return fail(SNAPGPU_ENOINIT, "snapgpu_init has not been called (or failed)");
     if (n == 0) return 0;
     if (!segs || !digests || (!data && n)) return fail(SNAPGPU_EINVAL, "null argument");
     std::vector<WorkItem> all(n);
@@ -1206,9 +1505,16 @@ int snapgpu_init(const int *devices, int ndev) {
     }
     for (int o : want)
         if (o < 0 || o >= visible) return fail(SNAPGPU_EINVAL, "device ordinal %d not visible (%d devices)", o, visible);
-    bool same = R.devs.size() == want.size();
-    for (size_t i = 0; same && i < want.size(); i++) same = R.devs[i]->ordinal == want[i];
-    if (same) return 0;
+    {
+        DevsInUse use(R.devs_mu);
+        bool same = R.devs.size() == want.size();
+        for (size_t i = 0; same && i < want.size(); i++) same = R.devs[i]->ordinal == want[i];
+        if (same) return 0;
+    }
+    // the new device list is built aside and published in one step; the exclusive lock waits for
+    // the calls in flight on the old list before it is torn down
+    std::vector<std::unique_ptr<Device>> fresh;
+    std::unique_lock<std::shared_mutex> excl(R.devs_mu);
     for (auto &d : R.devs) destroy_device(*d);
     R.devs.clear();
     for (int o : want) {
@@ -1216,27 +1522,32 @@ int snapgpu_init(const int *devices, int ndev) {
         int rc = init_device(*d, o);
         if (rc) {
             destroy_device(*d);
-            for (auto &x : R.devs) destroy_device(*x);
-            R.devs.clear();
+            for (auto &x : fresh) destroy_device(*x);
             return rc;
         }
-        R.devs.push_back(std::move(d));
+        fresh.push_back(std::move(d));
     }
+    R.devs = std::move(fresh);
     return 0;
 }
 
 void snapgpu_shutdown(void) {
     auto &R = rt();
     std::lock_guard<std::mutex> lock(R.mu);
+    std::unique_lock<std::shared_mutex> excl(R.devs_mu);
     for (auto &d : R.devs) destroy_device(*d);
     R.devs.clear();
 }
 
-int snapgpu_num_devices(void) { return (int)rt().devs.size(); }
+int snapgpu_num_devices(void) {
+    DevsInUse use(rt().devs_mu);
+    return (int)rt().devs.size();
+}
 
 #ifdef SNAPGPU_TRACE_WARPS
 // experimental build only: the per-warp records of the last SHA-512 launch on device `dev`
 int snapgpu_test_warp_trace(int dev, unsigned long long *out, size_t nwarps) {
+    DevsInUse use(rt().devs_mu);
     Device *D = nullptr;
     int rc = get_device(dev, &D);
     if (rc) return rc;
@@ -1281,7 +1592,8 @@ int snapgpu_set_option(const char *key, long long value) {
 
 void *snapgpu_alloc_pinned(size_t bytes) {
     void *p = nullptr;
-    if (!runtime_ready()) {
+    DevsInUse use(rt().devs_mu);
+    if (rt().devs.empty()) {
         set_error("snapgpu_init has not been called (or failed)");
         return nullptr;
     }
@@ -1302,9 +1614,11 @@ void snapgpu_free(void *p) { free(p); }
 
 int snapgpu_sha512_batch(const uint8_t *data, const uint64_t *offsets, const uint64_t *lengths, size_t nfiles,
                          uint8_t *digests) {
-    if (nfiles == 0) return runtime_ready() ? 0 : fail(SNAPGPU_ENOINIT, "snapgpu_init has not been called (or failed)");
+    DevsInUse use(rt().devs_mu);
+    const bool ready = !rt().devs.empty();
+    if (nfiles == 0) return ready ? 0 : fail(SNAPGPU_ENOINIT, "snapgpu_init has not been called (or failed)");
     if (!data || !offsets || !lengths || !digests) return fail(SNAPGPU_EINVAL, "null argument");
-    if (!runtime_ready()) return fail(SNAPGPU_ENOINIT, "snapgpu_init has not been called (or failed)");
+    if (!ready) return fail(SNAPGPU_ENOINIT, "snapgpu_init has not been called (or failed)");
     if (rt().devs.size() == 1)       // one device: the caller's arrays are the item list
         return sha512_shard(*rt().devs[0], data, ItemList(offsets, lengths, nfiles), digests);
     std::vector<size_t> cut;
@@ -1332,7 +1646,8 @@ int snapgpu_sha512_stream(uint8_t state[64], int first, const uint8_t *data, uin
 
 int snapgpu_cmp_batch(const uint8_t *a, const uint8_t *b, const uint64_t *offsets, const uint64_t *lengths,
                       size_t npairs, uint8_t *equal) {
-    if (!runtime_ready()) return fail(SNAPGPU_ENOINIT, "snapgpu_init has not been called (or failed)");
+    DevsInUse use(rt().devs_mu);
+    if (rt().devs.empty()) return fail(SNAPGPU_ENOINIT, "snapgpu_init has not been called (or failed)");
     if (npairs == 0) return 0;
     if (!a || !b || !offsets || !lengths || !equal) return fail(SNAPGPU_EINVAL, "null argument");
     memset(equal, 1, npairs);
@@ -1355,12 +1670,14 @@ int snapgpu_cmp_batch(const uint8_t *a, const uint8_t *b, const uint64_t *offset
 
 int snapgpu_sha512_batch_device(int dev, const void *d_data, const uint64_t *offsets, const uint64_t *lengths,
                                 size_t nfiles, void *d_digests, void *stream) {
-    Device *D = nullptr;
-    int rc = get_device(dev, &D);
+    DevsInUse use(rt().devs_mu);
+    Device *dv = nullptr;
+    int rc = get_device(dev, &dv);
     if (rc) return rc;
     if (nfiles == 0) return 0;
     if (!d_data || !offsets || !lengths || !d_digests) return fail(SNAPGPU_EINVAL, "null argument");
-    std::lock_guard<std::mutex> lock(D->mu);
+    PipeLease lease(*dv);
+    Pipe *D = lease.pipe;
     SG_CUDA(cudaSetDevice(D->ordinal));
     if (nfiles > 0xfffffff0ull) return fail(SNAPGPU_EINVAL, "too many files in one launch (%zu)", nfiles);
     auto get = [offsets, lengths](size_t i) { return SegDesc{offsets[i], lengths[i], 0, (u32)i, 0}; };
@@ -1370,12 +1687,14 @@ int snapgpu_sha512_batch_device(int dev, const void *d_data, const uint64_t *off
 
 int snapgpu_cmp_batch_device(int dev, const void *d_a, const void *d_b, const uint64_t *offsets,
                              const uint64_t *lengths, size_t npairs, void *d_equal, void *stream) {
-    Device *D = nullptr;
-    int rc = get_device(dev, &D);
+    DevsInUse use(rt().devs_mu);
+    Device *dv = nullptr;
+    int rc = get_device(dev, &dv);
     if (rc) return rc;
     if (npairs == 0) return 0;
     if (!d_a || !d_b || !offsets || !lengths || !d_equal) return fail(SNAPGPU_EINVAL, "null argument");
-    std::lock_guard<std::mutex> lock(D->mu);
+    PipeLease lease(*dv);
+    Pipe *D = lease.pipe;
     SG_CUDA(cudaSetDevice(D->ordinal));
     std::vector<CmpItem> items(npairs);
     for (size_t i = 0; i < npairs; i++) items[i] = CmpItem{offsets[i], lengths[i]};
@@ -1385,13 +1704,15 @@ int snapgpu_cmp_batch_device(int dev, const void *d_a, const void *d_b, const ui
 
 int snapgpu_synth_fill_device(int dev, void *d_data, const uint64_t *offsets, const uint64_t *lengths, size_t nfiles,
                               uint64_t first_index, uint64_t seed, void *stream) {
-    Device *D = nullptr;
-    int rc = get_device(dev, &D);
+    DevsInUse use(rt().devs_mu);
+    Device *dv = nullptr;
+    int rc = get_device(dev, &dv);
     if (rc) return rc;
     if (nfiles == 0) return 0;
     if (!d_data || !offsets || !lengths) return fail(SNAPGPU_EINVAL, "null argument");
     if (nfiles > 0xfffffff0ull) return fail(SNAPGPU_EINVAL, "too many files");
-    std::lock_guard<std::mutex> lock(D->mu);
+    PipeLease lease(*dv);
+    Pipe *D = lease.pipe;
     SG_CUDA(cudaSetDevice(D->ordinal));
     PlanSlot *slot;
     if ((rc = acquire_slot(*D, nfiles * sizeof(SynthFile), &slot))) return rc;
@@ -1420,19 +1741,21 @@ int snapgpu_get_stats(snapgpu_stats *out) {
     out->d2h_bytes = R.d2h_bytes;
     double sha_sum = 0, cmp_sum = 0;
     uint64_t sha_n = 0, cmp_n = 0;
-    for (auto &dp : R.devs) {
-        Device &D = *dp;
-        std::lock_guard<std::mutex> lock(D.mu);
-        cudaSetDevice(D.ordinal);
-        harvest_timings(D.sha_t, 8, D.sha_ms_sum, D.sha_ms_n, D.sha_ms_last, true);
-        harvest_timings(D.cmp_t, 8, D.cmp_ms_sum, D.cmp_ms_n, D.cmp_ms_last, true);
-        sha_sum += D.sha_ms_sum;
-        sha_n += D.sha_ms_n;
-        cmp_sum += D.cmp_ms_sum;
-        cmp_n += D.cmp_ms_n;
-        out->last_sha512_kernel_ms = D.sha_ms_last;
-        out->last_cmp_kernel_ms = D.cmp_ms_last;
-    }
+    DevsInUse use(R.devs_mu);
+    for (auto &dp : R.devs)
+        for (auto &pp : dp->pipes) {
+            Pipe &D = *pp;
+            std::lock_guard<std::mutex> lock(D.mu);
+            cudaSetDevice(D.ordinal);
+            harvest_timings(D.sha_t, 8, D.sha_ms_sum, D.sha_ms_n, D.sha_ms_last, true);
+            harvest_timings(D.cmp_t, 8, D.cmp_ms_sum, D.cmp_ms_n, D.cmp_ms_last, true);
+            sha_sum += D.sha_ms_sum;
+            sha_n += D.sha_ms_n;
+            cmp_sum += D.cmp_ms_sum;
+            cmp_n += D.cmp_ms_n;
+            if (D.sha_ms_n) out->last_sha512_kernel_ms = D.sha_ms_last;
+            if (D.cmp_ms_n) out->last_cmp_kernel_ms = D.cmp_ms_last;
+        }
     out->sha512_kernel_ms_sum = sha_sum;
     out->sha512_kernel_timed = sha_n;
     out->cmp_kernel_ms_sum = cmp_sum;
@@ -1448,15 +1771,17 @@ void snapgpu_reset_stats(void) {
     R.cmp_launches = 0;
     R.h2d_bytes = 0;
     R.d2h_bytes = 0;
-    for (auto &dp : R.devs) {
-        Device &D = *dp;
-        std::lock_guard<std::mutex> lock(D.mu);
-        cudaSetDevice(D.ordinal);
-        harvest_timings(D.sha_t, 8, D.sha_ms_sum, D.sha_ms_n, D.sha_ms_last, true);
-        harvest_timings(D.cmp_t, 8, D.cmp_ms_sum, D.cmp_ms_n, D.cmp_ms_last, true);
-        D.sha_ms_sum = D.cmp_ms_sum = 0;
-        D.sha_ms_n = D.cmp_ms_n = 0;
-    }
+    DevsInUse use(R.devs_mu);
+    for (auto &dp : R.devs)
+        for (auto &pp : dp->pipes) {
+            Pipe &D = *pp;
+            std::lock_guard<std::mutex> lock(D.mu);
+            cudaSetDevice(D.ordinal);
+            harvest_timings(D.sha_t, 8, D.sha_ms_sum, D.sha_ms_n, D.sha_ms_last, true);
+            harvest_timings(D.cmp_t, 8, D.cmp_ms_sum, D.cmp_ms_n, D.cmp_ms_last, true);
+            D.sha_ms_sum = D.cmp_ms_sum = 0;
+            D.sha_ms_n = D.cmp_ms_n = 0;
+        }
 }
 
 // ---- test hooks: host logic only, callable without a GPU ---------------------------------
@@ -1465,11 +1790,13 @@ void snapgpu_reset_stats(void) {
 // order[k] = index of the k-th file of the plan.  Needs a GPU (runs the plan kernels on device 0).
 int snapgpu_test_plan_order(const uint64_t *lengths, size_t n, uint32_t *order) {
     if (!lengths || !order) return fail(SNAPGPU_EINVAL, "null argument");
-    Device *D = nullptr;
-    int rc = get_device(0, &D);
+    DevsInUse use(rt().devs_mu);
+    Device *dv = nullptr;
+    int rc = get_device(0, &dv);
     if (rc) return rc;
     if (n == 0) return 0;
-    std::lock_guard<std::mutex> lock(D->mu);
+    PipeLease lease(*dv);
+    Pipe *D = lease.pipe;
     SG_CUDA(cudaSetDevice(D->ordinal));
     PlanSlot *slot;
     if ((rc = acquire_slot(*D, plan_bytes(n, kPlanTopMax + 1), &slot))) return rc;
@@ -1536,8 +1863,9 @@ typedef void (*ProbeKernel)(uint32_t *, int, uint32_t, uint32_t, unsigned long l
 
 int snapgpu_pipe_microbench(int dev, int kind, int warps_per_sm, double *inst_per_clk_per_sm, double *elapsed_ms,
                             double *sm_clock_mhz) {
-    Device *D = nullptr;
-    int rc = get_device(dev, &D);
+    DevsInUse use(rt().devs_mu);
+    Device *dv = nullptr;
+    int rc = get_device(dev, &dv);
     if (rc) return rc;
     static const ProbeKernel table[kProbeCount] = {
         pipe_probe_kernel<0>, pipe_probe_kernel<1>, pipe_probe_kernel<2>, pipe_probe_kernel<3>,
@@ -1546,7 +1874,8 @@ int snapgpu_pipe_microbench(int dev, int kind, int warps_per_sm, double *inst_pe
     };
     if (kind < 0 || kind >= kProbeCount) return fail(SNAPGPU_EINVAL, "unknown probe kind %d", kind);
     if (warps_per_sm < 4 || warps_per_sm > 64 || warps_per_sm % 4) return fail(SNAPGPU_EINVAL, "warps_per_sm must be 4..64, multiple of 4");
-    std::lock_guard<std::mutex> lock(D->mu);
+    PipeLease lease(*dv);
+    Pipe *D = lease.pipe;
     SG_CUDA(cudaSetDevice(D->ordinal));
     const int ctas_per_sm = warps_per_sm / (kProbeThreads / 32);
     const int grid = D->sm_count * ctas_per_sm;
