@@ -221,6 +221,12 @@ void snapgpu_reset_stats(void);
 int snapgpu_pipe_microbench(int dev, int kind, int warps_per_sm, double *inst_per_clk_per_sm,
                             double *elapsed_ms, double *sm_clock_mhz);
 
+/* Raw pinned host-to-device copy rate on every bound device at once (device d copies
+ * bytes_per_dev bytes from host + d * bytes_per_dev, `reps` times, through the same
+ * cudaMemcpyAsync path the pipeline uses): *seconds = the slowest device's time.  The ceiling
+ * the end-to-end figures are stated against. */
+int snapgpu_h2d_probe(const void *host, size_t bytes_per_dev, int reps, double *seconds);
+
 /* ---- test hooks (see tests/) ------------------------------------------------------------ */
 /* host logic only, usable without a GPU */
 int snapgpu_test_yaml_from_digests(const char *build_dir, const uint8_t *digests, size_t ndigests,

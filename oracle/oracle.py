@@ -69,6 +69,8 @@ def lib() -> ctypes.CDLL:
         L.oracle_sha512sum_file.restype = ctypes.c_int
         L.oracle_sha512_batch.argtypes = [u8p, u8p, u8p, ctypes.c_size_t, u8p, ctypes.c_int, ctypes.c_int]
         L.oracle_sha512_batch.restype = ctypes.c_int
+        L.oracle_sha512sum_files.argtypes = [ctypes.c_char_p, u8p, ctypes.c_size_t, u8p, ctypes.c_int, ctypes.c_int]
+        L.oracle_sha512sum_files.restype = ctypes.c_int
         L.oracle_cmp_batch.argtypes = [u8p, u8p, u8p, u8p, ctypes.c_size_t, u8p, ctypes.c_int]
         L.oracle_cmp_batch.restype = ctypes.c_int
         L.oracle_streams_equal.argtypes = [u8p, ctypes.c_size_t, u8p, ctypes.c_size_t]
@@ -118,6 +120,20 @@ def sha512_batch(data: np.ndarray, offsets: np.ndarray, lengths: np.ndarray,
                                        int(nthreads), int(use_openssl))
         if rc != 0:
             raise RuntimeError(f"oracle_sha512_batch failed: {rc}")
+    return out
+
+
+def sha512sum_files(paths, sizes, nthreads: int = 1, use_openssl: bool = False) -> np.ndarray:
+    """helpers.Sha512sum over a list of files -- the loop of writeHashes (snappy/build.go:240) --
+    on ``nthreads`` threads (1 = what the reference does; more = the file list statically sharded,
+    the "best CPU" comparator of SURVEY.md 8d).  Digests (n, 64) uint8; raises OSError."""
+    blob = b"".join(os.fsencode(p) + b"\0" for p in paths)
+    sizes = np.ascontiguousarray(sizes, dtype=np.uint64)
+    out = np.zeros((len(paths), 64), dtype=np.uint8)
+    if len(paths):
+        rc = lib().oracle_sha512sum_files(blob, _ptr(sizes), len(paths), _ptr(out), int(nthreads), int(use_openssl))
+        if rc != 0:
+            raise OSError(-rc, os.strerror(-rc))
     return out
 
 

@@ -437,6 +437,110 @@ int oracle_cmp_batch(const uint8_t *a, const uint8_t *b, const uint64_t *offsets
     return run_batch(j, npairs, nthreads);
 }
 
+/* ------------------------------------------------------------------ */
+/* Sha512sum over a file list: the loop of writeHashes on a real tree  */
+/* ------------------------------------------------------------------ */
+/* snappy/build.go:228-259 calls helpers.Sha512sum for every regular    */
+/* file, one goroutine, one file at a time (nthreads = 1).  nthreads >  */
+/* 1 is the "best CPU" comparator of SURVEY.md 8(d): the file list      */
+/* statically sharded over threads, contiguous shards balanced by       */
+/* bytes, each thread running the same open / 32 KiB read / update /    */
+/* close loop.  `paths` holds n NUL-terminated strings back to back,    */
+/* `sizes` their lengths in bytes (for the balancing only).             */
+
+typedef struct {
+    const char **paths;
+    size_t lo, hi;
+    uint8_t *out;
+    int use_openssl;
+    int err;           /* -errno of the first failure of this shard */
+} files_job;
+
+static int sha512sum_fd_loop(const char *path, uint8_t out[64], int use_openssl)
+{
+    int fd = open(path, O_RDONLY | O_CLOEXEC);
+    if (fd < 0) return -errno;
+    static __thread uint8_t buf[32768];      /* io.Copy's buffer */
+    oracle_sha512_ctx c;
+    uint64_t octx[64];
+    const int ossl = use_openssl && oracle_have_openssl();
+    if (ossl) ossl_init(octx);
+    else oracle_sha512_init(&c);
+    for (;;) {
+        ssize_t r = read(fd, buf, sizeof buf);
+        if (r < 0) {
+            if (errno == EINTR) continue;
+            int e = errno;
+            close(fd);
+            return -e;
+        }
+        if (r == 0) break;
+        if (ossl) ossl_update(octx, buf, (size_t)r);
+        else oracle_sha512_update(&c, buf, (size_t)r);
+    }
+    close(fd);
+    if (ossl) ossl_final(out, octx);
+    else oracle_sha512_final(&c, out);
+    return 0;
+}
+
+static void *files_worker(void *arg)
+{
+    files_job *j = (files_job *)arg;
+    for (size_t i = j->lo; i < j->hi; i++) {
+        int rc = sha512sum_fd_loop(j->paths[i], j->out + 64 * i, j->use_openssl);
+        if (rc && !j->err) j->err = rc;
+    }
+    return NULL;
+}
+
+int oracle_sha512sum_files(const char *paths, const uint64_t *sizes, size_t n, uint8_t *digests,
+                           int nthreads, int use_openssl)
+{
+    if (n == 0) return 0;
+    const char **list = (const char **)calloc(n, sizeof *list);
+    if (!list) return -ENOMEM;
+    const char *p = paths;
+    for (size_t i = 0; i < n; i++) {
+        list[i] = p;
+        p += strlen(p) + 1;
+    }
+    if (nthreads < 1) nthreads = 1;
+    if ((size_t)nthreads > n) nthreads = (int)n;
+    uint64_t total = 0;
+    for (size_t i = 0; i < n; i++) total += sizes[i] + 4096;     /* per-file cost: open/close */
+    pthread_t *th = (pthread_t *)calloc((size_t)nthreads, sizeof *th);
+    files_job *jobs = (files_job *)calloc((size_t)nthreads, sizeof *jobs);
+    if (!th || !jobs) {
+        free(list);
+        free(th);
+        free(jobs);
+        return -ENOMEM;
+    }
+    size_t pos = 0;
+    uint64_t acc = 0;
+    for (int t = 0; t < nthreads; t++) {
+        jobs[t].paths = list;
+        jobs[t].out = digests;
+        jobs[t].use_openssl = use_openssl;
+        jobs[t].lo = pos;
+        uint64_t goal = total / (uint64_t)nthreads * (uint64_t)(t + 1);
+        while (pos < n && (t == nthreads - 1 || acc < goal)) acc += sizes[pos++] + 4096;
+        jobs[t].hi = pos;
+        if (nthreads == 1) files_worker(&jobs[t]);
+        else pthread_create(&th[t], NULL, files_worker, &jobs[t]);
+    }
+    int rc = 0;
+    for (int t = 0; t < nthreads; t++) {
+        if (nthreads > 1) pthread_join(th[t], NULL);
+        if (jobs[t].err && !rc) rc = jobs[t].err;
+    }
+    free(list);
+    free(th);
+    free(jobs);
+    return rc;
+}
+
 /* bytes the reference's streamsEqual touches for one pair:
  * 2*L for an equal pair, 2*16384*(floor(first_diff/16384)+1) (capped at 2*L) otherwise. */
 uint64_t oracle_cmp_algorithmic_bytes(const uint8_t *a, const uint8_t *b, uint64_t len)

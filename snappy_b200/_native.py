@@ -100,6 +100,7 @@ SIGNATURES = {
     "snapgpu_get_stats": (_i, [ctypes.POINTER(Stats)]),
     "snapgpu_reset_stats": (None, []),
     "snapgpu_pipe_microbench": (_i, [_i, _i, _i, _pd, _pd, _pd]),
+    "snapgpu_h2d_probe": (_i, [_vp, _sz, _i, _pd]),
     "snapgpu_test_yaml_from_digests": (_i, [_cp, _vp, _sz, _pp, _psz]),
     "snapgpu_test_filehash_yaml": (_i, [_cp, ctypes.c_longlong, _cp, ctypes.c_uint, _pp, _psz]),
     "snapgpu_test_plan_order": (_i, [_vp, _sz, _vp]),

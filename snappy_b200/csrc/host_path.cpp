@@ -1992,12 +1992,18 @@ int copy_to_build_dir(const std::string &source_in, const std::string &build_dir
         sizes.push_back(S_ISREG(actions[i].st.st_mode) ? (int64_t)actions[i].st.st_size : 0);
     }
     std::vector<struct stat> written(to_copy.size());
+    // Only a file whose bytes went to the build dir out of the pinned batch -- the very bytes the
+    // GPU hashed -- gets its digest remembered.  One that grew, or is larger than a batch, is
+    // hashed from one read of the source and copied from another: its digest is not cached, the
+    // writeHashes that follows reads the copy.
+    std::vector<uint8_t> same_bytes(to_copy.size(), 0);
     FileSink sink = [&](size_t k, const uint8_t *bytes, uint64_t len) -> int {
         const CopyAction &a = actions[to_copy[k]];
         int out = ::open(a.dest.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_CLOEXEC, a.st.st_mode & 07777);
         if (out < 0) return fail(SNAPGPU_EIO, "%s", go_path_error("open", a.dest, errno).c_str());
         int err = 0;
         if (bytes) {
+            same_bytes[k] = 1;
             if (write_all(out, bytes, len) != 0) err = errno;
         } else {                                   // did not pass through a batch: plain io.Copy
             int in = ::open(a.src.c_str(), O_RDONLY | O_CLOEXEC);
@@ -2024,7 +2030,8 @@ int copy_to_build_dir(const std::string &source_in, const std::string &build_dir
     std::vector<uint8_t> digests;
     if ((rc = hash_files(paths, digests, &sizes, &sink))) return rc;
     const double t3 = wall_ms();
-    for (size_t k = 0; k < to_copy.size(); k++) cache_put(written[k], &digests[64 * k]);
+    for (size_t k = 0; k < to_copy.size(); k++)
+        if (same_bytes[k]) cache_put(written[k], &digests[64 * k]);
     if (getenv("SNAPGPU_TRACE"))
         fprintf(stderr, "[snapgpu] copyToBuildDir: walk %.2f ms (%zu entries), mkdir/link %.2f ms, copy+hash %.2f ms (%zu files), cache %.2f ms\n",
                 t1 - t0, actions.size(), t2 - t1, t3 - t2, to_copy.size(), wall_ms() - t3);

@@ -1859,6 +1859,63 @@ long long snapgpu_test_chunks(const uint64_t *offsets, const uint64_t *lengths, 
     return (long long)row;
 }
 
+// Raw host-to-device copy rate (bench support): every bound device copies `bytes_per_dev` bytes
+// `reps` times from its own slice of `host` (device d reads host + d * bytes_per_dev) with the call
+// the pipeline itself uses -- cudaMemcpyAsync on a pipe's copy stream -- all devices at once, one
+// thread each.  *seconds = the longest device's time for its reps (CUDA events), the ceiling that
+// the end-to-end figures are fractions of.
+int snapgpu_h2d_probe(const void *host, size_t bytes_per_dev, int reps, double *seconds) {
+    if (!host || !seconds || bytes_per_dev == 0 || reps < 1) return fail(SNAPGPU_EINVAL, "bad argument");
+    DevsInUse use(rt().devs_mu);
+    auto &R = rt();
+    if (R.devs.empty()) return fail(SNAPGPU_ENOINIT, "snapgpu_init has not been called (or failed)");
+    const size_t ndev = R.devs.size();
+    std::vector<double> secs(ndev, 0.0);
+    std::vector<int> rcs(ndev, 0);
+    std::vector<std::string> errs(ndev);
+    std::atomic<size_t> ready{0};
+    auto run = [&](size_t d) {
+        PipeLease lease(*R.devs[d]);
+        Pipe &P = *lease.pipe;
+        auto cuda_fail = [&](cudaError_t e, const char *what) {
+            rcs[d] = SNAPGPU_ECUDA;
+            errs[d] = std::string(what) + ": " + cudaGetErrorString(e);
+        };
+        cudaError_t e;
+        if ((e = cudaSetDevice(P.ordinal)) != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+        void *dst = nullptr;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if ((e = cudaMalloc(&dst, bytes_per_dev)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        const uint8_t *src = static_cast<const uint8_t *>(host) + d * bytes_per_dev;
+        e = cudaMemcpyAsync(dst, src, bytes_per_dev, cudaMemcpyHostToDevice, P.copy_stream);      // warm-up
+        if (e == cudaSuccess) e = cudaStreamSynchronize(P.copy_stream);
+        ready++;
+        while (ready.load() < ndev) std::this_thread::yield();       // all devices start together
+        if (e == cudaSuccess) e = cudaEventRecord(e0, P.copy_stream);
+        for (int r = 0; r < reps && e == cudaSuccess; r++)
+            e = cudaMemcpyAsync(dst, src, bytes_per_dev, cudaMemcpyHostToDevice, P.copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(e1, P.copy_stream);
+        if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+        float ms = 0;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        secs[d] = ms * 1e-3;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        cudaFree(dst);
+        if (e != cudaSuccess) cuda_fail(e, "host-to-device copy");
+    };
+    std::vector<std::thread> th;
+    for (size_t d = 1; d < ndev; d++) th.emplace_back(run, d);
+    run(0);
+    for (auto &t : th) t.join();
+    for (size_t d = 0; d < ndev; d++)
+        if (rcs[d]) return fail(rcs[d], "device %zu: %s", d, errs[d].c_str());
+    *seconds = *std::max_element(secs.begin(), secs.end());
+    return 0;
+}
+
 typedef void (*ProbeKernel)(uint32_t *, int, uint32_t, uint32_t, unsigned long long *);
 
 int snapgpu_pipe_microbench(int dev, int kind, int warps_per_sm, double *inst_per_clk_per_sm, double *elapsed_ms,

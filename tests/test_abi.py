@@ -86,3 +86,14 @@ def test_product_does_not_touch_the_oracle():
             text = p.read_text(errors="replace")
             assert "oracle" not in text.lower(), p
     assert "hashlib" not in "".join(p.read_text() for p in (ROOT / "snappy_b200").glob("*.py"))
+
+
+def test_c_caller_links_and_the_library_refuses_without_cuda(native, tmp_path):
+    """tests/c_abi_harness.c compiles as C11 with -Werror against include/snapgpu.h, links against
+    libsnapgpu.so and runs; in this container (no GPU) its --no-gpu mode checks that init and the
+    compute entry points fail instead of falling back to a CPU."""
+    import subprocess
+    from test_gpu_parity import build_c_harness
+    exe = build_c_harness(tmp_path)
+    p = subprocess.run([str(exe), "--no-gpu"], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0 and p.stdout.startswith("ok") or "nothing to check" in p.stdout, (p.stdout, p.stderr)

@@ -113,8 +113,11 @@ def test_unaligned_offsets_take_the_generic_path(gpu, oracle):
     assert (off % 16 != 0).any()
     assert np.array_equal(helpers.sha512_batch(data, off, ln), oracle.sha512_batch(data, off, ln, 4))
     # and a misaligned base pointer
-    shifted = np.concatenate([np.zeros(5, np.uint8), data])[5:]
-    assert shifted.ctypes.data % 16 != data.ctypes.data % 16 or True
+    backing = np.zeros(len(data) + 32, np.uint8)
+    start = (data.ctypes.data + 5 - backing.ctypes.data) % 16         # base pointer 5 bytes off data's phase
+    shifted = backing[start:start + len(data)]
+    shifted[:] = data
+    assert shifted.ctypes.data % 16 != data.ctypes.data % 16
     assert np.array_equal(helpers.sha512_batch(shifted, off, ln), oracle.sha512_batch(data, off, ln, 4))
 
 
@@ -793,3 +796,80 @@ def test_cmp_large_pageable_buffers(gpu, oracle):
     assert got.tolist() == [0, 1, 0, 1, 1, 1, 0]
     assert np.array_equal(got, oracle.cmp_batch(a, b, off, ln, 4))
     assert np.array_equal(helpers.sha512_batch(a, off, ln), oracle.sha512_batch(a, off, ln, 4))
+
+
+# ---- a C caller of the ABI (idiom of helpers/touch.go:20-57) ---------------
+
+def build_c_harness(tmp_path):
+    import subprocess
+    from conftest import ROOT
+    exe = tmp_path / "c_abi_harness"
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-O1", "-o", str(exe), str(ROOT / "tests" / "c_abi_harness.c"),
+                           "-L" + str(ROOT / "snappy_b200"), "-lsnapgpu", "-Wl,-rpath," + str(ROOT / "snappy_b200")])
+    return exe
+
+
+def test_c_program_writes_the_golden_hashes_yaml(gpu, golden_dir, tmp_path):
+    """tests/c_abi_harness.c, linked against libsnapgpu.so like a cgo shim would be: it builds the tree
+    of snappy/hashes_test.go:57-87 with libc, calls snapgpu_write_hashes and diffs DEBIAN/hashes.yaml with
+    the reference's golden document; then Sha512sum / FilesAreEqual known answers and a pinned batch."""
+    import subprocess
+    exe = build_c_harness(tmp_path)
+    p = subprocess.run([str(exe), str(tmp_path / "work"), str(golden_dir / "hashes_simple.yaml")], capture_output=True, text=True,
+                       timeout=300)
+    assert p.returncode == 0 and p.stdout.strip() == "ok", (p.returncode, p.stdout, p.stderr)
+
+
+def test_mixed_tree_every_size_class(gpu, oracle, tmp_path):
+    """The tree of tests/test_hostsim.py (small / mid / chain size classes, wide and nested directories,
+    symlinks, names yaml.v2 quotes, DEBIAN-prefixed names) through the real kernels, with a multi-piece
+    archive whose chain runs beside the tree's batches; twice, with different packer fan-out."""
+    from snappy_b200 import build
+    from test_hostsim import make_mixed_tree
+    rng = np.random.default_rng(7)
+    tree = tmp_path / "tree"
+    make_mixed_tree(tree, rng)
+    tar = tmp_path / "data.tar.gz"
+    tar.write_bytes(rng.integers(0, 256, size=(5 << 20) + 77, dtype=np.uint8).tobytes())
+    want = oracle.write_hashes(str(tree), str(tar))
+    for _ in range(2):
+        assert build.hashes_yaml(str(tree), str(tar)) == want
+    st = gpu.tree_stats()
+    assert st["files_hashed"] > 1100 and st["batches"] >= 1 and st["yaml_bytes"] == len(want)
+
+
+def test_concurrent_callers_overlap(gpu, oracle):
+    """Two callers on one device use different pipes: a chain-bound call (one 3 MiB message: ~45 ms of
+    serial chain, almost nothing to copy) and a copy-bound call (512 MiB of 64 KiB files: ~10 ms of PCIe)
+    together take less than the two one after the other."""
+    import threading
+    import time
+    from snappy_b200 import helpers
+    rng = np.random.default_rng(77)
+    chain = rng.integers(0, 256, size=3 << 20, dtype=np.uint8)
+    c_off, c_len = np.array([0], np.uint64), np.array([len(chain)], np.uint64)
+    n = 8192
+    bulk = rng.integers(0, 256, size=n * 65536, dtype=np.uint8)
+    b_off, b_len = np.arange(n, dtype=np.uint64) * np.uint64(65536), np.full(n, 65536, np.uint64)
+    want_chain = oracle.sha512_batch(chain, c_off, c_len, 1)
+    helpers.sha512_batch(chain, c_off, c_len)
+    helpers.sha512_batch(bulk, b_off, b_len)                      # warm-up: staging buffers of both shapes
+    best_serial, best_both = 1e9, 1e9
+    for _ in range(3):
+        t0 = time.perf_counter()
+        helpers.sha512_batch(chain, c_off, c_len)
+        helpers.sha512_batch(bulk, b_off, b_len)
+        best_serial = min(best_serial, time.perf_counter() - t0)
+        out = {}
+        th = [threading.Thread(target=lambda: out.__setitem__("c", helpers.sha512_batch(chain, c_off, c_len))),
+              threading.Thread(target=lambda: out.__setitem__("b", helpers.sha512_batch(bulk, b_off, b_len)))]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        best_both = min(best_both, time.perf_counter() - t0)
+        assert np.array_equal(out["c"], want_chain)
+    spot = [0, 1, n // 2, n - 1]
+    assert np.array_equal(out["b"][spot], oracle.sha512_batch(bulk, b_off[spot], b_len[spot], 1))
+    assert best_both < 0.9 * best_serial, (best_both, best_serial)

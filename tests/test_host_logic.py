@@ -362,3 +362,26 @@ def test_read_archive_sha512_like_new_snap_part(native, golden_dir, tmp_path):
     assert "Unknown file mode prw-r--r--" in str(e.value)
     with pytest.raises(OSError):
         build.readArchiveSha512(str(tmp_path / "missing.yaml"))
+
+
+def test_filehash_fragment_through_the_product_emitter(native, golden_dir):
+    """TestHashesYamlMarshal (snappy/hashes_test.go:30-55) on the C++ emitter of libsnapgpu: the
+    fileHash {Name: "foo", Size: 10, Mode: dir 0644} renders as the reference's fragment, omitempty
+    drops a nil size and an empty sha512, and the mode string follows yamlFileMode.MarshalYAML."""
+    import ctypes
+    import stat
+
+    def render(name, size, sha, mode):
+        ptr, ln = ctypes.c_void_p(), ctypes.c_size_t()
+        native.check(native.lib().snapgpu_test_filehash_yaml(name.encode(), size, sha.encode() if sha else None, mode,
+                                                             ctypes.byref(ptr), ctypes.byref(ln)))
+        return native.take_string(ptr, ln.value)
+
+    assert render("foo", 10, None, stat.S_IFDIR | 0o644) == (golden_dir / "filehash_fragment.yaml").read_bytes()
+    assert render("foo", -1, None, stat.S_IFLNK | 0o777) == b"name: foo\nmode: lrwxrwxrwx\n"
+    assert render("bin/bar", 4, "cc" * 64, stat.S_IFREG | 0o644) == \
+        b"name: bin/bar\nsize: 4\nsha512: " + b"cc" * 64 + b"\nmode: frw-r--r--\n"
+    assert render("true", 0, None, stat.S_IFREG | 0o600) == b'name: "true"\nsize: 0\nmode: frw-------\n'
+    ptr, ln = ctypes.c_void_p(), ctypes.c_size_t()
+    rc = native.lib().snapgpu_test_filehash_yaml(b"pipe", -1, None, stat.S_IFIFO | 0o644, ctypes.byref(ptr), ctypes.byref(ln))
+    assert rc == native.EMODE and "Unknown file mode" in native.last_error()

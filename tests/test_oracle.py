@@ -204,3 +204,22 @@ def test_apparmor_delta(oracle, tmp_path):
     ps, ts = oracle.apparmor_delta(str(orig), str(dest), "x-")
     assert ps == {"x-policygroups0": True, "x-policygroups1": True, "x-policygroups2": True}
     assert ts == {}
+
+
+def test_sha512sum_files_threaded_equals_hashlib(oracle, tmp_path):
+    """The CPU tree comparator of bench.py (Sha512sum over a file list, 1 and several threads, both
+    block functions) against hashlib, incl. an empty file, a >32 KiB file and a missing one."""
+    import hashlib
+    rng = np.random.default_rng(1)
+    paths, sizes = [], []
+    for i, n in enumerate([0, 1, 111, 112, 4096, 32768, 32769, 100_000] + [int(x) for x in rng.integers(0, 5000, 40)]):
+        p = tmp_path / f"f{i:03d}"
+        p.write_bytes(rng.integers(0, 256, n, dtype=np.uint8).tobytes())
+        paths.append(str(p))
+        sizes.append(n)
+    want = np.array([list(hashlib.sha512(open(p, "rb").read()).digest()) for p in paths], dtype=np.uint8)
+    for threads in (1, 3, 8):
+        for ossl in (False, True):
+            assert np.array_equal(oracle.sha512sum_files(paths, sizes, threads, ossl), want)
+    with pytest.raises(OSError):
+        oracle.sha512sum_files(paths + [str(tmp_path / "missing")], sizes + [0], 2)
