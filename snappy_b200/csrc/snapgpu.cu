@@ -113,6 +113,10 @@ struct Pipe {
     int sm_count = 0;
     std::mutex mu;
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr, long_stream = nullptr;
+    cudaStream_t slot_long_stream[kStageBufs] = {};
+    cudaStream_t slot_stream[kStageBufs] = {};   // batch sessions: one compute stream per staging buffer, so that the
+                                                 // kernels of consecutive batches (each at least as long as the chain of
+                                                 // its longest file, mostly on a fraction of the SMs) run side by side
     PlanSlot slots[kPlanSlots];
     int next_slot = 0;
     // host-buffer pipeline (allocated on first use)
@@ -266,6 +270,10 @@ static void destroy_pipe(Pipe &D) {
     if (D.copy_stream) cudaStreamDestroy(D.copy_stream);
     if (D.compute_stream) cudaStreamDestroy(D.compute_stream);
     if (D.long_stream) cudaStreamDestroy(D.long_stream);
+    for (auto &st : D.slot_stream)
+        if (st) cudaStreamDestroy(st);
+    for (auto &st : D.slot_long_stream)
+        if (st) cudaStreamDestroy(st);
     D.ordinal = -1;
 }
 
@@ -276,6 +284,8 @@ static int init_pipe(Pipe &D, int ordinal, int sm_count) {
     SG_CUDA(cudaStreamCreateWithFlags(&D.copy_stream, cudaStreamNonBlocking));
     SG_CUDA(cudaStreamCreateWithFlags(&D.compute_stream, cudaStreamNonBlocking));
     SG_CUDA(cudaStreamCreateWithFlags(&D.long_stream, cudaStreamNonBlocking));
+    for (auto &st : D.slot_stream) SG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto &st : D.slot_long_stream) SG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     for (auto &s : D.slots) {
         SG_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         SG_CUDA(cudaEventCreate(&s.uploaded));
@@ -548,7 +558,8 @@ static int enqueue_length_binning(Pipe &D, cudaStream_t stream, const DevicePlan
 // caller's stream is still running.
 template <typename Get>
 static int launch_sha512(Pipe &D, cudaStream_t stream, const uint8_t *d_data, Get get, size_t n,
-                         uint8_t *d_digests) {
+                         uint8_t *d_digests, cudaStream_t long_stream = nullptr) {
+    if (!long_stream) long_stream = D.long_stream;
     if (n == 0) return 0;
     if (n > 0xfffffff0ull) return fail(SNAPGPU_EINVAL, "too many files in one launch (%zu)", n);
     auto &R = rt();
@@ -646,26 +657,26 @@ static int launch_sha512(Pipe &D, cudaStream_t stream, const uint8_t *d_data, Ge
     if (n_long) {
         // everything `stream` has been asked to do so far (the data, a chaining value) comes first
         SG_CUDA(cudaEventRecord(slot->fork, stream));
-        SG_CUDA(cudaStreamWaitEvent(D.long_stream, slot->fork, 0));
+        SG_CUDA(cudaStreamWaitEvent(long_stream, slot->fork, 0));
         if (R.opt.long_kernel.load() >= 2) {                // one chain per lane pair (sha512_pair.cuh)
             const u32 long_grid = (u32)((n_long + kPairFilesPerCta - 1) / kPairFilesPerCta);
             if (aligned)
-                sha512_pair_kernel<true><<<long_grid, kLongThreads, kPairSmemBytes, D.long_stream>>>(
+                sha512_pair_kernel<true><<<long_grid, kLongThreads, kPairSmemBytes, long_stream>>>(
                     d_data, plan.long_descs, (u32)n_long, d_digests);
             else
-                sha512_pair_kernel<false><<<long_grid, kLongThreads, kPairSmemBytes, D.long_stream>>>(
+                sha512_pair_kernel<false><<<long_grid, kLongThreads, kPairSmemBytes, long_stream>>>(
                     d_data, plan.long_descs, (u32)n_long, d_digests);
         } else {                                            // one chain per lane (sha512_long.cuh)
             const u32 long_grid = (u32)((n_long + kLongFilesPerCta - 1) / kLongFilesPerCta);
             if (aligned)
-                sha512_long_kernel<true><<<long_grid, kLongThreads, kLongSmemBytes, D.long_stream>>>(
+                sha512_long_kernel<true><<<long_grid, kLongThreads, kLongSmemBytes, long_stream>>>(
                     d_data, plan.long_descs, (u32)n_long, d_digests);
             else
-                sha512_long_kernel<false><<<long_grid, kLongThreads, kLongSmemBytes, D.long_stream>>>(
+                sha512_long_kernel<false><<<long_grid, kLongThreads, kLongSmemBytes, long_stream>>>(
                     d_data, plan.long_descs, (u32)n_long, d_digests);
         }
         SG_CUDA(cudaGetLastError());
-        SG_CUDA(cudaEventRecord(slot->join, D.long_stream));
+        SG_CUDA(cudaEventRecord(slot->join, long_stream));
         R.kernel_launches++;
         R.sha_long_launches++;
     }
@@ -1223,7 +1234,7 @@ int session_open(BatchSession **out, size_t max_batch_bytes) {
     std::unique_ptr<BatchSession> s(new BatchSession());
     auto &R = rt();
     if (R.devs.empty()) return fail(SNAPGPU_ENOINIT, "snapgpu_init has not been called (or failed)");
-    s->max_batch_bytes = std::min(std::max<size_t>(max_batch_bytes, 1u << 20), staging_bytes());
+    s->max_batch_bytes = std::max<size_t>(max_batch_bytes, 1u << 20);
     s->lanes.resize(R.devs.size());
     for (size_t d = 0; d < R.devs.size(); d++) {
         s->lanes[d].dev = R.devs[d].get();
@@ -1327,14 +1338,15 @@ int session_submit(BatchSession *s, const HostSpan *spans, size_t nspans, const 
                                     P.copy_stream));
     R.h2d_bytes += total;
     SG_CUDA(cudaEventRecord(P.ev_copied[b], P.copy_stream));
-    SG_CUDA(cudaStreamWaitEvent(P.compute_stream, P.ev_copied[b], 0));
+    cudaStream_t cs = P.slot_stream[b];
+    SG_CUDA(cudaStreamWaitEvent(cs, P.ev_copied[b], 0));
     const uint64_t *base = s->span_base.data();
     auto get = [segs, base](size_t i) { return SegDesc{base[segs[i].span] + segs[i].off, segs[i].len, 0, (u32)i, 0}; };
-    int rc = launch_sha512(P, P.compute_stream, P.d_stage[b], get, nsegs, P.d_out[b]);
+    int rc = launch_sha512(P, cs, P.d_stage[b], get, nsegs, P.d_out[b], P.slot_long_stream[b]);
     if (rc) return rc;
-    SG_CUDA(cudaMemcpyAsync(P.h_out[b], P.d_out[b], nsegs * 64, cudaMemcpyDeviceToHost, P.compute_stream));
+    SG_CUDA(cudaMemcpyAsync(P.h_out[b], P.d_out[b], nsegs * 64, cudaMemcpyDeviceToHost, cs));
     R.d2h_bytes += nsegs * 64;
-    SG_CUDA(cudaEventRecord(P.ev_done[b], P.compute_stream));
+    SG_CUDA(cudaEventRecord(P.ev_done[b], cs));
     BatchSession::Slot &S = lane->slot[b];
     S.busy = true;
     S.copy_reported = false;

@@ -845,6 +845,8 @@ private:
         std::vector<uint64_t> copied;
         const size_t cap_bytes = (size_t)448 << 20, cap_items = (size_t)1 << 20;
         bool all_done = false;
+        const bool trace = getenv("SNAPGPU_TRACE") != nullptr;
+        const double t_start = wall_ms();
         while (!fatal_rc_) {
             bool progressed = false;
             const int made_small = small_chunks().serve_allocations(), made_large = large_chunks().serve_allocations();
@@ -891,11 +893,19 @@ private:
                 }
                 uint64_t ticket = 0;
                 copied.clear();
+                const double t_submit = wall_ms();
                 rc = session_submit(session_, spans.data(), spans.size(), segs.data(), dst.data(), segs.size(), &ticket, &copied);
                 if (rc) { fatal(rc); break; }
                 in_copy_.emplace_back(ticket, take);
                 recycle(copied);
                 nbatches_++;
+                if (trace) {
+                    size_t bytes = 0;
+                    for (Chunk *c : take) bytes += c->used;
+                    fprintf(stderr, "[snapgpu] tree batch %zu at %.2f ms: %zu chunks, %.1f MiB, %zu files; %zu in flight, submit took %.2f ms\n",
+                            nbatches_, wall_ms() - t_start, take.size(), bytes / 1048576.0, segs.size(), session_in_flight(session_),
+                            wall_ms() - t_submit);
+                }
                 continue;
             }
             if (all_done) break;
@@ -919,6 +929,7 @@ private:
             }
         }
         const double t0 = wall_ms();
+        if (trace) fprintf(stderr, "[snapgpu] tree: workers done at %.2f ms, %zu batches in flight\n", t0 - t_start, session_in_flight(session_));
         copied.clear();
         int rc = session_poll(session_, &copied, true);
         if (rc && !fatal_rc_) fatal(rc);

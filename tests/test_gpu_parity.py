@@ -548,12 +548,15 @@ def test_copy_to_build_dir_fused_with_hashing(gpu, oracle, tmp_path):
     assert snapshot(got)["bin/hello-world"][3] is False          # really copied
     nfiles = sum(1 for v in snapshot(got).values() if v[0] == "f")
     entries, hits = build.digest_cache_stats()
-    assert entries == nfiles and hits == 0
+    # bin/link (a symlink whose target is copied: it "grows" from the 0 bytes planned for it) did not go
+    # to the build dir out of the pinned batch, so its digest is not remembered
+    assert entries == nfiles - 1 and hits == 0
     tar = tmp_path / "data.tar.gz"
     tar.write_bytes(b"not really a tarball")
     doc = build.hashes_yaml(str(got), str(tar))
     assert doc == oracle.write_hashes(str(want), str(tar))
-    assert build.digest_cache_stats()[1] == nfiles               # nothing was read a second time
+    assert build.digest_cache_stats() == (0, nfiles - 1)         # the others were not read a second time, and
+                                                                 # the cache served this one writeHashes only
     # a file changed after the copy is hashed again (size or mtime no longer match)
     victim = got / "lib" / "blob07"
     body = bytearray(victim.read_bytes() or b"x")
