@@ -77,7 +77,7 @@ std::string hex_lower(const uint8_t *p, size_t n) {
 // ------------------------------------------------------------------------------------------
 
 constexpr int kPlanSlots = 4;
-constexpr int kStageBufs = 3;
+constexpr int kStageBufs = 4;
 constexpr size_t kCounterBytes = 64 + 8 * (2 + 4 * 256);   // unit counter | balance[2 + sub-partitions] (up to 256 SMs)
 constexpr int kFeeders = 8;                     // at most this many host threads move pageable memory into pinned bounce buffers
 constexpr size_t kBounceBytes = 4u << 20;
@@ -1201,6 +1201,7 @@ public:
     uint64_t next_ticket = 1;
     size_t in_flight = 0;
     std::vector<uint64_t> span_base;
+    double t_open = 0;
 
     BatchSession() : use(rt().devs_mu) {}
 };
@@ -1218,6 +1219,7 @@ static int session_retire(BatchSession *s, BatchSession::Lane &L, int b, std::ve
         if (e != cudaSuccess) return fail(SNAPGPU_ECUDA, "host-to-device copy failed: %s", cudaGetErrorString(e));
         S.copy_reported = true;
         if (copied) copied->push_back(S.ticket);
+        if (trace_on()) fprintf(stderr, "[snapgpu] session: batch %llu copied, seen at %.2f ms\n", (unsigned long long)S.ticket, now_ms() - s->t_open);
     }
     cudaError_t e = wait ? cudaEventSynchronize(P.ev_done[b]) : cudaEventQuery(P.ev_done[b]);
     if (e == cudaErrorNotReady) return 0;
@@ -1226,6 +1228,7 @@ static int session_retire(BatchSession *s, BatchSession::Lane &L, int b, std::ve
     for (size_t i = 0; i < S.dst.size(); i++) memcpy(S.dst[i], src + 64 * i, 64);
     S.busy = false;
     s->in_flight--;
+    if (trace_on()) fprintf(stderr, "[snapgpu] session: batch %llu done, seen at %.2f ms\n", (unsigned long long)S.ticket, now_ms() - s->t_open);
     return 0;
 }
 
@@ -1235,6 +1238,7 @@ int session_open(BatchSession **out, size_t max_batch_bytes) {
     auto &R = rt();
     if (R.devs.empty()) return fail(SNAPGPU_ENOINIT, "snapgpu_init has not been called (or failed)");
     s->max_batch_bytes = std::max<size_t>(max_batch_bytes, 1u << 20);
+    s->t_open = now_ms();
     s->lanes.resize(R.devs.size());
     for (size_t d = 0; d < R.devs.size(); d++) {
         s->lanes[d].dev = R.devs[d].get();
@@ -1326,11 +1330,15 @@ int session_submit(BatchSession *s, const HostSpan *spans, size_t nspans, const 
             }
             b = 0;
         }
-        size_t want = (size_t)16 << 20;
-        while (want < total) want <<= 1;
-        int rc = ensure_staging(P, std::max(P.stage_cap, std::min(want, std::max(s->max_batch_bytes, total))),
-                                std::max(P.out_cap, nsegs * 64), kStageBufs);
+        // the session's batch size at once (growing step by step would pay cudaMalloc again and again)
+        const size_t want = std::max(s->max_batch_bytes, total);
+        const double tg = now_ms();
+        int rc = ensure_staging(P, std::max(P.stage_cap, want), std::max(P.out_cap, std::max<size_t>(nsegs * 64, 1u << 20)),
+                                kStageBufs);
         if (rc) return rc;
+        if (trace_on())
+            fprintf(stderr, "[snapgpu] session: staging grown to %d x %zu MiB (+ %zu KiB of digests) in %.2f ms\n", kStageBufs,
+                    P.stage_cap >> 20, P.out_cap >> 10, now_ms() - tg);
     }
     for (size_t k = 0; k < nspans; k++)
         if (spans[k].bytes)

@@ -107,11 +107,12 @@ private:
 // pinned chunks
 // ------------------------------------------------------------------------------------------
 
-constexpr size_t kSmallChunk = (size_t)4 << 20;      // files up to kSmallMax are packed into these
-constexpr size_t kSmallMax = (size_t)512 << 10;
+constexpr size_t kSmallChunk = (size_t)2 << 20;      // files up to kSmallMax are packed into these
+constexpr size_t kSmallMax = (size_t)256 << 10;
 constexpr size_t kLargeChunk = (size_t)32 << 20;     // files up to kMidMax, a few per chunk
 constexpr size_t kMidMax = (size_t)16 << 20;         // longer files are chains of their own (ChainStreamer)
 constexpr size_t kChunkSlack = 256;
+constexpr size_t kTreeBatchBytes = (size_t)64 << 20; // one batch of the tree hasher: at least two large chunks
 
 struct PackedRef {
     uint8_t *digest;       // where the digest goes (a TEntry's)
@@ -132,7 +133,8 @@ struct Chunk {
 // the thread that drives the session (serve_allocations).
 class ChunkPool {
 public:
-    ChunkPool(size_t chunk_bytes, size_t max_chunks, int cls) : bytes_(chunk_bytes), max_(max_chunks), cls_(cls) {}
+    ChunkPool(size_t chunk_bytes, size_t max_chunks, size_t first_slab, int cls)
+        : bytes_(chunk_bytes), max_(max_chunks), first_slab_(first_slab), cls_(cls) {}
 
     // worker side: a free chunk or nullptr.  A worker that got none announces itself with
     // begin_wait() and keeps trying; the driver allocates for the waiters it sees (up to the cap),
@@ -159,31 +161,32 @@ public:
         free_.push_back(c);
     }
     // driver side (may call CUDA): returns how many chunks were added, -1 when workers wait and
-    // there is not a single chunk to recycle for them (pinned memory cannot be had at all)
+    // there is not a single chunk to recycle for them (pinned memory cannot be had at all).
+    // Pinning is slow (~0.4 ms per MiB) and holds up every other CUDA call of the process while
+    // it lasts, so the pool grows in slabs that double it (at least `first_slab` chunks): a
+    // handful of allocations during the first large tree of a process, none afterwards.
     int serve_allocations() {
         size_t want = 0;
         {
             std::lock_guard<std::mutex> lk(mu_);
-            if (waiters_ > free_.size()) want = std::min(waiters_ - free_.size(), max_ - std::min(max_, all_.size()));
+            if (waiters_ > free_.size() && all_.size() < max_)
+                want = std::min(std::max(first_slab_, all_.size()), max_ - all_.size());
         }
-        int made = 0;
+        if (!want) return 0;
+        uint8_t *p = nullptr;
+        for (; want; want /= 2)                  // a smaller slab if the large one cannot be pinned
+            if ((p = static_cast<uint8_t *>(snapgpu_alloc_pinned(want * bytes_)))) break;
+        std::lock_guard<std::mutex> lk(mu_);
+        if (!p) return all_.empty() ? -1 : 0;   // the workers keep waiting for recycled chunks
         for (size_t k = 0; k < want; k++) {
-            uint8_t *p = static_cast<uint8_t *>(snapgpu_alloc_pinned(bytes_));
-            if (!p) {                           // the workers keep waiting for recycled chunks
-                std::lock_guard<std::mutex> lk(mu_);
-                if (all_.empty()) return -1;
-                break;
-            }
             Chunk *c = new Chunk();
-            c->base = p;
+            c->base = p + k * bytes_;
             c->cap = bytes_;
             c->cls = cls_;
-            std::lock_guard<std::mutex> lk(mu_);
             all_.push_back(c);
             free_.push_back(c);
-            made++;
         }
-        return made;
+        return (int)want;
     }
     size_t allocated() {
         std::lock_guard<std::mutex> lk(mu_);
@@ -191,7 +194,7 @@ public:
     }
 
 private:
-    const size_t bytes_, max_;
+    const size_t bytes_, max_, first_slab_;
     const int cls_;
     std::mutex mu_;
     std::vector<Chunk *> all_, free_;
@@ -199,11 +202,11 @@ private:
 };
 
 inline ChunkPool &small_chunks() {
-    static ChunkPool *p = new ChunkPool(kSmallChunk, 192, 0);      // up to 768 MiB pinned
+    static ChunkPool *p = new ChunkPool(kSmallChunk, 384, 16, 0);  // 32 MiB, doubling up to 768 MiB pinned
     return *p;
 }
 inline ChunkPool &large_chunks() {
-    static ChunkPool *p = new ChunkPool(kLargeChunk, 24, 1);       // up to 768 MiB pinned
+    static ChunkPool *p = new ChunkPool(kLargeChunk, 24, 2, 1);    // 64 MiB, doubling up to 768 MiB pinned
     return *p;
 }
 
@@ -489,7 +492,7 @@ public:
         struct stat st;
         if (lstat(root_.c_str(), &st) != 0 || !S_ISDIR(st.st_mode)) return 0;      // Walk visits only the root: no entries
         if (hash_) {
-            int rc = session_open(&session_, (size_t)512 << 20);
+            int rc = session_open(&session_, kTreeBatchBytes);
             if (rc) return rc;
         }
         TDir *root = new_dir(root_, "");
@@ -707,14 +710,20 @@ private:
             // half-filled chunk: every chunk is then free, being filled by a running worker,
             // ready or in flight), wake the driver, wait for a new or a recycled chunk
             flush_chunk(W, cls ^ 1);
-            pool.begin_wait();
-            while (!(c = pool.try_get())) {
+            bool asked = false;
+            for (int spins = 0; !(c = pool.try_get()); spins++) {
+                // a chunk whose copy has just finished is usually back within a few hundred
+                // microseconds; only a worker that has waited longer asks for the pool to grow
+                if (spins == 2 && !asked) {
+                    pool.begin_wait();
+                    asked = true;
+                }
                 std::unique_lock<std::mutex> lk(r_mu_);
                 r_cv_.notify_all();
-                chunk_cv_.wait_for(lk, std::chrono::microseconds(200));
+                chunk_cv_.wait_for(lk, std::chrono::microseconds(150));
                 if (abort_.load()) break;
             }
-            pool.end_wait();
+            if (asked) pool.end_wait();
             if (!c) return nullptr;
         }
         W.cur[cls] = c;
@@ -843,7 +852,10 @@ private:
         std::vector<SpanSeg> segs;
         std::vector<uint8_t *> dst;
         std::vector<uint64_t> copied;
-        const size_t cap_bytes = (size_t)448 << 20, cap_items = (size_t)1 << 20;
+        // 64 MiB batches: four of them in flight (H2D ~1.2 ms, kernel >= 2 ms each) carry more than
+        // twice what sixteen packers produce, and the staging buffers (four of this size per device)
+        // are allocated once and never grow -- cudaMalloc is slow enough to show in a 50 ms call
+        const size_t cap_bytes = kTreeBatchBytes - 4096, cap_items = (size_t)1 << 20, kMinBatch = (size_t)32 << 20;
         bool all_done = false;
         const bool trace = getenv("SNAPGPU_TRACE") != nullptr;
         const double t_start = wall_ms();
@@ -864,13 +876,23 @@ private:
             int rc = session_poll(session_, &copied, false);
             if (rc) { fatal(rc); break; }
             if (recycle(copied)) progressed = true;
-            // submit what is ready when a slot is free -- or, while everything is in flight, keep
-            // collecting: the next batch is then as large as the GPU's pace allows
+            // Submit what is ready when a slot is free -- but not crumbs: every batch costs the GPU at
+            // least the chain of its longest file (2 ms for a 64 KiB one) and holds a slot for that
+            // long, so unless the GPU has nothing to do, or the workers are done, a batch waits until
+            // kMinBatch bytes are ready (the packers fill that in about a millisecond).  While every
+            // slot is taken the chunks keep collecting and the next batch is as large as the GPU's
+            // pace allows.
             take.clear();
             if (session_in_flight(session_) < session_capacity(session_)) {
                 std::lock_guard<std::mutex> lk(r_mu_);
                 size_t bytes = 0, items = 0;
-                while (!ready_.empty()) {
+                const bool workers_done = workers_done_ == nworkers;
+                if (!workers_done && session_in_flight(session_) > 0) {
+                    size_t ready_bytes = 0;
+                    for (Chunk *c : ready_) ready_bytes += c->used;
+                    if (ready_bytes < kMinBatch) bytes = cap_bytes + 1;          // not yet
+                }
+                while (!ready_.empty() && bytes <= cap_bytes) {
                     Chunk *c = ready_.front();
                     if (!take.empty() && (bytes + c->used > cap_bytes || items + c->files.size() > cap_items)) break;
                     bytes += (c->used + 255) & ~(size_t)255;
@@ -911,8 +933,7 @@ private:
             if (all_done) break;
             if (!progressed) {
                 std::unique_lock<std::mutex> lk(r_mu_);
-                if (ready_.empty() || session_in_flight(session_) >= session_capacity(session_))
-                    r_cv_.wait_for(lk, std::chrono::microseconds(session_in_flight(session_) ? 50 : 500));
+                r_cv_.wait_for(lk, std::chrono::microseconds(session_in_flight(session_) ? 50 : 300));
             }
         }
         if (fatal_rc_) {
