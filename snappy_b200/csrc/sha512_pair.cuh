@@ -81,7 +81,29 @@ __device__ __forceinline__ u64 pair_muladd(u64 x, u32 mul, u64 y) {
     return pack64(lo * mul, hi * mul) + y;
 }
 
-template <bool kAligned16>
+__device__ __forceinline__ u64 pair_exchange(u64 x) {      // with the other lane of the pair
+    return __shfl_xor_sync(0xffffffffu, x, 1);
+}
+
+// How the two lanes of a pair exchange their round results -- each needs exactly what its partner
+// produced in the previous iteration:
+//
+// kShuffle = false (option pair_form 0, the default): through shared-memory mailboxes read by the
+//   loads that fetch W+K (see the file header).  A store of iteration i is loaded by the partner
+//   in iteration i+1, so the pair must execute the straight-line round code together.  That is
+//   arranged, not assumed: every group of 16 rounds (and the prologue, and the two tail rounds)
+//   starts with __syncwarp() -- a convergence point; the slow path of its BRA.DIV re-converges a
+//   diverged warp -- and contains no branch up to the next one, and converged lanes do not part
+//   in branch-free code: ptxas relies on the same fact when it checks convergence ONCE for the 32
+//   shfl.sync of a group of the shuffle form below.  tests/test_sass.py pins the shape (one
+//   BRA.DIV and no other branch inside the round loop, every mailbox store ahead of the load of
+//   the next round in program order).  1.86 us per block.
+// kShuffle = true (pair_form 1): a warp shuffle (__shfl_xor_sync) carries the exchange, so the
+//   synchronisation is in the instruction itself.  Role 1 loads a zero where role 0 loads W+K,
+//   and both form PD = S2*mul + kw + r (tests/test_pair_schedule.py::compress_pair_shuffle).
+//   2.04 us per block -- two SHFL and two more IMAD per round cost more than the LDS/STS they
+//   replace (profiles/r02_pair_forms.jsonl) -- so it is the cross-check, not the default.
+template <bool kAligned16, bool kShuffle>
 __global__ void __launch_bounds__(kLongThreads, 1)
 sha512_pair_kernel(const uint8_t *__restrict__ data, const SegDesc *__restrict__ descs, u32 nsegs,
                    uint8_t *__restrict__ digests) {
@@ -147,12 +169,59 @@ sha512_pair_kernel(const uint8_t *__restrict__ data, const SegDesc *__restrict__
                 do ready = ld_volatile_shared(produced); while (b >= ready);
                 __threadfence_block();
             }
-            volatile u64 *const kin = role ? Tm : ring + ((size_t)slot_index * nf + min(file, nf - 1)) * kLongSlotWords;
+            volatile u64 *const kin = role ? (kShuffle ? zero : Tm)
+                                           : ring + ((size_t)slot_index * nf + min(file, nf - 1)) * kLongSlotWords;
             slot_index = slot_index + 1 == ring_steps ? 0 : slot_index + 1;
+            if (kShuffle) {
+                // role 0 needs role 1's d and c (H3, H2) for its first two rounds; role 1 starts from
+                // the two seeds that make its idle iterations produce b and a
+                const u64 kw0 = kin[0];
+                const u64 x3 = pair_exchange(st[3]), x2 = pair_exchange(st[2]);
+                const u64 seed0 = st[1] - pair_sigma(st[2], rp, rq, rs) - pair_f(st[2], st[3], 0, mask);
+                const u64 seed1 = st[0] - pair_sigma(st[1], rp, rq, rs) - pair_f(st[1], st[2], st[3], mask);
+                u64 D = role ? 0 : x3;                     // what is subtracted from this round's result: d | 0
+                u64 r = role ? seed1 : x2;                 // what the partner sent last: T1 | a
+                u64 S0 = role ? st[2] : st[0], S1 = role ? st[3] : st[1], S2 = role ? 0 : st[2], S3 = role ? 0 : st[3];
+                u64 PD = role ? seed0 : st[3] + kw0 + D;
+#define SNAPGPU_PAIR_ITER_X(KIN, I)                                                           \
+    {                                                                                            \
+        const u64 kwn = (KIN)[(I) + 1];                                                          \
+        const u64 e = pair_sigma(S0, rp, rq, rs) + pair_f(S0, S1, S2, mask) + PD;                \
+        const u64 out = e - D;                                                                   \
+        PD = pair_muladd(S2, mul, kwn) + r;                                                      \
+        D = pair_muladd(r, mul, 0);                                                              \
+        r = pair_exchange(out);                                                                  \
+        S3 = S2; S2 = S1; S1 = S0; S0 = e;                                                       \
+    }
+#pragma unroll 1
+                for (int grp = 0; grp < 5; grp++) {
+                    volatile u64 *const k = kin + 16 * grp;
+                    SNAPGPU_PAIR_ITER_X(k, 0)  SNAPGPU_PAIR_ITER_X(k, 1)  SNAPGPU_PAIR_ITER_X(k, 2)  SNAPGPU_PAIR_ITER_X(k, 3)
+                    SNAPGPU_PAIR_ITER_X(k, 4)  SNAPGPU_PAIR_ITER_X(k, 5)  SNAPGPU_PAIR_ITER_X(k, 6)  SNAPGPU_PAIR_ITER_X(k, 7)
+                    SNAPGPU_PAIR_ITER_X(k, 8)  SNAPGPU_PAIR_ITER_X(k, 9)  SNAPGPU_PAIR_ITER_X(k, 10) SNAPGPU_PAIR_ITER_X(k, 11)
+                    SNAPGPU_PAIR_ITER_X(k, 12) SNAPGPU_PAIR_ITER_X(k, 13) SNAPGPU_PAIR_ITER_X(k, 14) SNAPGPU_PAIR_ITER_X(k, 15)
+                }
+                const u64 e0 = S0, e1 = S1, e2 = S2, e3 = S3;      // role 0 is done after iteration 79; role 1 needs two more
+                {
+                    volatile u64 *const k = kin + 80;
+                    SNAPGPU_PAIR_ITER_X(k, 0)  SNAPGPU_PAIR_ITER_X(k, 1)
+                }
+#undef SNAPGPU_PAIR_ITER_X
+                if (b < my_blocks) {
+                    st[0] += role ? S0 : e0;
+                    st[1] += role ? S1 : e1;
+                    st[2] += role ? S2 : e2;
+                    st[3] += role ? S3 : e3;
+                }
+                __syncwarp();                              // this step's slot may be overwritten once every lane has read it
+                if (lane == 0) st_volatile_shared(consumed, b + 1);
+                continue;
+            }
 
             // prologue.  role 1 publishes d and c, and the seed that makes its second idle iteration
             // produce a (the first one's, which produces b, it keeps in a register); its window
             // starts as (c, d, 0).  Ordered so that every load sits well behind the store it needs.
+            __syncwarp();                                  // convergence point (see the template's comment)
             const u64 kw0 = kin[0];
             seed_a[0] = st[3];
             seed_a[1] = st[2];
@@ -175,6 +244,7 @@ sha512_pair_kernel(const uint8_t *__restrict__ data, const SegDesc *__restrict__
 #pragma unroll 1
             for (int grp = 0; grp < 5; grp++) {
                 volatile u64 *const k = kin + 16 * grp, *const d = din + 16 * grp, *const o = out + 16 * grp;
+                __syncwarp();                              // convergence point: the 16 rounds below are branch-free
                 SNAPGPU_PAIR_ITER(k, d, o, 0)  SNAPGPU_PAIR_ITER(k, d, o, 1)
                 SNAPGPU_PAIR_ITER(k, d, o, 2)  SNAPGPU_PAIR_ITER(k, d, o, 3)
                 SNAPGPU_PAIR_ITER(k, d, o, 4)  SNAPGPU_PAIR_ITER(k, d, o, 5)
@@ -188,6 +258,7 @@ sha512_pair_kernel(const uint8_t *__restrict__ data, const SegDesc *__restrict__
             const u64 e0 = S0, e1 = S1, e2 = S2, e3 = S3;
             {
                 volatile u64 *const k = kin + 80, *const d = din + 80, *const o = out + 80;
+                __syncwarp();
                 SNAPGPU_PAIR_ITER(k, d, o, 0)  SNAPGPU_PAIR_ITER(k, d, o, 1)
             }
 #undef SNAPGPU_PAIR_ITER

@@ -204,6 +204,7 @@ struct Options {
                                                 // (experimental)
     std::atomic<long long> feeders{0};          // bounce-buffer threads per device for pageable input, 0 = auto
     std::atomic<long long> long_kernel{2};      // 0 off, 1 one lane per file, 2 a lane pair per file
+    std::atomic<long long> pair_form{0};        // lane-pair kernel: 0 lanes exchange through mailboxes, 1 by shuffle
 };
 
 // devs is written only by snapgpu_init / snapgpu_shutdown, under mu AND devs_mu held exclusively;
@@ -302,6 +303,13 @@ static int init_pipe(Pipe &D, int ordinal, int sm_count) {
     return 0;
 }
 
+typedef void (*PairKernel)(const uint8_t *, const SegDesc *, u32, uint8_t *);
+// the lane-pair kernel by alignment and exchange form (sha512_pair.cuh): 0 mailboxes (default), 1 shuffle
+static PairKernel pair_kernel_for(bool aligned, int form) {
+    if (form == 1) return aligned ? sha512_pair_kernel<true, true> : sha512_pair_kernel<false, true>;
+    return aligned ? sha512_pair_kernel<true, false> : sha512_pair_kernel<false, false>;
+}
+
 static void destroy_device(Device &dev) {
     for (auto &p : dev.pipes)
         if (p) {
@@ -322,8 +330,10 @@ static int init_device(Device &dev, int ordinal) {
                     prop.major, prop.minor);
     SG_CUDA(cudaFuncSetAttribute(sha512_long_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytes));
     SG_CUDA(cudaFuncSetAttribute(sha512_long_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytes));
-    SG_CUDA(cudaFuncSetAttribute(sha512_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes));
-    SG_CUDA(cudaFuncSetAttribute(sha512_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes));
+    for (int form = 0; form < 2; form++) {
+        SG_CUDA(cudaFuncSetAttribute(pair_kernel_for(true, form), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes));
+        SG_CUDA(cudaFuncSetAttribute(pair_kernel_for(false, form), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes));
+    }
     for (auto &p : dev.pipes) {
         p.reset(new Pipe());
         int rc = init_pipe(*p, ordinal, dev.sm_count);
@@ -660,12 +670,8 @@ static int launch_sha512(Pipe &D, cudaStream_t stream, const uint8_t *d_data, Ge
         SG_CUDA(cudaStreamWaitEvent(long_stream, slot->fork, 0));
         if (R.opt.long_kernel.load() >= 2) {                // one chain per lane pair (sha512_pair.cuh)
             const u32 long_grid = (u32)((n_long + kPairFilesPerCta - 1) / kPairFilesPerCta);
-            if (aligned)
-                sha512_pair_kernel<true><<<long_grid, kLongThreads, kPairSmemBytes, long_stream>>>(
-                    d_data, plan.long_descs, (u32)n_long, d_digests);
-            else
-                sha512_pair_kernel<false><<<long_grid, kLongThreads, kPairSmemBytes, long_stream>>>(
-                    d_data, plan.long_descs, (u32)n_long, d_digests);
+            pair_kernel_for(aligned, (int)R.opt.pair_form.load())<<<long_grid, kLongThreads, kPairSmemBytes, long_stream>>>(
+                d_data, plan.long_descs, (u32)n_long, d_digests);
         } else {                                            // one chain per lane (sha512_long.cuh)
             const u32 long_grid = (u32)((n_long + kLongFilesPerCta - 1) / kLongFilesPerCta);
             if (aligned)
@@ -1601,6 +1607,9 @@ int snapgpu_set_option(const char *key, long long value) {
     } else if (k == "feeders") {
         if (value < 0 || value > kFeeders) return fail(SNAPGPU_EINVAL, "feeders out of range");
         o.feeders = value;
+    } else if (k == "pair_form") {
+        if (value < 0 || value > 1) return fail(SNAPGPU_EINVAL, "pair_form: 0 shared-memory mailboxes, 1 shuffle exchange");
+        o.pair_form = value;
     } else if (k == "long_kernel") {
         if (value < 0 || value > 2) return fail(SNAPGPU_EINVAL, "long_kernel: 0 off, 1 one lane per file, 2 lane pair per file");
         o.long_kernel = value;

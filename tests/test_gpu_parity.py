@@ -19,6 +19,7 @@ def default_options(gpu):
     gpu.set_option("sha_variant", 0)
     gpu.set_option("sha_warps_per_sm", 0)
     gpu.set_option("long_kernel", 2)
+    gpu.set_option("pair_form", 0)
     yield
 
 
@@ -241,13 +242,16 @@ def test_long_file_chain(gpu):
     assert dg[1].tobytes() == hashlib.sha512(synth.file_bytes(1, 100)).digest()
 
 
-@pytest.mark.parametrize("mode", [1, 2])
-def test_long_file_kernel(gpu, oracle, mode):
+@pytest.mark.parametrize("mode,pair_form", [(1, 0), (2, 0), (2, 1)])
+def test_long_file_kernel(gpu, oracle, mode, pair_form):
     """The long-file bin: files whose chain would dominate a launch leave the batched kernel when a
     launch has at most 256 of them -- mode 1 one lane per file (sha512_long.cuh), mode 2 a lane pair
-    per file (sha512_pair.cuh).  Same digests with the bin switched off, and both equal the oracle."""
+    per file (sha512_pair.cuh), its lanes exchanging through shared-memory mailboxes (pair_form 0, the
+    default) or by warp shuffle (pair_form 1).  Same digests with the bin switched off, and all equal the
+    oracle."""
     from snappy_b200 import helpers
     gpu.set_option("long_kernel", mode)
+    gpu.set_option("pair_form", pair_form)
     rng = np.random.default_rng(21)
     MiB = 1 << 20
     cases = [

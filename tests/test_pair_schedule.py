@@ -115,6 +115,57 @@ def test_pair_schedule_matches_hashlib():
         assert sha512_pair(m) == hashlib.sha512(m).digest(), n
 
 
+# ---- the shuffle form (sha512_pair.cuh, kShuffle): the lanes exchange through a warp shuffle -------------------
+
+def compress_pair_shuffle(state, ring):
+    """Same two-lane round, but what a lane needs from its partner -- always the value the partner
+    produced in the PREVIOUS iteration -- arrives by an exchange at the end of every iteration
+    (__shfl_xor_sync with lane mask 1) instead of through shared-memory mailboxes.  Lane 1 loads a
+    zero where lane 0 loads W+K, so that both form PD = S2*mul + kw + r."""
+    st = [state[4:8], state[0:4]]
+    a, b, c, d = st[1]
+    seed0 = (b - pair_sigma(c, 1) - pair_f(c, d, 0, 1)) & M            # iteration 0 of lane 1 produces b
+    seed1 = (a - pair_sigma(b, 1) - pair_f(b, c, d, 1)) & M            # iteration 1 of lane 1 produces a
+    win = [list(st[0]), [c, d, 0, 0]]
+    # prologue exchange: lane 0 gets d and c from lane 1 (two shuffles per block)
+    D = [d * MUL[0], 0 * MUL[1]]                       # D = (what the partner sent two iterations ago) * mul
+    r = [c, seed1]                                     # what the partner "sent" before iteration 0
+    PD = [(win[0][3] + ring[0] + D[0]) & M, seed0]
+    final0 = None
+    for i in range(82):
+        kw = [ring[i + 1] if i + 1 < 80 else 0xdeadbeef, 0]            # lane 1 reads the zero array
+        out = []
+        for l in (0, 1):
+            s0, s1, s2, s3 = win[l]
+            e = (pair_sigma(s0, l) + pair_f(s0, s1, s2, l) + PD[l]) & M
+            out.append((e - D[l]) & M)
+            PD[l] = (s2 * MUL[l] + kw[l] + r[l]) & M
+            D[l] = (r[l] * MUL[l]) & M
+            win[l] = [e, s0, s1, s2]
+        r = [out[1], out[0]]                           # the exchange
+        if i == 79:
+            final0 = list(win[0])
+    efgh = [(x + y) & M for x, y in zip(st[0], final0)]
+    abcd = [(x + y) & M for x, y in zip(st[1], win[1])]
+    return abcd + efgh
+
+
+def sha512_pair_shuffle(msg):
+    n = len(msg)
+    msg = msg + b"\x80" + b"\0" * ((111 - n) % 128) + (8 * n).to_bytes(16, "big")
+    s = list(IV)
+    for o in range(0, len(msg), 128):
+        s = compress_pair_shuffle(s, producer(msg[o:o + 128]))
+    return b"".join(x.to_bytes(8, "big") for x in s)
+
+
+def test_shuffle_form_matches_hashlib():
+    rng = np.random.default_rng(4)
+    for n in (0, 1, 3, 111, 112, 127, 128, 129, 1000, 4096, 5001):
+        m = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert sha512_pair_shuffle(m) == hashlib.sha512(m).digest(), n
+
+
 # ---- design check for the next step (DESIGN.md section 10): no pipeline refill between blocks ----------------
 
 def sha512_pair_continuous(msg):

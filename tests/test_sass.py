@@ -98,11 +98,13 @@ def test_probe_kernels_issue_what_they_claim(sass, kind, opcode, least):
 
 
 def test_pair_kernel_round_loop(native):
-    """sha512_pair_kernel: the 16-round loop of the consumer has ~17 ALU instructions per round (28 in the
-    one-lane consumer), talks through shared memory only (two LDS.64 + one STS.64 per round, no shuffle,
-    no divergence check) and does not spill."""
+    """sha512_pair_kernel, mailbox form (the default): the 16-round loop of the consumer has ~17 ALU
+    instructions per round (28 in the one-lane consumer) and talks through shared memory only.  The
+    exchange is safe because the loop body is ONE convergence check (the BRA.DIV of __syncwarp) followed
+    by branch-free code in which the volatile accesses keep their order -- load, load, store per round, so
+    every mailbox store sits ahead of the partner's load in the next round.  No spills."""
     text = subprocess.run(["cuobjdump", "-sass", str(native.LIB_PATH)], capture_output=True, text=True, check=True).stdout
-    body = [p for p in text.split("Function : ") if p.startswith("_ZN7snapgpu18sha512_pair_kernelILb1E")]
+    body = [p for p in text.split("Function : ") if p.startswith("_ZN7snapgpu18sha512_pair_kernelILb1ELb0E")]
     assert len(body) == 1
     insts = []
     for line in body[0].splitlines():
@@ -113,7 +115,7 @@ def test_pair_kernel_round_loop(native):
     # loops = backward branches; the round loop is the one whose body holds 16 STS.64 and 32 LDS.64
     loops = []
     for addr, op, rest in insts:
-        if op.startswith("BRA"):
+        if op.startswith("BRA") and not op.startswith("BRA.DIV"):
             m = re.search(r"0x([0-9a-f]+)", rest)
             if m and int(m.group(1), 16) < addr:
                 loops.append((int(m.group(1), 16), addr))
@@ -125,7 +127,22 @@ def test_pair_kernel_round_loop(native):
                 and len(ops) < 500):
             found = True
             assert sum(op.startswith("SHF.R.W") for op in ops) == 16 * 6
-            assert not any(op.startswith(("SHFL", "BRA.DIV", "WARPSYNC", "BAR")) for op in ops)
+            assert not any(op.startswith(("SHFL", "WARPSYNC", "BAR", "BSSY", "BSYNC", "CALL", "RET", "EXIT")) for op in ops)
+            branches = [op for op in ops if op.startswith(("BRA", "BRX", "JMP"))]
+            assert sorted(branches) == ["BRA", "BRA.DIV"], branches          # the back edge and one convergence check
+            assert ops.index("BRA.DIV") < next(i for i, op in enumerate(ops) if op.startswith(("LDS", "STS")))
+            mem = ["L" if op.startswith("LDS") else "S" for op in ops if op.startswith(("LDS.64", "STS.64"))]
+            assert "".join(mem) == "LLS" * 16, "".join(mem)
             n_alu = sum(bool(alu.match(op)) for op in ops)
             assert n_alu <= 16 * 17.5, n_alu
     assert found
+
+
+def test_pair_kernel_shuffle_form(native):
+    """The cross-check form (pair_form 1): the lanes exchange by SHFL.BFLY, two per round, and the round
+    loop stores nothing to shared memory."""
+    text = subprocess.run(["cuobjdump", "-sass", str(native.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    body = [p for p in text.split("Function : ") if p.startswith("_ZN7snapgpu18sha512_pair_kernelILb1ELb1E")]
+    assert len(body) == 1
+    ops = re.findall(r"/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", body[0])
+    assert ops.count("SHFL.BFLY") >= 2 * 18 and not any(op.startswith(("LDL", "STL")) for op in ops)

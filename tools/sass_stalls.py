@@ -73,6 +73,12 @@ print(f"loop 0x{best[0]:x}..0x{best[1]:x}: {len(loop)} instructions, ALU {n_alu}
       f"other {len(loop) - n_alu - n_fma - n_wide}")
 print(f"sum of stall counts = {stalls} cycles/iteration (single warp); ALU-pipe bound = {2 * n_alu}")
 print("stall histogram:", dict(sorted(hist.items())))
-if "--dump" in sys.argv:
+if "--range" in sys.argv:              # --range 0xb70 0x2520: the control words of an address range
+    k = sys.argv.index("--range")
+    lo_, hi_ = int(sys.argv[k + 1], 16), int(sys.argv[k + 2], 16)
+    for x in insts:
+        if lo_ <= x[0] <= hi_:
+            print(f"{x[0]:06x} s{x[3]:2d} {'Y' if x[4] else ' '} {x[2]}")
+elif "--dump" in sys.argv:
     for x in loop:
         print(f"{x[0]:06x} s{x[3]:2d} {'Y' if x[4] else ' '} {x[2]}")
