@@ -48,8 +48,7 @@ const char *snapgpu_version(void);
  * "cmp_ctas_per_sm", "time_kernels", "feeders" (host threads per device that bounce pageable
  * input into pinned memory, 0 = auto), "long_kernel" (the long-file bin: 0 off, 1 one lane per
  * file, 2 a lane pair per file = default), "pair_form" (how the two lanes of a pair exchange round results:
- * 0 shared-memory mailboxes = default, 1 warp shuffle; sha512_pair.cuh), "balance" (experimental: balance unit claims between
- * SM sub-partitions when several CTAs share an SM, default 0). */
+ * 0 shared-memory mailboxes = default, 1 warp shuffle; sha512_pair.cuh). */
 int snapgpu_set_option(const char *key, long long value);
 
 /* C-owned pinned host memory for the Go side to pack file contents into

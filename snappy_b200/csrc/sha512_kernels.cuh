@@ -103,8 +103,7 @@ template <int kRoundFma, int kSchedFma, bool kAligned16, int kCtasPerSm>
 __global__ void __launch_bounds__(kShaThreads, kCtasPerSm)
 sha512_segments_kernel(const uint8_t *__restrict__ data, const SegDesc *__restrict__ descs,
                        const u32 *__restrict__ order, u32 nsegs,
-                       uint8_t *__restrict__ digests, u32 *__restrict__ unit_counter, u32 one,
-                       unsigned long long * /*balance*/, u32 /*nsmsp*/) {
+                       uint8_t *__restrict__ digests, u32 *__restrict__ unit_counter, u32 one) {
     const u32 lane = threadIdx.x & 31;
     const u32 warp = threadIdx.x >> 5;
     const u32 nunits = (nsegs + 31) >> 5;
@@ -260,46 +259,20 @@ template <int kAddMode, int kCtasPerSm, bool kAligned16 = true>
 __global__ void __launch_bounds__(kShaThreads, kCtasPerSm)
 sha512_segments_kernel_v2(const uint8_t *__restrict__ data, const SegDesc *__restrict__ descs,
                           const u32 *__restrict__ order, u32 nsegs,
-                          uint8_t *__restrict__ digests, u32 *__restrict__ unit_counter, u32 one,
-                          unsigned long long *__restrict__ balance, u32 nsmsp) {
+                          uint8_t *__restrict__ digests, u32 *__restrict__ unit_counter, u32 one) {
     constexpr int kStage = kAligned16 ? kStageBytesPerWarp : kStageBytesPerWarpAny;
     __shared__ __align__(16) uint8_t stages[kShaWarpsPerCta][2][kStage];
     const u32 lane = threadIdx.x & 31;
     const u32 warp = threadIdx.x >> 5;
     const u32 nunits = (nsegs + 31) >> 5;
     const u32 stage0 = (u32)__cvta_generic_to_shared(&stages[warp][0][0]);
-    // With balancing on, every unit -- the first one included -- is claimed from the counter in arrival order.  CTAs are
-    // placed one wave at a time (one per SM, then the next one per SM, ...), so the first wave -- whose
-    // warps hold the lowest hardware slots and get most of their sub-partition's ALU pipe -- takes the
-    // longest units of the length-sorted order, one per sub-partition, the second wave the next tier,
-    // and every sub-partition starts with the same mix whichever CTAs end up sharing an SM.  (The
-    // static first assignment by warp index of the default path gives three sub-partitions of each SM
-    // the longest files and the fourth the shortest of the first wave.)
-    const u32 total_warps = balance ? 0u : gridDim.x * kShaWarpsPerCta;   // units handed out before the counter starts
+    // The first unit of every warp is assigned statically, the others are claimed from a counter in
+    // the order of the length-sorted plan (longest first): list scheduling.  (A variant that also
+    // balanced the claims between SM sub-partitions with bounded spin-waits was measured in round 1
+    // -- better on some mixed batches, worse on config 2, different from process to process -- and
+    // has been removed: no wait loop lives in this kernel.)
+    const u32 total_warps = gridDim.x * kShaWarpsPerCta;   // units handed out before the counter starts
     u32 unit = warp * gridDim.x + blockIdx.x;
-    if (balance) {
-        if (lane == 0) unit = atomicAdd(unit_counter, 1u);
-        unit = __shfl_sync(0xffffffffu, unit, 0);
-    }
-    // Load balance between SM sub-partitions when several CTAs share an SM (balance != nullptr).
-    // A sub-partition is the real processor here and its warps are claim slots: it does not share
-    // its ALU pipe evenly -- the warp of the CTA placed first gets ~83 % of it, in this kernel as in
-    // a register-only loop (tools/warp_trace_probe.py, tools/arb_probe.cu) -- so a long unit
-    // claimed by a slow slot is a backlog its sub-partition carries to the end while the fast slot
-    // keeps claiming, and work cannot move between sub-partitions once claimed.  balance[0] counts
-    // the blocks claimed by the whole launch, balance[1] the sub-partitions that have claimed
-    // anything, balance[2 + q] the blocks claimed by sub-partition q; a warp does not claim while
-    // its sub-partition is more than kBalanceSlack blocks ahead of the mean (its other warps work
-    // meanwhile).  A warp's waits are bounded by a budget for the whole launch (~8 ms of sleeping), so
-    // that nothing here can hang or crawl.
-    constexpr u32 kBalanceSlack = 32;
-    u32 smsp = 0xffffffffu, wait_budget = 8192;
-    if (balance) {
-        u32 smid, hw;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        asm volatile("mov.u32 %0, %%warpid;" : "=r"(hw));
-        if (smid * 4 + 3 < nsmsp) smsp = smid * 4 + (hw & 3);
-    }
 #ifdef SNAPGPU_TRACE_WARPS
     unsigned long long tr_start, tr_units = 0, tr_blocks = 0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_start));
@@ -319,10 +292,6 @@ sha512_segments_kernel_v2(const uint8_t *__restrict__ data, const SegDesc *__res
         }
         const u32 nblk = have ? (u32)seg_blocks(sd.len, sd.flags) : 0u;
         const u32 nblk_max = __reduce_max_sync(0xffffffffu, nblk);
-        if (smsp != 0xffffffffu && lane == 0 && nblk_max) {
-            if (atomicAdd(balance + 2 + smsp, (unsigned long long)nblk_max) == 0) atomicAdd(balance + 1, 1ull);
-            atomicAdd(balance, (unsigned long long)nblk_max);
-        }
 #ifdef SNAPGPU_TRACE_WARPS
         tr_units++;
         tr_blocks += nblk_max;
@@ -410,20 +379,7 @@ sha512_segments_kernel_v2(const uint8_t *__restrict__ data, const SegDesc *__res
         }
 
         u32 next = 0;
-        if (lane == 0) {
-            if (smsp != 0xffffffffu) {
-                // wait while this sub-partition is ahead of the others
-                for (; wait_budget; wait_budget--) {
-                    const unsigned long long mine = *reinterpret_cast<volatile unsigned long long *>(balance + 2 + smsp);
-                    const unsigned long long all = *reinterpret_cast<volatile unsigned long long *>(balance);
-                    const unsigned long long active = *reinterpret_cast<volatile unsigned long long *>(balance + 1);
-                    if (mine * active <= all + (unsigned long long)kBalanceSlack * active) break;
-                    if (*reinterpret_cast<volatile u32 *>(unit_counter) + total_warps >= nunits) break;   // nothing left
-                    __nanosleep(1000);
-                }
-            }
-            next = atomicAdd(unit_counter, 1u) + total_warps;
-        }
+        if (lane == 0) next = atomicAdd(unit_counter, 1u) + total_warps;
         unit = __shfl_sync(0xffffffffu, next, 0);
     }
 #ifdef SNAPGPU_TRACE_WARPS

@@ -78,7 +78,7 @@ std::string hex_lower(const uint8_t *p, size_t n) {
 
 constexpr int kPlanSlots = 4;
 constexpr int kStageBufs = 4;
-constexpr size_t kCounterBytes = 64 + 8 * (2 + 4 * 256);   // unit counter | balance[2 + sub-partitions] (up to 256 SMs)
+constexpr size_t kCounterBytes = 64;                     // the launch's unit counter
 constexpr int kFeeders = 8;                     // at most this many host threads move pageable memory into pinned bounce buffers
 constexpr size_t kBounceBytes = 4u << 20;
 constexpr size_t kMaxChunkItems = 1u << 20;
@@ -200,8 +200,6 @@ struct Options {
     std::atomic<long long> sha_variant{0};
     std::atomic<long long> cmp_ctas_per_sm{0};
     std::atomic<long long> time_kernels{1};
-    std::atomic<long long> balance{0};          // balance claims between SM sub-partitions when CTAs share an SM
-                                                // (experimental)
     std::atomic<long long> feeders{0};          // bounce-buffer threads per device for pageable input, 0 = auto
     std::atomic<long long> long_kernel{2};      // 0 off, 1 one lane per file, 2 a lane pair per file
     std::atomic<long long> pair_form{0};        // lane-pair kernel: 0 lanes exchange through mailboxes, 1 by shuffle
@@ -427,7 +425,7 @@ static bool trace_on() {
     return on;
 }
 
-typedef void (*ShaKernel)(const uint8_t *, const SegDesc *, const u32 *, u32, uint8_t *, u32 *, u32, unsigned long long *, u32);
+typedef void (*ShaKernel)(const uint8_t *, const SegDesc *, const u32 *, u32, uint8_t *, u32 *, u32);
 
 constexpr int kShaCtasPerSmMax = 3;   // 168 registers per thread: no spills with the one-block-ahead prefetch
 constexpr int kShaVariants = 6;
@@ -687,12 +685,7 @@ static int launch_sha512(Pipe &D, cudaStream_t stream, const uint8_t *d_data, Ge
         R.sha_long_launches++;
     }
     if (n_main) {
-        // several CTAs per SM: claims are balanced between SM sub-partitions (sha512_kernels.cuh)
-        unsigned long long *balance = nullptr;
-        if (grid > (u32)D.sm_count && D.sm_count <= 256 && R.opt.balance.load())
-            balance = reinterpret_cast<unsigned long long *>(reinterpret_cast<uint8_t *>(slot->d_counter) + 64);
-        k<<<grid, kShaThreads, 0, stream>>>(d_data, plan.descs, plan.order, (u32)n, d_digests, slot->d_counter, 1u, balance,
-                                            (u32)D.sm_count * 4);
+        k<<<grid, kShaThreads, 0, stream>>>(d_data, plan.descs, plan.order, (u32)n, d_digests, slot->d_counter, 1u);
         SG_CUDA(cudaGetLastError());
         R.kernel_launches++;
     }
@@ -1602,8 +1595,6 @@ int snapgpu_set_option(const char *key, long long value) {
         o.cmp_ctas_per_sm = value;
     } else if (k == "time_kernels") {
         o.time_kernels = value ? 1 : 0;
-    } else if (k == "balance") {
-        o.balance = value ? 1 : 0;
     } else if (k == "feeders") {
         if (value < 0 || value > kFeeders) return fail(SNAPGPU_EINVAL, "feeders out of range");
         o.feeders = value;

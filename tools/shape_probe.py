@@ -37,9 +37,8 @@ for name, lengths in cases.items():
     blocks = synth.blocks(lengths)
     row = {"lengths": name, "files": len(lengths), "max_over_mean_blocks": round(float(blocks.max() / blocks.mean()), 2),
            "depth": round(float(blocks.sum() / (148 * 128 * blocks.max())), 2)}
-    for bal in (1, 0):
-        N.set_option("balance", bal)
-        for r in ((0, 1, 2, 3) if bal else (2, 3)):
+    for bal in (1,):                       # (round 1 also ran an opt-in "balance" mode here; it has been removed)
+        for r in (0, 1, 2, 3):
             N.set_option("sha_warps_per_sm", r)
             dg = torch.empty((len(lengths), 64), dtype=torch.uint8, device="cuda:0")
             for _ in range(2):
@@ -54,6 +53,5 @@ for name, lengths in cases.items():
             key = ("auto" if r == 0 else f"R{r}") + ("" if bal else " unbalanced")
             row[key] = round(int(blocks.sum()) * 3568 / (ms * 1e-3) / PEAK, 4)
             print("   ", name, key, row[key], file=sys.stderr, flush=True)
-    N.set_option("balance", 0)
     print(json.dumps(row), flush=True)
     del d
