@@ -122,6 +122,15 @@ int snapgpu_write_hashes(const char *build_dir, const char *data_tar);
  * verification mode. */
 int snapgpu_hashes_yaml(const char *build_dir, const char *data_tar, char **out, size_t *out_len);
 
+/* writeHashes when archive-sha512 is known already: clickdeb.Build writes data.tar.gz through gzip -9
+ * (clickdeb/deb.go:261-285,360-366) far slower than one SHA-512 chain runs on the GPU, so a
+ * snapgpu_hasher fed by an io.MultiWriter beside the file has the digest the moment the archive is
+ * closed, and the callback (snappy/build.go:517-520) passes it here instead of the file name.  The
+ * finished archive is not read again; everything else is snapgpu_write_hashes / snapgpu_hashes_yaml. */
+int snapgpu_write_hashes_digest(const char *build_dir, const uint8_t archive_sha512[64]);
+int snapgpu_hashes_yaml_digest(const char *build_dir, const uint8_t archive_sha512[64], char **out,
+                               size_t *out_len);
+
 /* Phases of the most recent snapgpu_write_hashes / snapgpu_hashes_yaml / snapgpu_verify_hashes
  * made by the calling thread (bench support).  Directory scan, file reads, host-to-device
  * copies and kernels overlap inside pack_ms; the tails are what was left to wait for after the

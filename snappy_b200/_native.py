@@ -81,6 +81,8 @@ SIGNATURES = {
     "snapgpu_sha512sum_file": (_i, [_cp, _cp]),
     "snapgpu_write_hashes": (_i, [_cp, _cp]),
     "snapgpu_hashes_yaml": (_i, [_cp, _cp, _pp, _psz]),
+    "snapgpu_write_hashes_digest": (_i, [_cp, _vp]),
+    "snapgpu_hashes_yaml_digest": (_i, [_cp, _vp, _pp, _psz]),
     "snapgpu_tree_stats": (_i, [ctypes.POINTER(TreeStats)]),
     "snapgpu_files_are_equal": (_i, [_cp, _cp]),
     "snapgpu_dir_updated": (_i, [_cp, _cp, _cp, _pp, _psz]),

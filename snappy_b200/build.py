@@ -66,6 +66,17 @@ def digest_cache_stats() -> tuple[int, int]:
     return entries.value, hits.value
 
 
+def hashes_yaml_digest(buildDir: str, archiveSha512: bytes) -> bytes:
+    """writeHashes with archive-sha512 already known (streamed through ``helpers.Sha512Stream`` while
+    data.tar.gz was being written, clickdeb/deb.go:360-366): the archive is not read again."""
+    assert len(archiveSha512) == 64
+    buf = ctypes.create_string_buffer(archiveSha512, 64)
+    ptr, length = ctypes.c_void_p(), ctypes.c_size_t()
+    _raise(N.lib().snapgpu_hashes_yaml_digest(N.fs(buildDir), ctypes.cast(buf, ctypes.c_void_p), ctypes.byref(ptr),
+                                              ctypes.byref(length)))
+    return N.take_string(ptr, length.value)
+
+
 def hashes_yaml(buildDir: str, dataTar: str) -> bytes:
     ptr, length = ctypes.c_void_p(), ctypes.c_size_t()
     _raise(N.lib().snapgpu_hashes_yaml(N.fs(buildDir), N.fs(dataTar), ctypes.byref(ptr), ctypes.byref(length)))

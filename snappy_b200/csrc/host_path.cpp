@@ -1438,7 +1438,10 @@ thread_local TreeStats g_tree_stats;
 
 // data_tar == nullptr (verification without the archive): the archive digest is left zero.
 // make_debian: create DEBIAN/ first as writeHashes does (build.go:218-219); verification does not.
-int build_tree_doc(const std::string &build_dir, const std::string *data_tar, bool make_debian, TreeDoc *doc) {
+// known_archive (optional): archive-sha512 computed already -- by a snapgpu_hasher that saw the
+// archive's bytes while they were being written -- so the finished file is not read again.
+int build_tree_doc(const std::string &build_dir, const std::string *data_tar, bool make_debian, TreeDoc *doc,
+                   const uint8_t *known_archive = nullptr) {
     const double t0 = wall_ms();
     // build.go:218-226: DEBIAN/ is made, then the archive is hashed, and only then the tree is
     // walked -- an archive that cannot be opened is reported before any error of the walk (and
@@ -1457,7 +1460,8 @@ int build_tree_doc(const std::string &build_dir, const std::string *data_tar, bo
     uint8_t archive_op = 0;
     TreeHasher tree(build_dir, true);
     tree.chains.start();
-    if (data_tar) tree.chains.add(*data_tar, archive_digest, &archive_err, &archive_op);
+    if (known_archive) memcpy(archive_digest, known_archive, 64);
+    else if (data_tar) tree.chains.add(*data_tar, archive_digest, &archive_err, &archive_op);
     rc = tree.run();
     const double t1 = wall_ms();
     const int chain_rc = tree.chains.finish();
@@ -2079,6 +2083,27 @@ int snapgpu_hashes_yaml(const char *build_dir, const char *data_tar, char **out,
     const std::string tar = data_tar;
     TreeDoc doc;
     int rc = build_tree_doc(clean_dir(build_dir), &tar, true, &doc);
+    if (rc) return rc;
+    *out = doc.buf;
+    *out_len = doc.len;
+    return 0;
+}
+
+int snapgpu_write_hashes_digest(const char *build_dir, const uint8_t archive_sha512[64]) {
+    if (!build_dir || !archive_sha512) return fail(SNAPGPU_EINVAL, "null argument");
+    const std::string dir = clean_dir(build_dir);
+    TreeDoc doc;
+    int rc = build_tree_doc(dir, nullptr, true, &doc, archive_sha512);
+    if (rc) return rc;
+    rc = write_file_0644(dir + "/DEBIAN/hashes.yaml", doc.buf, doc.len);
+    free(doc.buf);
+    return rc;
+}
+
+int snapgpu_hashes_yaml_digest(const char *build_dir, const uint8_t archive_sha512[64], char **out, size_t *out_len) {
+    if (!build_dir || !archive_sha512 || !out || !out_len) return fail(SNAPGPU_EINVAL, "null argument");
+    TreeDoc doc;
+    int rc = build_tree_doc(clean_dir(build_dir), nullptr, true, &doc, archive_sha512);
     if (rc) return rc;
     *out = doc.buf;
     *out_len = doc.len;

@@ -113,6 +113,7 @@ constexpr size_t kLargeChunk = (size_t)32 << 20;     // files up to kMidMax, a f
 constexpr size_t kMidMax = (size_t)16 << 20;         // longer files are chains of their own (ChainStreamer)
 constexpr size_t kChunkSlack = 256;
 constexpr size_t kTreeBatchBytes = (size_t)64 << 20; // one batch of the tree hasher: at least two large chunks
+constexpr size_t kHungryFlush = (size_t)384 << 10;   // a worker hands over a chunk this full when the GPU is idle
 
 struct PackedRef {
     uint8_t *digest;       // where the digest goes (a TEntry's)
@@ -835,6 +836,9 @@ private:
             }
             c->files.push_back(PackedRef{e.digest, (uint32_t)c->used, (uint32_t)got});
             c->used += align_up(got + 1);
+            // the GPU has nothing to do (the start of a tree, or a slow disk): do not sit on a
+            // chunk until it is full
+            if (hungry_.load(std::memory_order_relaxed) && c->used >= kHungryFlush) flush_chunk(W, cls);
         }
         if (dfd_in < 0) ::close(dfd);
         nhashed_ += hashed;
@@ -902,6 +906,7 @@ private:
                 }
                 all_done = workers_done_ == nworkers && ready_.empty();
             }
+            hungry_.store(take.empty() && session_in_flight(session_) == 0, std::memory_order_relaxed);
             if (!take.empty()) {
                 spans.clear();
                 segs.clear();
@@ -1001,7 +1006,7 @@ private:
     std::condition_variable q_cv_;
     std::deque<Task> queue_;
     size_t pending_ = 0;
-    std::atomic<bool> abort_{false};
+    std::atomic<bool> abort_{false}, hungry_{true};
     // ready chunks
     std::mutex r_mu_;
     std::condition_variable r_cv_, chunk_cv_;

@@ -880,3 +880,31 @@ def test_concurrent_callers_overlap(gpu, oracle):
     spot = [0, 1, n // 2, n - 1]
     assert np.array_equal(out["b"][spot], oracle.sha512_batch(bulk, b_off[spot], b_len[spot], 1))
     assert best_both < 0.9 * best_serial, (best_both, best_serial)
+
+
+def test_archive_hashed_while_written_then_write_hashes_with_the_digest(gpu, oracle, tmp_path):
+    """The flow of INTEGRATION.md section 3b: data.tar.gz goes through an io.MultiWriter(file, hasher)
+    while tar | gzip produces it (clickdeb/deb.go:261-285), and writeHashes gets the digest instead of
+    the file name (snapgpu_hashes_yaml_digest): the document equals the one made from the finished file."""
+    import subprocess
+    from snappy_b200 import build, helpers
+    from test_hostsim import make_mixed_tree
+    rng = np.random.default_rng(17)
+    tree = tmp_path / "tree"
+    make_mixed_tree(tree, rng, nfiles=150)
+    tar = tmp_path / "data.tar.gz"
+    h = helpers.Sha512Stream()
+    p = subprocess.Popen(["tar", "-C", str(tree), "-cz", "."], stdout=subprocess.PIPE)
+    with open(tar, "wb") as f:
+        while True:
+            piece = p.stdout.read(1 << 16)
+            if not piece:
+                break
+            f.write(piece)
+            h.Write(piece)
+    assert p.wait() == 0
+    digest = h.Sum()
+    assert digest.hex() == oracle.sha512sum(str(tar))
+    want = oracle.write_hashes(str(tree), str(tar))
+    assert build.hashes_yaml_digest(str(tree), digest) == want
+    assert build.hashes_yaml(str(tree), str(tar)) == want
