@@ -79,7 +79,7 @@ int snapgpu_sha512_stream(uint8_t state[64], int first, const uint8_t *data, uin
 /* The same as an object with the method set of Go's hash.Hash, for io.Copy(hasher, r)
  * (helpers/helpers.go:195-196) or io.MultiWriter(tarball, hasher) while data.tar.gz is being
  * written (clickdeb/deb.go:360-366 -> snappy/build.go:222): Write gathers bytes in pinned
- * memory and hashes each full 4 MiB piece on a worker thread while the caller goes on writing;
+ * memory and hashes each full 512 KiB piece on a worker thread while the caller goes on writing;
  * Sum returns the digest of everything written so far without disturbing the state. */
 typedef struct snapgpu_hasher snapgpu_hasher;
 snapgpu_hasher *snapgpu_hasher_new(void);                                     /* sha512.New()  */
@@ -98,8 +98,10 @@ int snapgpu_cmp_batch(const uint8_t *a, const uint8_t *b, const uint64_t *offset
  * Same contracts, but `d_data`/`d_a`/`d_b`/`d_digests`/`d_equal` are device pointers on
  * bound device number `dev` (index into the snapgpu_init list) and the work is enqueued on
  * `stream` (a cudaStream_t passed as void*; NULL = the legacy default stream).  offsets and
- * lengths stay host arrays (they come from stat(2)).  The allocation behind d_data must
- * extend to the next 16-byte boundary past the last file.  Returns after enqueueing.
+ * lengths stay host arrays (they come from stat(2)).  The allocations behind d_data, d_a
+ * and d_b must extend to the next 16-byte boundary past the last file or pair: the aligned
+ * kernels read whole 16-byte words (bytes past an item's end never reach a digest or a
+ * verdict).  cudaMalloc'd buffers always do.  Returns after enqueueing.
  */
 int snapgpu_sha512_batch_device(int dev, const void *d_data, const uint64_t *offsets,
                                 const uint64_t *lengths, size_t nfiles, void *d_digests,

@@ -1739,7 +1739,10 @@ int dir_updated(const std::string &dir_a, const std::string &dir_b, const std::s
 // when the serial chain on the GPU is slower than the producer of the bytes.
 // ------------------------------------------------------------------------------------------
 
-constexpr size_t kHasherBuffer = 4u << 20;      // multiple of 128
+// Piece size: one piece is ~7 ms of chain (70 MB/s).  Small enough that a writer slower than the
+// chain -- gzip -9 producing data.tar.gz -- leaves almost nothing for Sum() to wait for, large
+// enough that the ~0.1 ms of a GPU call per piece does not show.
+constexpr size_t kHasherBuffer = 512u << 10;    // multiple of 128
 
 }  // namespace
 }  // namespace snapgpu

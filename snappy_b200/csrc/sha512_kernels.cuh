@@ -327,9 +327,12 @@ sha512_segments_kernel_v2(const uint8_t *__restrict__ data, const SegDesc *__res
             for (u32 r = 0; r < 4; r++) delta[r] = lane * 16u + (ws + r < 4 ? (ws + r) * 4u : 512u + (ws + r - 4) * 4u);
             prmt_sel = (bs + 3) | ((bs + 2) << 4) | ((bs + 1) << 8) | (bs << 12);
         }
+        // source address of the copies that read nothing (src-size 0): cp.async wants it 16-byte
+        // aligned all the same, and `data` need not be on the any-alignment path
+        const uint8_t *const safe = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(data) & ~(uintptr_t)15);
         auto stage = [&](u32 addr, const uint8_t *q, long long left) {
-            if (kAligned16) stage_block(addr, lane, q, left, data);
-            else stage_block_any(addr, lane, q, left > 0 ? (long long)phase + (left < 128 ? left : 128) : 0, data);
+            if (kAligned16) stage_block(addr, lane, q, left, safe);
+            else stage_block_any(addr, lane, q, left > 0 ? (long long)phase + (left < 128 ? left : 128) : 0, safe);
         };
         stage(stage0, p, rem);
 

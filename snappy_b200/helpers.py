@@ -89,7 +89,7 @@ def cmp_batch(a: np.ndarray, b: np.ndarray, offsets, lengths) -> np.ndarray:
 class Sha512Stream:
     """sha512.New(): a hash.Hash-shaped streaming digest of one long message (snapgpu_hasher_*).
 
-    ``Write`` gathers bytes in pinned memory; every full 4 MiB piece is hashed on the GPU by a
+    ``Write`` gathers bytes in pinned memory; every full 512 KiB piece is hashed on the GPU by a
     worker thread while the caller keeps writing.  ``Sum`` does not disturb the running state."""
 
     def __init__(self):

@@ -171,7 +171,7 @@ def test_stream_api_matches_one_shot(gpu):
 
 
 def test_hasher_streams_like_hash_hash(gpu, tmp_path):
-    """snapgpu_hasher_*: Write in arbitrary pieces across several 4 MiB buffers, Sum in mid-stream without
+    """snapgpu_hasher_*: Write in arbitrary pieces across many 512 KiB buffers, Sum in mid-stream without
     disturbing the state, and the archive-sha512 use: hashing data.tar.gz WHILE it is written
     (io.MultiWriter shape; clickdeb/deb.go:360-366 + snappy/build.go:222) equals hashing the finished file."""
     import tarfile
@@ -181,7 +181,7 @@ def test_hasher_streams_like_hash_hash(gpu, tmp_path):
     h = helpers.Sha512Stream()
     assert h.Sum() == hashlib.sha512(b"").digest()
     pos = 0
-    for step in (0, 1, 127, 128, 4 << 20, (4 << 20) - 256, 3, 5_000_000):
+    for step in (0, 1, 127, 128, 512 << 10, (512 << 10) - 256, 3, (512 << 10) - 3 + 128, 4 << 20, 5_000_000):
         h.Write(msg[pos:pos + step])
         pos += step
         assert h.Sum() == hashlib.sha512(msg[:pos]).digest()
