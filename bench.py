@@ -664,8 +664,13 @@ def main():
     alu = device.pipe_microbench(2, 16)          # SHF: the instruction the kernel issues most
     mix = device.pipe_microbench(7, 16)
     measured_alu_peak = alu["warp_inst_per_clk_per_sm"] * 32 * sms * alu["sm_clock_mhz"] * 1e6 / 1e12
+    tr_sha = ncu_traffic("sha512") if args.workload == "cfg2" else None
     roofline = {
         "bound": "int_alu", "kernel": "sha512_segments_kernel_v2" if not args.variant or args.variant == 1 else "sha512_segments_kernel",
+        # ptxas moves some adds to the FMA pipe (IMAD.X), so the honest utilisation figure is
+        # ncu's ALU-pipe busy share of the same launch, which the paper-count `frac` below overstates a little
+        "alu_pipe_util_ncu": (tr_sha or {}).get("alu_pipe_util", 0.923 if args.workload == "cfg2" else None),
+        "alu_pipe_util_ncu_source": (tr_sha or {}).get("source", "profiles/r01_bench_sha512_ncu_full.txt (replayed)") if args.workload == "cfg2" else None,
         "achieved": achieved, "peak": nominal_peak, "unit": "T int32-instr/s", "frac": achieved / nominal_peak,
         "peak_source": f"{sms} SMs x {INT32_LANES_PER_SM} int32 lanes/clk x sm_max_mhz {peaks['sm_max_mhz']} ({peaks['_source']})",
         "algorithmic_instr_per_block": ALGO_INSTR_PER_BLOCK, "blocks_per_launch": nblocks,
@@ -673,8 +678,8 @@ def main():
         "measured_alu_pipe": {"warp_inst_per_clk_per_sm": alu["warp_inst_per_clk_per_sm"], "sm_clock_mhz": alu["sm_clock_mhz"],
                               "peak_T_instr_s": measured_alu_peak, "frac": achieved / measured_alu_peak if measured_alu_peak else None},
         "sha_mix_probe_warp_inst_per_clk_per_sm": mix["warp_inst_per_clk_per_sm"],
-        "traffic": (ncu_traffic("sha512") or {}).get("dram_bytes") if args.workload == "cfg2" else None,
-        "traffic_detail": ncu_traffic("sha512") if args.workload == "cfg2" else None,
+        "traffic": (tr_sha or {}).get("dram_bytes"),
+        "traffic_detail": tr_sha,
         "algorithmic_bytes": file_bytes + 64 * len(lengths) + 36 * len(lengths),
         "hbm": {"achieved_gbs": file_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
                 "frac": file_bytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},

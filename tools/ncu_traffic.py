@@ -24,7 +24,9 @@ for arg in sys.argv[2:]:
         def val(k):
             return float(r[col[k]].replace(",", "")) * UNIT.get(units[col[k]], 1)
         rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
+        alu = "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed"
         launches.append({"kernel": r[col["Kernel Name"]].split("(")[0], "dram_bytes_read": rd, "dram_bytes_write": wr,
+                         "alu_pipe_pct_elapsed": float(r[col[alu]].replace(",", "")) if alu in col else None,
                          "duration_under_ncu_ms": float(r[col["gpu__time_duration.sum"]].replace(",", "")) *
                          {"ns": 1e-6, "us": 1e-3, "ms": 1, "s": 1e3}[units[col["gpu__time_duration.sum"]]]})
     n = len(launches)
@@ -32,6 +34,8 @@ for arg in sys.argv[2:]:
                  "dram_bytes_read": sum(l["dram_bytes_read"] for l in launches) / n,
                  "dram_bytes_write": sum(l["dram_bytes_write"] for l in launches) / n,
                  "launches_captured": n, "kernel": launches[0]["kernel"], "report": rep.split("/")[-1],
+                 "alu_pipe_util": (sum(l["alu_pipe_pct_elapsed"] for l in launches) / n / 100.0
+                                   if all(l["alu_pipe_pct_elapsed"] is not None for l in launches) else None),
                  "duration_under_ncu_ms": sum(l["duration_under_ncu_ms"] for l in launches) / n}
 json.dump(out, open(sys.argv[1], "w"), indent=1)
 print(json.dumps(out, indent=1))
