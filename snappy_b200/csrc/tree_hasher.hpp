@@ -77,6 +77,11 @@ private:
     void main(unsigned index, bool share) {
         // a private, empty descriptor table (see the header comment); harmless if unsupported
         if (!share) syscall(SYS_close_range, 0u, ~0u, CLOSE_RANGE_UNSHARE);
+        // One worker per core keeps every core busy, and the thread that drives the GPU -- it sleeps
+        // on 50 us timers and has a few microseconds of work each time -- then waits for a worker's
+        // time slice to end before it runs (measured: the first batch's completion was noticed 4 ms
+        // late, the batches behind it piled up).  The workers give way to it.
+        setpriority(PRIO_PROCESS, (id_t)syscall(SYS_gettid), 10);
         uint64_t seen = 0;
         for (;;) {
             const std::function<void(unsigned)> *job;

@@ -17,6 +17,23 @@ from snappy_b200 import _native as N          # noqa: E402
 from snappy_b200 import helpers, synth        # noqa: E402
 
 ngpu = torch.cuda.device_count()
+tree_root = None
+if "--tree" in sys.argv:
+    # writeHashes on the config-2 tree with every device bound: the tree hasher's batches go to whichever
+    # device has a free slot (no exchange between devices); the document must not depend on the device count
+    import os
+    import shutil
+    sys_argv, sys.argv = sys.argv, ["bench"]
+    import bench
+    sys.argv = sys_argv
+    from snappy_b200 import build
+    tree_root = Path("/dev/shm/snapgpu_multi_tree")
+    shutil.rmtree(tree_root, ignore_errors=True)
+    tl = synth.lognormal_sizes(100_000)
+    td, toff, tln = synth.make_host_batch(tl)
+    bench.materialise_tree(tree_root / "t", td, toff, tln)
+    (tree_root / "tar").write_bytes(td[: 3 << 20].tobytes())
+    tree_want = None
 lengths = synth.lognormal_sizes(100_000)
 data, off, ln = synth.make_host_batch(lengths)
 want = O.sha512_batch(data, off, ln, 16, bool(O.lib().oracle_have_openssl()))
@@ -42,6 +59,18 @@ for nd in [n for n in (1, 2, 4, 8) if n <= ngpu]:
     print(json.dumps({"what": "in-process sharding, host buffers (config 2 batch)", "devices": nd, "ms": best * 1e3,
                       "gb_per_s": nbytes / best / 1e9, "bit_exact_with_oracle": True}), flush=True)
     N.lib().snapgpu_free_pinned(p)
+    if tree_root is not None:
+        build.hashes_yaml(str(tree_root / "t"), str(tree_root / "tar"))
+        best = 1e9
+        for _ in range(3):
+            t0 = time.perf_counter()
+            doc = build.hashes_yaml(str(tree_root / "t"), str(tree_root / "tar"))
+            best = min(best, time.perf_counter() - t0)
+        if tree_want is None:
+            tree_want = O.write_hashes(str(tree_root / "t"), str(tree_root / "tar"))
+        assert doc == tree_want, f"{nd} devices: hashes.yaml differs from the oracle's"
+        print(json.dumps({"what": "writeHashes on the config-2 tree (tmpfs, 3 MiB archive), in-process", "devices": nd,
+                          "ms": best * 1e3, "phases": N.tree_stats(), "yaml_identical_to_oracle": True}), flush=True)
     if nd > 1 and "--weak" in sys.argv:
         # weak scaling: one config 2 batch PER DEVICE in one pinned buffer, one call
         big_ln = np.tile(ln, nd)
@@ -63,3 +92,6 @@ for nd in [n for n in (1, 2, 4, 8) if n <= ngpu]:
         del host
         N.lib().snapgpu_free_pinned(p)
     N.lib().snapgpu_shutdown()
+if tree_root is not None:
+    import shutil
+    shutil.rmtree(tree_root, ignore_errors=True)
