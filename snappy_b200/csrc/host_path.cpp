@@ -1473,8 +1473,7 @@ int build_tree_doc(const std::string &build_dir, const std::string *data_tar, bo
         return fail(SNAPGPU_EIO, "%s", go_path_error(archive_op == 2 ? "open" : "read", *data_tar, archive_err).c_str());
     if (rc) return rc;
     if (chain_rc) return fail(chain_rc, "%s", chain_err.c_str());
-    std::vector<FlatEntry> flat;
-    tree.flatten(flat);
+    const std::vector<FlatEntry> &flat = tree.flat();
     if ((rc = tree.first_error(flat))) return rc;
     const double t3 = wall_ms();
     rc = emit_tree_yaml(flat, archive_digest, nullptr, doc);
@@ -2143,8 +2142,7 @@ int snapgpu_test_yaml_from_digests(const char *build_dir, const uint8_t *digests
     TreeHasher tree(dir, false);                             // scan and lstat only: no GPU
     int rc = tree.run();
     if (rc) return rc;
-    std::vector<FlatEntry> flat;
-    tree.flatten(flat);
+    const std::vector<FlatEntry> &flat = tree.flat();
     if ((rc = tree.first_error(flat))) return rc;
     const double t1 = wall_ms();
     size_t nreg = 0;

@@ -511,7 +511,14 @@ public:
         return 0;
     }
 
-    // entries in filepath.Walk order
+    // entries in filepath.Walk order (laid out once; during the GPU tail when there is one)
+    const std::vector<FlatEntry> &flat() {
+        if (!flattened_) {
+            flatten(flat_);
+            flattened_ = true;
+        }
+        return flat_;
+    }
     void flatten(std::vector<FlatEntry> &out) const {
         out.clear();
         out.reserve(nentries_.load());
@@ -961,6 +968,12 @@ private:
         }
         const double t0 = wall_ms();
         if (trace) fprintf(stderr, "[snapgpu] tree: workers done at %.2f ms, %zu batches in flight\n", t0 - t_start, session_in_flight(session_));
+        // every directory has been read: the walk order can be laid out while the last batches are
+        // still on the GPU (it needs names and modes, not digests)
+        if (!fatal_rc_) {
+            flatten(flat_);
+            flattened_ = true;
+        }
         copied.clear();
         int rc = session_poll(session_, &copied, true);
         if (rc && !fatal_rc_) fatal(rc);
@@ -1001,6 +1014,8 @@ private:
 
     const std::string root_;
     const bool hash_;
+    std::vector<FlatEntry> flat_;
+    bool flattened_ = false;
     BatchSession *session_ = nullptr;
     TDir *root_dir_ = nullptr;
     std::mutex dirs_mu_;
