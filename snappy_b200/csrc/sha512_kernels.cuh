@@ -103,7 +103,7 @@ template <int kRoundFma, int kSchedFma, bool kAligned16, int kCtasPerSm>
 __global__ void __launch_bounds__(kShaThreads, kCtasPerSm)
 sha512_segments_kernel(const uint8_t *__restrict__ data, const SegDesc *__restrict__ descs,
                        const u32 *__restrict__ order, u32 nsegs,
-                       uint8_t *__restrict__ digests, u32 *__restrict__ unit_counter, u32 one) {
+                       uint8_t *__restrict__ digests, u32 *__restrict__ unit_counter, u32 one, u32 /*first_wave*/) {
     const u32 lane = threadIdx.x & 31;
     const u32 warp = threadIdx.x >> 5;
     const u32 nunits = (nsegs + 31) >> 5;
@@ -259,7 +259,7 @@ template <int kAddMode, int kCtasPerSm, bool kAligned16 = true>
 __global__ void __launch_bounds__(kShaThreads, kCtasPerSm)
 sha512_segments_kernel_v2(const uint8_t *__restrict__ data, const SegDesc *__restrict__ descs,
                           const u32 *__restrict__ order, u32 nsegs,
-                          uint8_t *__restrict__ digests, u32 *__restrict__ unit_counter, u32 one) {
+                          uint8_t *__restrict__ digests, u32 *__restrict__ unit_counter, u32 one, u32 first_wave) {
     constexpr int kStage = kAligned16 ? kStageBytesPerWarp : kStageBytesPerWarpAny;
     __shared__ __align__(16) uint8_t stages[kShaWarpsPerCta][2][kStage];
     const u32 lane = threadIdx.x & 31;
@@ -271,14 +271,31 @@ sha512_segments_kernel_v2(const uint8_t *__restrict__ data, const SegDesc *__res
     // balanced the claims between SM sub-partitions with bounded spin-waits was measured in round 1
     // -- better on some mixed batches, worse on config 2, different from process to process -- and
     // has been removed: no wait loop lives in this kernel.)
+    //
+    // Two-ended claims (first_wave != 0, launches with several CTAs per SM).  An SM sub-partition
+    // does not share its ALU pipe evenly: of two resident warps one gets ~83 % and the other ~16 %
+    // (DESIGN.md section 10), so a long unit claimed by the slow one is a backlog that ends the
+    // launch late.  Here a warp that is running slowly -- it times its own units: more than
+    // kSlowClocksPerBlock per block -- claims its next unit from the SHORT end of the sorted plan,
+    // everybody else from the long end; the two ends meet in the middle.  One 64-bit counter holds
+    // both ends (low word: claims from the long end, high word: from the short end), so the order
+    // of the atomic adds numbers the claims and every unit is claimed exactly once.  Nobody waits.
     const u32 total_warps = gridDim.x * kShaWarpsPerCta;   // units handed out before the counter starts
+    // Which warp of a sub-partition is the favoured one is not known beforehand, so EVERY warp
+    // starts with one of the shortest units -- a few blocks, enough to time itself -- and chooses
+    // its end from then on.
+    const bool two_ended = first_wave != 0;
+    const u32 head0 = 0, tail0 = total_warps;
     u32 unit = warp * gridDim.x + blockIdx.x;
+    if (two_ended) unit = nunits - 1 - unit;
+    constexpr long long kSlowClocksPerBlock = 16000;       // a lone warp needs ~7600, the favoured one of two ~8400, the other ~43000
 #ifdef SNAPGPU_TRACE_WARPS
     unsigned long long tr_start, tr_units = 0, tr_blocks = 0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_start));
 #endif
 
     while (unit < nunits) {
+        const long long t_unit = two_ended ? clock64() : 0;
         const u32 idx = unit * 32 + lane;
         bool have = idx < nsegs;
         SegDesc sd;
@@ -382,7 +399,17 @@ sha512_segments_kernel_v2(const uint8_t *__restrict__ data, const SegDesc *__res
         }
 
         u32 next = 0;
-        if (lane == 0) next = atomicAdd(unit_counter, 1u) + total_warps;
+        if (lane == 0) {
+            if (!two_ended) {
+                next = atomicAdd(unit_counter, 1u) + total_warps;
+            } else {
+                const bool slow = nblk_max != 0 && (clock64() - t_unit) > kSlowClocksPerBlock * (long long)nblk_max;
+                const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long *>(unit_counter),
+                                                         slow ? (1ull << 32) : 1ull);
+                const u32 from_head = (u32)old + head0, from_tail = (u32)(old >> 32) + tail0;
+                next = from_head + from_tail >= nunits ? nunits : (slow ? nunits - 1 - from_tail : from_head);
+            }
+        }
         unit = __shfl_sync(0xffffffffu, next, 0);
     }
 #ifdef SNAPGPU_TRACE_WARPS

@@ -204,6 +204,7 @@ struct Options {
     std::atomic<long long> time_kernels{1};
     std::atomic<long long> feeders{0};          // bounce-buffer threads per device for pageable input, 0 = auto
     std::atomic<long long> long_kernel{2};      // 0 off, 1 one lane per file, 2 a lane pair per file
+    std::atomic<long long> two_ended{1};        // several CTAs per SM: slow warps claim from the short end of the plan
     std::atomic<long long> pair_form{0};        // lane-pair kernel: 0 lanes exchange through mailboxes, 1 by shuffle
 };
 
@@ -432,7 +433,7 @@ static bool trace_on() {
     return on;
 }
 
-typedef void (*ShaKernel)(const uint8_t *, const SegDesc *, const u32 *, u32, uint8_t *, u32 *, u32);
+typedef void (*ShaKernel)(const uint8_t *, const SegDesc *, const u32 *, u32, uint8_t *, u32 *, u32, u32);
 
 constexpr int kShaCtasPerSmMax = 3;   // 168 registers per thread: no spills with the one-block-ahead prefetch
 constexpr int kShaVariants = 6;
@@ -692,7 +693,10 @@ static int launch_sha512(Pipe &D, cudaStream_t stream, const uint8_t *d_data, Ge
         R.sha_long_launches++;
     }
     if (n_main) {
-        k<<<grid, kShaThreads, 0, stream>>>(d_data, plan.descs, plan.order, (u32)n, d_digests, slot->d_counter, 1u);
+        // several CTAs per SM and plenty of units: claims from both ends of the sorted plan (sha512_kernels.cuh)
+        const u32 first_wave = (R.opt.two_ended.load() && grid > (u32)D.sm_count && nunits >= 8 * grid * kShaWarpsPerCta)
+                                   ? (u32)D.sm_count : 0u;
+        k<<<grid, kShaThreads, 0, stream>>>(d_data, plan.descs, plan.order, (u32)n, d_digests, slot->d_counter, 1u, first_wave);
         SG_CUDA(cudaGetLastError());
         R.kernel_launches++;
     }
@@ -1608,6 +1612,8 @@ int snapgpu_set_option(const char *key, long long value) {
     } else if (k == "feeders") {
         if (value < 0 || value > kFeeders) return fail(SNAPGPU_EINVAL, "feeders out of range");
         o.feeders = value;
+    } else if (k == "two_ended") {
+        o.two_ended = value ? 1 : 0;
     } else if (k == "pair_form") {
         if (value < 0 || value > 1) return fail(SNAPGPU_EINVAL, "pair_form: 0 shared-memory mailboxes, 1 shuffle exchange");
         o.pair_form = value;

@@ -20,6 +20,7 @@ def default_options(gpu):
     gpu.set_option("sha_warps_per_sm", 0)
     gpu.set_option("long_kernel", 2)
     gpu.set_option("pair_form", 0)
+    gpu.set_option("two_ended", 1)
     yield
 
 
@@ -908,3 +909,25 @@ def test_archive_hashed_while_written_then_write_hashes_with_the_digest(gpu, ora
     want = oracle.write_hashes(str(tree), str(tar))
     assert build.hashes_yaml_digest(str(tree), digest) == want
     assert build.hashes_yaml(str(tree), str(tar)) == want
+
+
+def test_two_ended_claims_cover_every_unit_once(gpu, oracle):
+    """Launches with several CTAs per SM claim units from both ends of the length-sorted plan (slow warps
+    from the short end, sha512_kernels.cuh): on 400,000 files -- enough units for the mode to switch on at
+    two and at three CTAs per SM -- every digest equals the oracle's, with the mode on and off."""
+    import torch
+    from snappy_b200 import device
+    rng = np.random.default_rng(99)
+    lengths = np.concatenate([rng.integers(0, 3000, 399_000), rng.integers(20_000, 70_000, 1000)]).astype(np.uint64)
+    rng.shuffle(lengths)
+    data, off, ln = pack(lengths, rng)
+    want = oracle.sha512_batch(data, off, ln, 16, True)
+    d = torch.from_numpy(data).cuda()
+    for warps in (2, 3):
+        gpu.set_option("sha_warps_per_sm", warps)
+        for mode in (1, 0):
+            gpu.set_option("two_ended", mode)
+            got = device.sha512_batch_device(d, off, ln).cpu().numpy()
+            assert np.array_equal(got, want), (warps, mode)
+    gpu.set_option("sha_warps_per_sm", 0)
+    gpu.set_option("two_ended", 1)

@@ -26,6 +26,11 @@ cases = {
     "uniform 8K..16K": rng.integers(8192, 16384, n).astype(np.uint64),
     "half 4K half 64K": np.concatenate([np.full(n // 4, 4096), np.full(n // 8, 65536)]).astype(np.uint64),
     "uniform 4K": np.full(n, 4096, dtype=np.uint64),
+    # narrow distributions at the depths where the automatic shape is two CTAs per SM
+    "uniform 8K..16K, 100k files": rng.integers(8192, 16384, 100_000).astype(np.uint64),
+    "uniform 24K..32K, 87k files": rng.integers(24576, 32768, 87_000).astype(np.uint64),
+    "uniform 60K..64K, 58k files": rng.integers(61440, 65536, 58_000).astype(np.uint64),
+    "lognormal s=0.25, 150k files": np.clip(np.round(np.exp(rng.normal(np.log(8192), 0.25, 150_000))), 1024, 65536).astype(np.uint64),
 }
 only = sys.argv[1] if len(sys.argv) > 1 else ""
 for name, lengths in cases.items():
@@ -37,8 +42,9 @@ for name, lengths in cases.items():
     blocks = synth.blocks(lengths)
     row = {"lengths": name, "files": len(lengths), "max_over_mean_blocks": round(float(blocks.max() / blocks.mean()), 2),
            "depth": round(float(blocks.sum() / (148 * 128 * blocks.max())), 2)}
-    for bal in (1,):                       # (round 1 also ran an opt-in "balance" mode here; it has been removed)
-        for r in (0, 1, 2, 3):
+    for bal in (1, 0):                     # two-ended claims on (the default) and off
+        N.set_option("two_ended", bal)
+        for r in ((0, 1, 2, 3) if bal else (0, 2, 3)):
             N.set_option("sha_warps_per_sm", r)
             dg = torch.empty((len(lengths), 64), dtype=torch.uint8, device="cuda:0")
             for _ in range(2):
@@ -50,7 +56,7 @@ for name, lengths in cases.items():
             torch.cuda.synchronize()
             s = N.stats()
             ms = s.sha512_kernel_ms_sum / s.sha512_kernel_timed
-            key = ("auto" if r == 0 else f"R{r}") + ("" if bal else " unbalanced")
+            key = ("auto" if r == 0 else f"R{r}") + ("" if bal else " one-ended")
             row[key] = round(int(blocks.sum()) * 3568 / (ms * 1e-3) / PEAK, 4)
             print("   ", name, key, row[key], file=sys.stderr, flush=True)
     print(json.dumps(row), flush=True)
