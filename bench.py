@@ -472,11 +472,20 @@ def main():
 
     # ---- config 5, strong scaling: 2 M x 64 KiB split over the ranks, digests gathered by index --
     cfg5 = None
+    cfg5_fits = False
     if not args.no_cfg5 and args.workload == "cfg2":
         del d_data
         torch.cuda.empty_cache()
         total_files = int(os.environ.get("SNAPGPU_CFG5_TOTAL", "2000000"))
         per = total_files // world
+        need5 = per * (65536 + 64 + 36 + 8) + (4 << 30)
+        fits = torch.tensor([1.0 if torch.cuda.mem_get_info(dev)[0] > need5 else 0.0], device=dev)
+        if world > 1:
+            dist.all_reduce(fits, op=dist.ReduceOp.MIN)          # every rank takes the same decision
+        cfg5_fits = bool(fits.item() > 0)
+        if not cfg5_fits and rank == 0:
+            cfg5 = {"skipped": f"a rank has less than {need5 / 1e9:.0f} GB of free HBM for its {per} files x 64 KiB"}
+    if cfg5_fits:
         lo = rank * per
         l5 = np.full(per, 65536, dtype=np.uint64)
         o5, t5 = synth.layout(l5)
@@ -550,6 +559,7 @@ def main():
         ncores = len(os.sched_getaffinity(0)) or os.cpu_count() or 1
         use_ossl = bool(O.lib().oracle_have_openssl())
         root = bench_root()
+        tree_error = None
         e2e_tree = {"where": str(root.parent), "call": "snapgpu_hashes_yaml(buildDir, dataTar): walk + read + H2D + SHA-512 + "
                     "D2H + hashes.yaml in memory, best of 3 after one warm-up call, page cache hot",
                     "cpu": "helpers.Sha512sum (open / 32 KiB reads / close, OpenSSL block function) looped over the same files; "
@@ -654,6 +664,10 @@ def main():
                           "package's data.tar.gz, not its tree, sets writeHashes' time on the GPU -- which is why INTEGRATION.md "
                           "hashes it while gzip writes it (snapgpu_hasher) instead of re-reading the finished file")
             e2e_tree["cfg1_real_archive"] = r1
+        except (OSError, subprocess.CalledProcessError, MemoryError) as exc:      # no room on tmpfs, no tar, ...: the
+            tree_error = f"{type(exc).__name__}: {exc}"                         # other legs of the line still stand
+            e2e_tree["error"] = tree_error
+            log("e2e_tree leg failed:", tree_error)
         finally:
             shutil.rmtree(root, ignore_errors=True)
 
@@ -812,7 +826,7 @@ def main():
                         if use_ossl else "C restatement, scalar block function"),
                "bit_exact_with_gpu": True}
 
-    if cpu is not None and e2e_tree is not None:
+    if cpu is not None and e2e_tree is not None and "cfg2" in e2e_tree:
         c2 = e2e_tree["cfg2"]
         cpu.update({"tree_1core_gbs": c2["cpu_1core_gbs"], "tree_allcores_gbs": c2["cpu_allcores_gbs"],
                     "tree_1core_files_per_s": c2["cpu_1core_files_per_s"], "tree_allcores_files_per_s": c2["cpu_allcores_files_per_s"],
@@ -821,40 +835,43 @@ def main():
     # ---- one process, every GPU of the box: what a cgo caller gets (N > 1 only) ---------------
     inproc = None
     if world > 1 and not args.no_inprocess and host_view is not None and e2e is not None:
-        N.init(list(range(world)))                      # rank 0 re-binds: devices 0..N-1, the other ranks idle
-        stride = (total_alloc + 4095) & ~4095
-        big, big_ptr = pinned_array(world * stride)
-        lens_all = np.tile(lengths, world)
-        offs_all = np.concatenate([offsets + np.uint64(r * stride) for r in range(world)])
-        for r in range(world):                          # N copies of rank 0's batch: every copy hashes to rank 0's digests
-            big[r * stride: r * stride + total_alloc] = host_view
-        N.lib().snapgpu_free_pinned(host_ptr)
-        del host_view, host_t
-        out_all = np.empty((len(lens_all), 64), dtype=np.uint8)
-        for _ in range(2):
-            helpers.sha512_batch(big, offs_all, lens_all, out=out_all)
-        assert np.array_equal(out_all.reshape(world, len(lengths), 64), np.broadcast_to(digest_host, (world, len(lengths), 64))), \
-            "in-process digests differ from the per-rank run"
-        N.reset_stats()
-        isteps = 5
-        t0 = time.perf_counter()
-        for _ in range(isteps):
-            helpers.sha512_batch(big, offs_all, lens_all, out=out_all)
-        dti = (time.perf_counter() - t0) / isteps
-        sti = N.stats()
-        launches += int(sti.kernel_launches)
-        secs = ctypes.c_double()
-        pb = min(stride, 1 << 30) & ~4095
-        N.check(N.lib().snapgpu_h2d_probe(big_ptr, pb, 4, ctypes.byref(secs)))
-        ip_peak = world * pb * 4 / secs.value / 1e9
-        ip_gbs = world * file_bytes / dti / 1e9
-        inproc = {"what": f"ONE process bound to {world} devices (snapgpu_init), one pinned buffer holding {world} config-2 batches, one "
-                          f"snapgpu_sha512_batch call per step; the other ranks idle",
-                  "gbs": ip_gbs, "files_per_s": world * len(lengths) / dti, "ms_per_step": dti * 1e3,
-                  "frac_of_torchrun": ip_gbs / e2e["value"], "h2d_peak_gbs": ip_peak, "frac_of_h2d_peak": ip_gbs / ip_peak,
-                  "h2d_bytes_per_step": int(sti.h2d_bytes // isteps), "bit_exact_with_per_rank_run": True}
-        N.lib().snapgpu_free_pinned(big_ptr)
-        del big
+        def inprocess_leg():
+            N.init(list(range(world)))                      # rank 0 re-binds: devices 0..N-1, the other ranks idle
+            stride = (total_alloc + 4095) & ~4095
+            big, big_ptr = pinned_array(world * stride)
+            lens_all = np.tile(lengths, world)
+            offs_all = np.concatenate([offsets + np.uint64(r * stride) for r in range(world)])
+            for r in range(world):                          # N copies of rank 0's batch: every copy hashes to rank 0's digests
+                big[r * stride: r * stride + total_alloc] = host_view
+            N.lib().snapgpu_free_pinned(host_ptr)
+            out_all = np.empty((len(lens_all), 64), dtype=np.uint8)
+            for _ in range(2):
+                helpers.sha512_batch(big, offs_all, lens_all, out=out_all)
+            assert np.array_equal(out_all.reshape(world, len(lengths), 64), np.broadcast_to(digest_host, (world, len(lengths), 64))), \
+                "in-process digests differ from the per-rank run"
+            N.reset_stats()
+            isteps = 5
+            t0 = time.perf_counter()
+            for _ in range(isteps):
+                helpers.sha512_batch(big, offs_all, lens_all, out=out_all)
+            dti = (time.perf_counter() - t0) / isteps
+            sti = N.stats()
+            secs = ctypes.c_double()
+            pb = min(stride, 1 << 30) & ~4095
+            N.check(N.lib().snapgpu_h2d_probe(big_ptr, pb, 4, ctypes.byref(secs)))
+            ip_peak = world * pb * 4 / secs.value / 1e9
+            ip_gbs = world * file_bytes / dti / 1e9
+            return int(sti.kernel_launches), {"what": f"ONE process bound to {world} devices (snapgpu_init), one pinned buffer holding {world} config-2 batches, one "
+                              f"snapgpu_sha512_batch call per step; the other ranks idle",
+                      "gbs": ip_gbs, "files_per_s": world * len(lengths) / dti, "ms_per_step": dti * 1e3,
+                      "frac_of_torchrun": ip_gbs / e2e["value"], "h2d_peak_gbs": ip_peak, "frac_of_h2d_peak": ip_gbs / ip_peak,
+                      "h2d_bytes_per_step": int(sti.h2d_bytes // isteps), "bit_exact_with_per_rank_run": True}
+        try:
+            more, inproc = inprocess_leg()
+            launches += more
+        except (RuntimeError, MemoryError, OSError) as exc:      # resources; a digest mismatch still raises
+            inproc = {"error": f"{type(exc).__name__}: {exc}"}
+            log("inprocess leg failed:", inproc["error"])
 
     total_bytes = world * file_bytes
     line = {
