@@ -1139,34 +1139,52 @@ struct CachedDigest {
     struct timespec mtime, ctime;
     uint8_t digest[64];
 };
+// Sharded by inode: writeHashes looks every file up from all packer threads at once.
 struct DigestCache {
-    std::mutex mu;
-    std::map<std::pair<dev_t, ino_t>, CachedDigest> map;
+    static constexpr size_t kShards = 64;
+    struct Shard {
+        std::mutex mu;
+        std::map<std::pair<dev_t, ino_t>, CachedDigest> map;
+    };
+    Shard shard[kShards];
     std::atomic<size_t> entries{0};
-    uint64_t hits = 0;
+    std::atomic<uint64_t> hits{0};
+    Shard &of(ino_t ino) { return shard[(size_t)(ino * 0x9E3779B97F4A7C15ull >> 58) % kShards]; }
+    void clear() {
+        for (Shard &s : shard) {
+            std::lock_guard<std::mutex> lock(s.mu);
+            s.map.clear();
+        }
+        entries = 0;
+    }
 };
 DigestCache &digest_cache() {
     static DigestCache c;
     return c;
 }
-void cache_put(const struct stat &st, const uint8_t digest[64]) {
+void cache_put(dev_t dev, ino_t ino, off_t size, const struct timespec &mtime, const struct timespec &ctime,
+               const uint8_t digest[64]) {
     CachedDigest d;
-    d.size = st.st_size;
-    d.mtime = st.st_mtim;
-    d.ctime = st.st_ctim;
+    d.size = size;
+    d.mtime = mtime;
+    d.ctime = ctime;
     memcpy(d.digest, digest, 64);
     DigestCache &C = digest_cache();
-    std::lock_guard<std::mutex> lock(C.mu);
-    if (C.map.size() >= ((size_t)1 << 22)) C.map.clear();      // bounded: a build stages one tree at a time
-    C.map[std::make_pair(st.st_dev, st.st_ino)] = d;
-    C.entries = C.map.size();
+    if (C.entries.load() >= ((size_t)1 << 22)) C.clear();          // bounded: a build stages one tree at a time
+    DigestCache::Shard &S = C.of(ino);
+    std::lock_guard<std::mutex> lock(S.mu);
+    if (S.map.insert_or_assign(std::make_pair(dev, ino), d).second) C.entries++;
+}
+void cache_put(const struct stat &st, const uint8_t digest[64]) {
+    cache_put(st.st_dev, st.st_ino, st.st_size, st.st_mtim, st.st_ctim, digest);
 }
 bool cache_get(const struct stat &st, uint8_t digest[64]) {
     DigestCache &C = digest_cache();
-    if (C.entries.load(std::memory_order_relaxed) == 0) return false;     // the usual case, without the lock
-    std::lock_guard<std::mutex> lock(C.mu);
-    auto it = C.map.find(std::make_pair(st.st_dev, st.st_ino));
-    if (it == C.map.end()) return false;
+    if (C.entries.load(std::memory_order_relaxed) == 0) return false;     // the usual case, without a lock
+    DigestCache::Shard &S = C.of(st.st_ino);
+    std::lock_guard<std::mutex> lock(S.mu);
+    auto it = S.map.find(std::make_pair(st.st_dev, st.st_ino));
+    if (it == S.map.end()) return false;
     const CachedDigest &d = it->second;
     if (d.size != st.st_size || d.mtime.tv_sec != st.st_mtim.tv_sec || d.mtime.tv_nsec != st.st_mtim.tv_nsec ||
         d.ctime.tv_sec != st.st_ctim.tv_sec || d.ctime.tv_nsec != st.st_ctim.tv_nsec)
@@ -1175,12 +1193,7 @@ bool cache_get(const struct stat &st, uint8_t digest[64]) {
     C.hits++;
     return true;
 }
-void cache_clear_entries() {
-    DigestCache &C = digest_cache();
-    std::lock_guard<std::mutex> lock(C.mu);
-    C.map.clear();
-    C.entries = 0;
-}
+void cache_clear_entries() { digest_cache().clear(); }
 
 std::string clean_dir(const char *p) {
     std::string s(p ? p : "");
@@ -1202,9 +1215,12 @@ int mkdir_all(const std::string &path, mode_t mode) {
     return (stat(path.c_str(), &st) == 0 && S_ISDIR(st.st_mode)) ? 0 : -1;
 }
 
+bool should_exclude(const std::string &b);      // shouldExclude, defined with copyToBuildDir below
+
 #include "tree_hasher.hpp"
 
 bool TreeHasher::cache_lookup(const struct stat &st, uint8_t digest[64]) { return cache_get(st, digest); }
+bool TreeHasher::cache_nonempty() { return digest_cache().entries.load(std::memory_order_relaxed) != 0; }
 
 // ------------------------------------------------------------------------------------------
 // yaml.Marshal(hashesYaml{...}) (build.go:264), written by the pool in one parallel pass.
@@ -1952,6 +1968,39 @@ int copy_to_build_dir(const std::string &source_in, const std::string &build_dir
     }
     struct stat root;
     if (lstat(source.c_str(), &root) != 0) return fail(SNAPGPU_EIO, "%s", go_path_error("lstat", source, errno).c_str());
+    if (S_ISDIR(root.st_mode)) {
+        // The usual call: a source directory.  Scan, mkdir, link / copy and hashing of what is copied
+        // all run on the tree engine (tree_hasher.hpp); a copied file is read once.
+        if (should_exclude(base_name(source))) return 0;
+        const double tc0 = wall_ms();
+        if (mkdir(build_dir.c_str(), root.st_mode & 07777) != 0)
+            return fail(SNAPGPU_EIO, "%s", go_path_error("mkdir", build_dir, errno).c_str());
+        CopySpec spec;
+        spec.dest = build_dir;
+        spec.no_link = (flags & SNAPGPU_COPY_NO_LINK) != 0;
+        TreeHasher tree(source, true, &spec);
+        tree.chains.start();
+        int rc = tree.run();
+        const int chain_rc = tree.chains.finish();
+        if (rc) return rc;
+        if (chain_rc) return chain_rc;
+        if ((rc = tree.first_error(tree.flat()))) return rc;
+        size_t remembered = 0;
+        for (TDir *d : tree.dirs())
+            for (size_t i = 0; i < d->copies.size(); i++) {
+                const CopyRec &r = d->copies[i];
+                if (r.written && !d->entries[i].err) {
+                    cache_put(r.dev, r.ino, r.size, r.mtime, r.ctime, d->entries[i].digest);
+                    remembered++;
+                }
+            }
+        if (getenv("SNAPGPU_TRACE"))
+            fprintf(stderr, "[snapgpu] copyToBuildDir: %zu entries, %zu linked, %zu copied through the GPU (%zu digests remembered) "
+                            "in %zu batches, %.2f ms\n",
+                    tree.flat().size(), tree.files_linked(), tree.files_hashed(), remembered, tree.batches(), wall_ms() - tc0);
+        return 0;
+    }
+    // a source that is not a directory (Walk visits just it): round 1's path
     std::vector<CopyAction> actions;
     const double t0 = wall_ms();
     int rc = copy_walk(source, build_dir, root, actions, true);
@@ -2301,16 +2350,14 @@ int snapgpu_should_exclude(const char *base_name_) { return base_name_ && should
 
 void snapgpu_digest_cache_clear(void) {
     DigestCache &C = digest_cache();
-    std::lock_guard<std::mutex> lock(C.mu);
-    C.map.clear();
+    C.clear();
     C.hits = 0;
 }
 
 void snapgpu_digest_cache_stats(size_t *entries, uint64_t *hits) {
     DigestCache &C = digest_cache();
-    std::lock_guard<std::mutex> lock(C.mu);
-    if (entries) *entries = C.map.size();
-    if (hits) *hits = C.hits;
+    if (entries) *entries = C.entries.load();
+    if (hits) *hits = C.hits.load();
 }
 
 int snapgpu_apparmor_delta(const char *old_path, const char *new_path, const char *prefix, char **policies,

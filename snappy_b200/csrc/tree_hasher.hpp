@@ -452,11 +452,20 @@ struct TEntry {
     mode_t mode = 0;
     int64_t size = 0;
     uint8_t kind = 0;          // 0 neither, 1 regular file, 2 directory
-    uint8_t err_op = 0;        // 1 lstat, 2 open, 3 read
+    uint8_t err_op = 0;        // 1 lstat, 2 open, 3 read, 4 mkdir, 5 write; | 0x80: on the destination path (copy mode)
     bool cached = false;       // digest came from the digest cache
     int err = 0;               // errno of that step
     TDir *child = nullptr;
     uint8_t digest[64];
+};
+
+// copy mode: what the library wrote for an entry, the key of its digest in the cache
+struct CopyRec {
+    bool written = false;      // its bytes went to the destination out of the pinned chunk the GPU hashed
+    dev_t dev = 0;
+    ino_t ino = 0;
+    off_t size = 0;
+    struct timespec mtime = {0, 0}, ctime = {0, 0};
 };
 
 struct TDir {
@@ -464,7 +473,17 @@ struct TDir {
     std::string rel;           // relative to the build dir with a trailing slash ("" for the root)
     std::string names;         // the entries' names back to back
     std::vector<TEntry> entries;
+    std::vector<CopyRec> copies;   // copy mode only, parallel to entries
     int open_err = 0;          // could not be read: Walk hands it to the callback a second time
+};
+
+// copyToBuildDir (snappy/build.go:362-418) on the same engine: the scan applies shouldExclude
+// instead of the /DEBIAN rule and creates the directories, the packers hard-link what can be
+// linked and copy the rest -- a copied file is read ONCE, its bytes go to the destination out of
+// the pinned chunk that the GPU hashes.
+struct CopySpec {
+    std::string dest;
+    bool no_link = false;
 };
 
 struct linux_dirent64_ {
@@ -484,11 +503,13 @@ class TreeHasher {
 public:
     // hash: read and hash the regular files on the GPU.  false: scan and lstat only (the test
     // hook that takes its digests from the caller).
-    TreeHasher(const std::string &root, bool hash) : root_(root), hash_(hash) {}
+    TreeHasher(const std::string &root, bool hash, const CopySpec *copy = nullptr)
+        : root_(root), hash_(hash), copy_(copy ? new CopySpec(*copy) : nullptr) {}
     ~TreeHasher() {
         chains.finish();                          // it writes into the entries
         for (TDir *d : dirs_) delete d;
         if (session_) session_close(session_);
+        delete copy_;
     }
 
     ChainStreamer chains;
@@ -497,7 +518,7 @@ public:
         IoPool &pool = IoPool::instance();
         struct stat st;
         if (lstat(root_.c_str(), &st) != 0 || !S_ISDIR(st.st_mode)) return 0;      // Walk visits only the root: no entries
-        if (hash_) {
+        if (hash_ && !copy_) {                 // copy mode opens it with the first batch: a tree that links needs no GPU
             int rc = session_open(&session_, kTreeBatchBytes);
             if (rc) return rc;
         }
@@ -527,16 +548,27 @@ public:
 
     // the first failing entry in walk order, the way the reference's Walk would stop at it
     int first_error(const std::vector<FlatEntry> &flat) const {
-        for (const FlatEntry &f : flat)
+        // copy mode: a directory that cannot be read is the error Walk hands to the callback, which
+        // returns it (build.go:374-376); writeHashes ignores it (build.go:228,241)
+        if (copy_ && root_dir_ && root_dir_->open_err)
+            return fail(SNAPGPU_EIO, "%s", go_path_error("open", root_dir_->path, root_dir_->open_err).c_str());
+        for (const FlatEntry &f : flat) {
+            if (copy_ && f.e->child && f.e->child->open_err && !f.e->err)
+                return fail(SNAPGPU_EIO, "%s", go_path_error("open", f.e->child->path, f.e->child->open_err).c_str());
             if (f.e->err) {
-                static const char *const ops[] = {"", "lstat", "open", "read"};
-                return fail(SNAPGPU_EIO, "%s", go_path_error(ops[f.e->err_op], entry_path(f), f.e->err).c_str());
+                static const char *const ops[] = {"", "lstat", "open", "read", "mkdir", "write"};
+                const std::string name = f.dir->names.substr(f.e->name_off, f.e->name_len);
+                const std::string path = (f.e->err_op & 0x80) && copy_ ? copy_->dest + "/" + f.dir->rel + name : entry_path(f);
+                return fail(SNAPGPU_EIO, "%s", go_path_error(ops[f.e->err_op & 7], path, f.e->err).c_str());
             }
+        }
         return 0;
     }
 
     static std::string entry_path(const FlatEntry &f) { return f.dir->path + "/" + f.dir->names.substr(f.e->name_off, f.e->name_len); }
 
+    const std::vector<TDir *> &dirs() const { return dirs_; }
+    size_t files_linked() const { return nlinked_.load(); }
     size_t files_hashed() const { return nhashed_.load(); }
     size_t files_cached() const { return ncached_.load(); }
     size_t batches() const { return nbatches_; }
@@ -656,7 +688,8 @@ private:
                 if (nm[0] == '.' && (!nm[1] || (nm[1] == '.' && !nm[2]))) continue;
                 // build.go:229: anything whose path below the build dir starts with "/DEBIAN" is
                 // skipped, which the top-level name decides for the whole subtree
-                if (top && strncmp(nm, "DEBIAN", 6) == 0) continue;
+                if (!copy_ && top && strncmp(nm, "DEBIAN", 6) == 0) continue;
+                if (copy_ && should_exclude(nm)) continue;          // build.go:378-383: the entry, a directory with its subtree
                 const size_t len = strlen(nm);
                 names.push_back(Name{(uint32_t)arena.size(), (uint32_t)len, e->d_type});
                 arena.append(nm, len);
@@ -668,6 +701,7 @@ private:
             return c ? c < 0 : a.len < b.len;
         });
         dir->entries.resize(names.size());
+        if (copy_) dir->copies.resize(names.size());
         nentries_ += names.size();
         uint32_t nreg = 0;
         std::string child_name;
@@ -694,15 +728,28 @@ private:
                 if (hash_) nreg++;
             } else if (S_ISDIR(st.st_mode)) {
                 e.kind = 2;
+                if (copy_ && ::mkdir((copy_->dest + "/" + dir->rel + child_name).c_str(), st.st_mode & 07777) != 0) {
+                    e.err = errno;                             // os.Mkdir(dest, info.Mode()), build.go:386-388
+                    e.err_op = 4 | 0x80;
+                    continue;
+                }
                 e.child = new_dir(dir->path + "/" + child_name, dir->rel + child_name + "/");
                 push_task(Task{e.child, 0, 0, 0});
+            } else if (copy_) {
+                // a symlink, a fifo ...: linked if possible, else copied the way the reference does it
+                // (os.Open follows a symlink; build.go:391-416)
+                const std::string dest = copy_->dest + "/" + dir->rel + child_name;
+                if (copy_->no_link || ::linkat(dfd, child_name.c_str(), AT_FDCWD, dest.c_str(), 0) != 0)
+                    plain_copy(dir->path + "/" + child_name, dest, st.st_mode, e);
             }
         }
         if (nreg) {
             // a small directory is packed right here through the descriptor that is already
             // open, a large one is cut into runs that any worker takes
             const uint32_t n = (uint32_t)names.size();
-            if (n <= 2 * kPackRun) {
+            // (copy mode: creating files serialises on the directory's lock, so one directory is one
+            // worker's unless it is huge -- the workers are then in different directories)
+            if (n <= 2 * kPackRun || (copy_ && n <= 8192)) {
                 pack(W, dir, 0, n, dfd);
             } else {
                 for (uint32_t lo = kPackRun; lo < n; lo += kPackRun) push_task(Task{dir, lo, std::min(n, lo + kPackRun), 1});
@@ -773,11 +820,41 @@ private:
         }
         std::string name;
         const char *base = dir->names.data();
-        size_t hashed = 0, cached = 0;
+        size_t hashed = 0, cached = 0, linked = 0;
+        const bool try_cache = !copy_ && cache_nonempty();
+        int ddfd = -1;                                         // copy mode: the destination directory
+        if (copy_) {
+            ddfd = ::open((copy_->dest + "/" + dir->rel).c_str(), O_RDONLY | O_DIRECTORY | O_CLOEXEC);
+            if (ddfd < 0) {
+                const int err = errno;
+                for (uint32_t i = lo; i < hi; i++)
+                    if (dir->entries[i].kind == 1) {
+                        dir->entries[i].err = err;
+                        dir->entries[i].err_op = 2 | 0x80;
+                    }
+                if (dfd_in < 0) ::close(dfd);
+                return;
+            }
+        }
         for (uint32_t i = lo; i < hi && !abort_.load(); i++) {
             TEntry &e = dir->entries[i];
             if (e.kind != 1) continue;
             name.assign(base + e.name_off, e.name_len);
+            if (copy_ && !copy_->no_link && ::linkat(dfd, name.c_str(), ddfd, name.c_str(), 0) == 0) {
+                linked++;                                      // "whee" (build.go:392-395): nothing to read
+                continue;
+            }
+            if (try_cache) {                                   // after copyToBuildDir: an lstat decides, the file is not opened
+                struct stat cst;
+                if (fstatat(dfd, name.c_str(), &cst, AT_SYMLINK_NOFOLLOW) == 0 && S_ISREG(cst.st_mode) &&
+                    cache_lookup(cst, e.digest)) {
+                    e.mode = cst.st_mode;
+                    e.size = cst.st_size;
+                    e.cached = true;
+                    cached++;
+                    continue;
+                }
+            }
             // O_NONBLOCK: should the name have become a fifo since the scan, the open returns
             int fd = ::openat(dfd, name.c_str(), O_RDONLY | O_CLOEXEC | O_NOFOLLOW | O_NONBLOCK | (W.noatime ? O_NOATIME : 0));
             if (fd < 0 && errno == EPERM && W.noatime) {     // O_NOATIME is for the owner only
@@ -803,14 +880,19 @@ private:
                 ::close(fd);
                 continue;
             }
-            if (cache_lookup(st, e.digest)) {
+            if (!copy_ && cache_lookup(st, e.digest)) {
                 e.cached = true;
                 cached++;
                 ::close(fd);
                 continue;
             }
-            hashed++;
             const uint64_t size = (uint64_t)st.st_size;
+            if (copy_ && size > kMidMax) {                   // too long for a chunk: plain io.Copy, hashed later by writeHashes
+                ::close(fd);
+                plain_copy(dir->path + "/" + name, copy_->dest + "/" + dir->rel + name, st.st_mode, e);
+                continue;
+            }
+            hashed++;
             if (size > kMidMax) {                            // a chain of its own
                 ::close(fd);
                 chains.add(dir->path + "/" + name, e.digest, &e.err, &e.err_op);
@@ -843,8 +925,40 @@ private:
                 continue;
             }
             if (got > size) {                                // grew after its fstat: hashed to EOF as a chain, like io.Copy would
-                chains.add(dir->path + "/" + name, e.digest, &e.err, &e.err_op);
+                if (copy_) plain_copy(dir->path + "/" + name, copy_->dest + "/" + dir->rel + name, st.st_mode, e);
+                else chains.add(dir->path + "/" + name, e.digest, &e.err, &e.err_op);
                 continue;
+            }
+            if (copy_) {
+                // the same bytes the GPU is about to hash go to the destination (build.go:403-414)
+                const int out = ::openat(ddfd, name.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_CLOEXEC, st.st_mode & 07777);
+                if (out < 0) {
+                    e.err = errno;
+                    e.err_op = 2 | 0x80;
+                    continue;
+                }
+                struct stat wst;
+                int werr = 0;
+                for (size_t done = 0; done < got && !werr;) {
+                    const ssize_t w = ::write(out, dst + done, got - done);
+                    if (w < 0 && errno == EINTR) continue;
+                    if (w < 0) werr = errno;
+                    else done += (size_t)w;
+                }
+                if (!werr && fstat(out, &wst) != 0) werr = errno;
+                if (::close(out) != 0 && !werr) werr = errno;
+                if (werr) {
+                    e.err = werr;
+                    e.err_op = 5 | 0x80;
+                    continue;
+                }
+                CopyRec &r = dir->copies[i];
+                r.written = true;
+                r.dev = wst.st_dev;
+                r.ino = wst.st_ino;
+                r.size = wst.st_size;
+                r.mtime = wst.st_mtim;
+                r.ctime = wst.st_ctim;
             }
             c->files.push_back(PackedRef{e.digest, (uint32_t)c->used, (uint32_t)got});
             c->used += align_up(got + 1);
@@ -853,11 +967,60 @@ private:
             if (hungry_.load(std::memory_order_relaxed) && c->used >= kHungryFlush) flush_chunk(W, cls);
         }
         if (dfd_in < 0) ::close(dfd);
+        if (ddfd >= 0) ::close(ddfd);
         nhashed_ += hashed;
         ncached_ += cached;
+        nlinked_ += linked;
+    }
+
+    // io.Copy of one entry without the GPU (build.go:396-416): what cannot go through a chunk.  Its
+    // digest is not remembered; the writeHashes that follows reads the copy.
+    static void plain_copy(const std::string &src, const std::string &dest, mode_t mode, TEntry &e) {
+        const int in = ::open(src.c_str(), O_RDONLY | O_CLOEXEC);
+        if (in < 0) {
+            e.err = errno;
+            e.err_op = 2;
+            return;
+        }
+        const int out = ::open(dest.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_CLOEXEC, mode & 07777);
+        if (out < 0) {
+            e.err = errno;
+            e.err_op = 2 | 0x80;
+            ::close(in);
+            return;
+        }
+        std::vector<uint8_t> buf(1 << 20);
+        for (;;) {
+            const ssize_t r = ::read(in, buf.data(), buf.size());
+            if (r < 0 && errno == EINTR) continue;
+            if (r < 0) {
+                e.err = errno;
+                e.err_op = 3;
+                break;
+            }
+            if (r == 0) break;
+            ssize_t done = 0;
+            while (done < r) {
+                const ssize_t w = ::write(out, buf.data() + done, (size_t)(r - done));
+                if (w < 0 && errno == EINTR) continue;
+                if (w < 0) {
+                    e.err = errno;
+                    e.err_op = 5 | 0x80;
+                    break;
+                }
+                done += w;
+            }
+            if (e.err) break;
+        }
+        ::close(in);
+        if (::close(out) != 0 && !e.err) {
+            e.err = errno;
+            e.err_op = 5 | 0x80;
+        }
     }
 
     static bool cache_lookup(const struct stat &st, uint8_t digest[64]);
+    static bool cache_nonempty();
 
     // ---- the driving thread: chunk allocation, batch submission, chunk recycling --------------
     void drive() {
@@ -889,7 +1052,7 @@ private:
             }
             // chunks whose copy has finished go back to the pool
             copied.clear();
-            int rc = session_poll(session_, &copied, false);
+            int rc = poll_session(&copied, false);
             if (rc) { fatal(rc); break; }
             if (recycle(copied)) progressed = true;
             // Submit what is ready when a slot is free -- but not crumbs: every batch costs the GPU at
@@ -899,11 +1062,11 @@ private:
             // slot is taken the chunks keep collecting and the next batch is as large as the GPU's
             // pace allows.
             take.clear();
-            if (session_in_flight(session_) < session_capacity(session_)) {
+            if (in_flight() < capacity()) {
                 std::lock_guard<std::mutex> lk(r_mu_);
                 size_t bytes = 0, items = 0;
                 const bool workers_done = workers_done_ == nworkers;
-                if (!workers_done && session_in_flight(session_) > 0) {
+                if (!workers_done && in_flight() > 0) {
                     size_t ready_bytes = 0;
                     for (Chunk *c : ready_) ready_bytes += c->used;
                     if (ready_bytes < kMinBatch) bytes = cap_bytes + 1;          // not yet
@@ -918,7 +1081,7 @@ private:
                 }
                 all_done = workers_done_ == nworkers && ready_.empty();
             }
-            hungry_.store(take.empty() && session_in_flight(session_) == 0, std::memory_order_relaxed);
+            hungry_.store(take.empty() && in_flight() == 0, std::memory_order_relaxed);
             if (!take.empty()) {
                 spans.clear();
                 segs.clear();
@@ -933,7 +1096,9 @@ private:
                 uint64_t ticket = 0;
                 copied.clear();
                 const double t_submit = wall_ms();
-                rc = session_submit(session_, spans.data(), spans.size(), segs.data(), dst.data(), segs.size(), &ticket, &copied);
+                rc = 0;
+                if (!session_ && !(rc = ensure_init())) rc = session_open(&session_, kTreeBatchBytes);     // copy mode: first batch
+                if (!rc) rc = session_submit(session_, spans.data(), spans.size(), segs.data(), dst.data(), segs.size(), &ticket, &copied);
                 if (rc) { fatal(rc); break; }
                 in_copy_.emplace_back(ticket, take);
                 recycle(copied);
@@ -942,7 +1107,7 @@ private:
                     size_t bytes = 0;
                     for (Chunk *c : take) bytes += c->used;
                     fprintf(stderr, "[snapgpu] tree batch %zu at %.2f ms: %zu chunks, %.1f MiB, %zu files; %zu in flight, submit took %.2f ms\n",
-                            nbatches_, wall_ms() - t_start, take.size(), bytes / 1048576.0, segs.size(), session_in_flight(session_),
+                            nbatches_, wall_ms() - t_start, take.size(), bytes / 1048576.0, segs.size(), in_flight(),
                             wall_ms() - t_submit);
                 }
                 continue;
@@ -950,7 +1115,7 @@ private:
             if (all_done) break;
             if (!progressed) {
                 std::unique_lock<std::mutex> lk(r_mu_);
-                r_cv_.wait_for(lk, std::chrono::microseconds(session_in_flight(session_) ? 50 : 300));
+                r_cv_.wait_for(lk, std::chrono::microseconds(in_flight() ? 50 : 300));
             }
         }
         if (fatal_rc_) {
@@ -967,7 +1132,7 @@ private:
             }
         }
         const double t0 = wall_ms();
-        if (trace) fprintf(stderr, "[snapgpu] tree: workers done at %.2f ms, %zu batches in flight\n", t0 - t_start, session_in_flight(session_));
+        if (trace) fprintf(stderr, "[snapgpu] tree: workers done at %.2f ms, %zu batches in flight\n", t0 - t_start, in_flight());
         // every directory has been read: the walk order can be laid out while the last batches are
         // still on the GPU (it needs names and modes, not digests)
         if (!fatal_rc_) {
@@ -975,13 +1140,17 @@ private:
             flattened_ = true;
         }
         copied.clear();
-        int rc = session_poll(session_, &copied, true);
+        int rc = poll_session(&copied, true);
         if (rc && !fatal_rc_) fatal(rc);
         for (auto &p : in_copy_)
             for (Chunk *c : p.second) (c->cls ? large_chunks() : small_chunks()).put(c);
         in_copy_.clear();
         t_drain_ms_ = wall_ms() - t0;
     }
+    // the session opens with the first batch in copy mode (a tree that hard-links needs no GPU)
+    size_t in_flight() const { return session_ ? session_in_flight(session_) : 0; }
+    size_t capacity() const { return session_ ? session_capacity(session_) : 1; }
+    int poll_session(std::vector<uint64_t> *copied, bool wait_all) { return session_ ? session_poll(session_, copied, wait_all) : 0; }
     bool recycle(const std::vector<uint64_t> &copied) {
         bool any = false;
         for (uint64_t t : copied)
@@ -1014,13 +1183,14 @@ private:
 
     const std::string root_;
     const bool hash_;
+    const CopySpec *const copy_;
     std::vector<FlatEntry> flat_;
     bool flattened_ = false;
     BatchSession *session_ = nullptr;
     TDir *root_dir_ = nullptr;
     std::mutex dirs_mu_;
     std::vector<TDir *> dirs_;
-    std::atomic<size_t> nentries_{0}, nhashed_{0}, ncached_{0};
+    std::atomic<size_t> nentries_{0}, nhashed_{0}, ncached_{0}, nlinked_{0};
     // task queue
     std::mutex q_mu_;
     std::condition_variable q_cv_;
