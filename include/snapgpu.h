@@ -168,8 +168,9 @@ int snapgpu_apparmor_delta(const char *old_path, const char *new_path, const cha
  * order skipping shouldExclude names (snappy/build.go:52-83; directories with their subtree),
  * creates directories with the source's mode, hard-links files and copies what cannot be linked.
  * Copied files are read ONCE: the bytes go to the build dir and through the SHA-512 kernel in the
- * same pass, and the digest is kept (keyed by device, inode, size, mtime of the written file) so
- * that the snapgpu_write_hashes that follows does not read them again.  On error the copy may be
+ * same pass, and the digest is kept (keyed by device and inode of the written file, valid while its
+ * size, mtime and ctime stay what they were) for the ONE snapgpu_write_hashes that follows, which then
+ * does not read them again.  On error the copy may be
  * partial, as in the reference.  flags: SNAPGPU_COPY_NO_LINK = never hard-link. */
 #define SNAPGPU_COPY_NO_LINK 1
 int snapgpu_copy_to_build_dir(const char *source_dir, const char *build_dir, int flags);

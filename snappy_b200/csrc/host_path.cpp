@@ -159,306 +159,15 @@ int stream_file(const std::string &path, uint8_t *buf, size_t cap, uint8_t diges
     return stream_fd(fd, path, buf, cap, digest);
 }
 
-// What the packer did with one file of a batch.
-struct PackedFile {
-    size_t index;          // position in `paths`
-    uint64_t off;          // slot in the batch buffer (16-byte aligned)
-    uint64_t planned;      // bytes reserved (size at stat time)
-    uint64_t len = 0;      // bytes read
-    int err = 0;           // errno of a failed open/read
-    const char *op = "";   // "open" / "read"
-    bool grew = false;     // more bytes than planned: re-hashed through stream_file
-};
-
-// One file into its slot: open, ONE read of planned+1 bytes, close.  For a regular file a read
-// that returns exactly the size it had at stat time has reached EOF (the slot has one spare
-// byte, so a file that grew shows up as planned+1 bytes and is re-hashed by streaming); only a
-// file that shrank needs the io.Copy-style "read until 0" loop.
-void pack_one(const std::string &path, uint8_t *buf, PackedFile &f) {
-    int fd = ::open(path.c_str(), O_RDONLY | O_CLOEXEC);
-    if (fd < 0) {
-        f.err = errno;
-        f.op = "open";
-        return;
-    }
-    uint8_t *dst = buf + f.off;
-    const size_t want = f.planned + 1;
-    size_t got = 0;
-    for (;;) {
-        ssize_t r = ::read(fd, dst + got, want - got);
-        if (r < 0) {
-            if (errno == EINTR) continue;
-            f.err = errno;
-            f.op = "read";
-            break;
-        }
-        got += (size_t)r;
-        if (r == 0 || got == f.planned || got == want) break;
-    }
-    if (!f.err) {
-        f.grew = got > f.planned;
-        f.len = std::min<uint64_t>(got, f.planned);
-    }
-    ::close(fd);
-}
-
-unsigned packer_threads(size_t nfiles) {
-    static const unsigned env = [] {
-        const char *e = getenv("SNAPGPU_PACK_THREADS");
-        return e ? (unsigned)atoi(e) : 0u;
-    }();
-    unsigned t = env ? env : std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
-    return (unsigned)std::min<size_t>(t, std::max<size_t>(1, nfiles / 16));
-}
-
-// Hash every file of `paths` (in order).  digests: paths.size()*64.  On the first I/O error (in
-// list order) returns SNAPGPU_EIO with a Go-style message, like the reference aborts its walk.
-//
-// The reference reads and hashes one file at a time (snappy/build.go:240-247).  Here the list
-// is cut into batches of up to host_ring_bytes(); a batch's files are read by several host
-// threads straight into their 16-byte aligned slots of a pinned buffer, and while the GPU
-// hashes batch k (one sha512_host_segments call) the threads already pack batch k+1 into the
-// other buffer.  size_hint (optional) carries the walk's lstat sizes so files are not stat'ed twice.
-// sink (optional): called once per file while its bytes sit in the pinned buffer -- from several
-// threads, concurrently with the GPU call of that batch -- so that a caller can write the same
-// bytes somewhere (copyToBuildDir) without reading the file a second time.  bytes == nullptr means
-// the file did not go through a batch (larger than a batch, or it grew): the sink copies it itself.
-typedef std::function<int(size_t index, const uint8_t *bytes, uint64_t len)> FileSink;
-
-// One more, long file hashed ALONGSIDE a list (writeHashes' data.tar.gz): a single SHA-512
-// chain runs at ~70 MB/s on the GPU however idle the rest of it is, so instead of sitting in
-// one batch and stretching that batch's GPU call, the file rides along in slices -- every
-// batch's launch carries the next slice as a continuation segment (the long-file kernel hashes
-// it beside the batched kernel), sized to what the packer needs for the next batch anyway.
-// What is left after the last batch is streamed at the end.
-struct Rider {
-    std::string path;
-    uint8_t digest[64] = {0};
-};
-
-int hash_files(const std::vector<std::string> &paths, std::vector<uint8_t> &digests,
-               const std::vector<int64_t> *size_hint = nullptr, const FileSink *sink = nullptr,
-               Rider *rider = nullptr) {
-    digests.assign(paths.size() * 64, 0);
-    if (paths.empty() && !rider) return 0;
+// helpers.Sha512sum of ONE file (helpers/helpers.go:188-201): streamed through a pinned buffer in
+// pieces, the chaining value carried between GPU calls.  (Trees go through tree_hasher.hpp.)
+int hash_one_file(const std::string &path, uint8_t digest[64]) {
     int rc = ensure_init();
     if (rc) return rc;
     Staging &S = staging();
     std::lock_guard<std::mutex> lock(S.mu);
-    // the rider is opened first: like build.go:222-226 a missing archive is the first error
-    int rider_fd = -1;
-    if (rider) {
-        rider_fd = ::open(rider->path.c_str(), O_RDONLY | O_CLOEXEC);
-        if (rider_fd < 0) return fail(SNAPGPU_EIO, "%s", go_path_error("open", rider->path, errno).c_str());
-    }
-    struct FdGuard {
-        int &fd;
-        ~FdGuard() { if (fd >= 0) ::close(fd); }
-    } rider_guard{rider_fd};
-    if (paths.empty()) {
-        if ((rc = ring_acquire(S, (size_t)16 << 20))) return rc;
-        const int fd = rider_fd;
-        rider_fd = -1;                                       // stream_fd closes it
-        return stream_fd(fd, rider->path, S.ring[0], S.ring_cap, rider->digest);
-    }
-    const size_t n = paths.size();
-    const unsigned nthreads = packer_threads(n);
-
-    auto parallel_for = [&](size_t count, const std::function<void(size_t)> &fn) {
-        if (nthreads <= 1 || count < 32) {
-            for (size_t i = 0; i < count; i++) fn(i);
-            return;
-        }
-        std::atomic<size_t> next{0};
-        auto work = [&]() {
-            for (;;) {
-                const size_t i0 = next.fetch_add(8);
-                if (i0 >= count) break;
-                for (size_t i = i0; i < std::min(count, i0 + 8); i++) fn(i);
-            }
-        };
-        std::vector<std::thread> th;
-        for (unsigned t = 1; t < nthreads; t++) th.emplace_back(work);
-        work();
-        for (auto &x : th) x.join();
-    };
-
-    // sizes at plan time (a file that is missing plans 0 bytes; its open fails in pack_one)
-    std::vector<uint64_t> planned(n, 0);
-    parallel_for(n, [&](size_t i) {
-        if (size_hint && (*size_hint)[i] >= 0) {
-            planned[i] = (uint64_t)(*size_hint)[i];
-            return;
-        }
-        struct stat st;
-        if (stat(paths[i].c_str(), &st) == 0 && S_ISREG(st.st_mode)) planned[i] = (uint64_t)st.st_size;
-    });
-
-    // pinned ring sized to the job (pinning memory costs ~0.4 ms per MiB): 16 MiB .. host_ring_bytes()
-    uint64_t total = 0;
-    for (size_t i = 0; i < n; i++) total += align_up(planned[i] + 1);
-    size_t want = (size_t)16 << 20;
-    while (want < total + 4096 && want < host_ring_bytes()) want <<= 1;
-    want = std::min(want, std::max(host_ring_bytes(), (size_t)1 << 20));
-    if ((rc = ring_acquire(S, want))) return rc;
-    const size_t cap = S.ring_cap;
-
-    // batches: consecutive files whose slots fit one buffer; a file that does not fit alone is
-    // a batch of its own and is streamed
-    struct Batch { size_t first, count; bool streamed; };
-    std::vector<Batch> batches;
-    // the rider's slice sits at the start of each buffer, so that it is part of the first chunk the
-    // GPU call uploads and its chain starts at once: 1/384 of the buffer (~0.7 MiB of a 256 MiB
-    // batch is ~10 ms of chain, what packing the next batch takes anyway), a multiple of 128 bytes
-    const size_t slice = rider ? std::min<size_t>(std::max<size_t>(cap / 384, (size_t)128 << 10), (size_t)1 << 20) & ~(size_t)127 : 0;
-    const size_t rider_off = 0;
-    const size_t room = cap - 256 - slice;
-    struct RiderPiece { size_t len = 0; bool eof = false; int err = 0; } piece[2];
-    bool rider_eof_read = false;                             // touched by the (sequential) fills only
-    for (size_t i = 0; i < n;) {
-        if (planned[i] + 1 > room) {
-            batches.push_back(Batch{i, 1, true});
-            i++;
-            continue;
-        }
-        size_t used = 0, j = i;
-        while (j < n && planned[j] <= room && align_up(used) + planned[j] + 1 <= room) {
-            used = align_up(used) + planned[j] + 1;            // one spare byte per slot, see pack_one
-            j++;
-        }
-        batches.push_back(Batch{i, j - i, false});
-        i = j;
-    }
-
-    std::vector<PackedFile> packed[2];
-    auto fill = [&](size_t bi) {
-        const Batch &B = batches[bi];
-        std::vector<PackedFile> &pf = packed[bi & 1];
-        pf.clear();
-        piece[bi & 1] = RiderPiece();
-        if (B.streamed) return;
-        size_t used = slice;                                 // files follow the rider's slice
-        for (size_t k = 0; k < B.count; k++) {
-            used = align_up(used);
-            PackedFile f;
-            f.index = B.first + k;
-            f.off = used;
-            f.planned = planned[f.index];
-            pf.push_back(f);
-            used += f.planned + 1;
-        }
-        uint8_t *buf = S.ring[bi & 1];
-        std::thread rider_reader;
-        if (rider && !rider_eof_read)                        // the next slice, read beside the packers
-            rider_reader = std::thread([&, buf, bi]() {
-                RiderPiece &rp = piece[bi & 1];
-                const ssize_t r = read_full(rider_fd, buf + rider_off, slice);
-                if (r < 0) {
-                    rp.err = errno;
-                    rider_eof_read = true;
-                    return;
-                }
-                rp.len = (size_t)r;
-                rp.eof = rider_eof_read = (size_t)r < slice;
-            });
-        parallel_for(pf.size(), [&](size_t k) { pack_one(paths[pf[k].index], buf, pf[k]); });
-        if (rider_reader.joinable()) rider_reader.join();
-    };
-
-    std::vector<HostSeg> segs;
-    std::vector<uint8_t> out;
-    std::thread prefetch;
-    uint64_t rider_prefix = 0;
-    bool rider_done = false;
-    fill(0);
-    for (size_t bi = 0; bi < batches.size() && !rc; bi++) {
-        const double tb0 = wall_ms();
-        if (prefetch.joinable()) prefetch.join();             // batch bi is packed
-        const double tb1 = wall_ms();
-        if (bi + 1 < batches.size()) prefetch = std::thread(fill, bi + 1);
-        const Batch &B = batches[bi];
-        uint8_t *buf = S.ring[bi & 1];
-        if (B.streamed) {
-            rc = stream_file(paths[B.first], buf, cap, &digests[64 * B.first]);
-            if (!rc && sink) rc = (*sink)(B.first, nullptr, 0);
-            continue;
-        }
-        std::vector<PackedFile> &pf = packed[bi & 1];
-        for (const PackedFile &f : pf)
-            if (f.err) {                                      // first failing file in list order
-                rc = fail(SNAPGPU_EIO, "%s", go_path_error(f.op, paths[f.index], f.err).c_str());
-                break;
-            }
-        if (rc) break;
-        const RiderPiece rp = piece[bi & 1];
-        if (rp.err) {
-            rc = fail(SNAPGPU_EIO, "%s", go_path_error("read", rider->path, rp.err).c_str());
-            break;
-        }
-        // segment 0 is the rider's slice (when there is one), the files follow
-        const bool ride = rider && !rider_done && (rp.len > 0 || rp.eof);
-        const size_t base = ride ? 1 : 0;
-        segs.clear();
-        if (ride)
-            segs.push_back(HostSeg{rider_off, rp.len, rider_prefix,
-                                   (rider_prefix ? kHostSegContinue : 0u) | (rp.eof ? 0u : kHostSegNoFinal)});
-        for (const PackedFile &f : pf) segs.push_back(HostSeg{f.off, f.grew ? 0 : f.len, 0, 0});
-        out.resize(segs.size() * 64);
-        if (ride) memcpy(&out[0], rider->digest, 64);                    // the chaining value so far
-        // the sink reads the same pinned bytes the GPU copy engine reads: it runs beside the GPU call
-        std::vector<int> sink_rc;
-        std::vector<std::string> sink_err;
-        std::thread sink_thread;
-        if (sink) {
-            sink_rc.assign(pf.size(), 0);
-            sink_err.resize(pf.size());
-            sink_thread = std::thread([&]() {
-                // contiguous ranges, one per thread: neighbouring files live in the same directory and
-                // creating files there serialises on the directory's lock, so threads should be in
-                // different directories at any one time
-                const size_t nt = std::max<size_t>(1, std::min<size_t>(nthreads, pf.size() / 64));
-                auto run = [&](size_t t) {
-                    for (size_t k = pf.size() * t / nt; k < pf.size() * (t + 1) / nt; k++) {
-                        const PackedFile &f = pf[k];
-                        sink_rc[k] = f.grew ? (*sink)(f.index, nullptr, 0) : (*sink)(f.index, buf + f.off, f.len);
-                        if (sink_rc[k]) sink_err[k] = snapgpu_last_error();
-                    }
-                };
-                const double ts = wall_ms();
-                std::vector<std::thread> th;
-                for (size_t t = 1; t < nt; t++) th.emplace_back(run, t);
-                run(0);
-                for (auto &x : th) x.join();
-                if (getenv("SNAPGPU_TRACE"))
-                    fprintf(stderr, "[snapgpu] batch %zu: sink wrote %zu files in %.2f ms on %zu threads\n", bi, pf.size(),
-                            wall_ms() - ts, nt);
-            });
-        }
-        rc = sha512_host_segments(buf, segs.data(), segs.size(), out.data());
-        if (sink_thread.joinable()) sink_thread.join();
-        if (rc) break;
-        for (size_t k = 0; k < sink_rc.size() && !rc; k++)
-            if (sink_rc[k]) rc = fail(sink_rc[k], "%s", sink_err[k].c_str());
-        if (rc) break;
-        if (getenv("SNAPGPU_TRACE"))
-            fprintf(stderr, "[snapgpu] batch %zu: %zu files, waited %.2f ms for the packer, GPU call %.2f ms\n", bi, pf.size(),
-                    tb1 - tb0, wall_ms() - tb1);
-        for (size_t k = 0; k < pf.size(); k++) memcpy(&digests[64 * pf[k].index], &out[64 * (k + base)], 64);
-        if (ride) {
-            memcpy(rider->digest, &out[0], 64);
-            rider_prefix += rp.len;
-            rider_done = rp.eof;
-        }
-        for (const PackedFile &f : pf)                        // rare: the file grew after its stat
-            if (f.grew && (rc = stream_file(paths[f.index], buf, cap, &digests[64 * f.index]))) break;
-    }
-    if (prefetch.joinable()) prefetch.join();
-    if (!rc && rider && !rider_done) {                        // what the batches did not carry
-        const int fd = rider_fd;
-        rider_fd = -1;                                        // stream_fd closes it
-        rc = stream_fd(fd, rider->path, S.ring[0], cap, rider->digest, rider_prefix);
-    }
-    return rc;
+    if ((rc = ring_acquire(S, std::min<size_t>(host_ring_bytes(), (size_t)16 << 20)))) return rc;
+    return stream_file(path, S.ring[0], S.ring_cap, digest);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1175,9 +884,6 @@ void cache_put(dev_t dev, ino_t ino, off_t size, const struct timespec &mtime, c
     std::lock_guard<std::mutex> lock(S.mu);
     if (S.map.insert_or_assign(std::make_pair(dev, ino), d).second) C.entries++;
 }
-void cache_put(const struct stat &st, const uint8_t digest[64]) {
-    cache_put(st.st_dev, st.st_ino, st.st_size, st.st_mtim, st.st_ctim, digest);
-}
 bool cache_get(const struct stat &st, uint8_t digest[64]) {
     DigestCache &C = digest_cache();
     if (C.entries.load(std::memory_order_relaxed) == 0) return false;     // the usual case, without a lock
@@ -1868,80 +1574,6 @@ std::string base_name(const std::string &p) {           // filepath.Base of a cl
     return k == std::string::npos ? p : p.substr(k + 1);
 }
 
-struct CopyAction {
-    std::string src, dest;
-    struct stat st;          // lstat of the source
-};
-
-// The Walk of copyToBuildDir: pre-order, sorted names, Lstat; excluded names are skipped
-// (directories with their whole subtree).  A directory that cannot be read, or an entry that
-// cannot be lstat'ed, is the error Walk hands to the callback and the callback returns.
-int copy_walk(const std::string &src, const std::string &dest, const struct stat &st, std::vector<CopyAction> &out,
-              bool top_level = false) {
-    if (should_exclude(base_name(src))) return 0;
-    out.push_back(CopyAction{src, dest, st});
-    if (!S_ISDIR(st.st_mode)) return 0;
-    DIR *d = opendir(src.c_str());
-    if (!d) return fail(SNAPGPU_EIO, "%s", go_path_error("open", src, errno).c_str());
-    std::vector<std::string> names;
-    while (struct dirent *e = readdir(d)) {
-        if (!strcmp(e->d_name, ".") || !strcmp(e->d_name, "..")) continue;
-        names.emplace_back(e->d_name);
-    }
-    std::sort(names.begin(), names.end());
-    const int dfd = dirfd(d);
-    std::vector<struct stat> sts(names.size());
-    for (size_t i = 0; i < names.size(); i++)
-        if (fstatat(dfd, names[i].c_str(), &sts[i], AT_SYMLINK_NOFOLLOW) != 0) {
-            const int e = errno;
-            closedir(d);
-            return fail(SNAPGPU_EIO, "%s", go_path_error("lstat", src + "/" + names[i], e).c_str());
-        }
-    closedir(d);
-
-    // sub-directories of the root: walked by several threads, each into its own list, and
-    // stitched back in Walk order below (the first error in that order is the one returned)
-    std::vector<size_t> subdirs;
-    if (top_level)
-        for (size_t i = 0; i < names.size(); i++)
-            if (S_ISDIR(sts[i].st_mode)) subdirs.push_back(i);
-    const unsigned nthreads = std::min<unsigned>(packer_threads(16 * subdirs.size()), (unsigned)subdirs.size());
-    if (nthreads >= 2) {
-        std::vector<std::vector<CopyAction>> sub(subdirs.size());
-        std::vector<int> sub_rc(subdirs.size(), 0);
-        std::vector<std::string> sub_err(subdirs.size());
-        std::atomic<size_t> next{0};
-        auto work = [&]() {
-            for (size_t k; (k = next.fetch_add(1)) < subdirs.size();) {
-                const size_t i = subdirs[k];
-                sub_rc[k] = copy_walk(src + "/" + names[i], dest + "/" + names[i], sts[i], sub[k]);
-                if (sub_rc[k]) sub_err[k] = snapgpu_last_error();
-            }
-        };
-        std::vector<std::thread> th;
-        for (unsigned t = 1; t < nthreads; t++) th.emplace_back(work);
-        work();
-        for (auto &x : th) x.join();
-        size_t k = 0;
-        for (size_t i = 0; i < names.size(); i++) {
-            if (S_ISDIR(sts[i].st_mode)) {
-                if (sub_rc[k]) return fail(sub_rc[k], "%s", sub_err[k].c_str());
-                out.insert(out.end(), std::make_move_iterator(sub[k].begin()), std::make_move_iterator(sub[k].end()));
-                k++;
-            } else {
-                int rc = copy_walk(src + "/" + names[i], dest + "/" + names[i], sts[i], out);
-                if (rc) return rc;
-            }
-        }
-        return 0;
-    }
-    for (size_t i = 0; i < names.size(); i++) {
-        int rc = copy_walk(src + "/" + names[i], dest + "/" + names[i], sts[i], out);
-        if (rc) return rc;
-    }
-    return 0;
-}
-
 int write_all(int fd, const uint8_t *p, uint64_t n) {
     while (n) {
         ssize_t w = ::write(fd, p, n);
@@ -2000,97 +1632,32 @@ int copy_to_build_dir(const std::string &source_in, const std::string &build_dir
                     tree.flat().size(), tree.files_linked(), tree.files_hashed(), remembered, tree.batches(), wall_ms() - tc0);
         return 0;
     }
-    // a source that is not a directory (Walk visits just it): round 1's path
-    std::vector<CopyAction> actions;
-    const double t0 = wall_ms();
-    int rc = copy_walk(source, build_dir, root, actions, true);
-    if (rc) return rc;
-    const double t1 = wall_ms();
-
-    // directories, then links; what cannot be linked is copied below
-    std::vector<size_t> to_copy;
-    for (size_t i = 0; i < actions.size(); i++) {
-        const CopyAction &a = actions[i];
-        if (S_ISDIR(a.st.st_mode) && mkdir(a.dest.c_str(), a.st.st_mode & 07777) != 0)
-            return fail(SNAPGPU_EIO, "%s", go_path_error("mkdir", a.dest, errno).c_str());
+    // a source that is not a directory: Walk visits just it -- linked, or copied the way build.go:391-416 does
+    if (should_exclude(base_name(source))) return 0;
+    if (!(flags & SNAPGPU_COPY_NO_LINK) && link(source.c_str(), build_dir.c_str()) == 0) return 0;
+    const int in = ::open(source.c_str(), O_RDONLY | O_CLOEXEC);
+    if (in < 0) return fail(SNAPGPU_EIO, "%s", go_path_error("open", source, errno).c_str());
+    const int out = ::open(build_dir.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_CLOEXEC, root.st_mode & 07777);
+    if (out < 0) {
+        const int e = errno;
+        ::close(in);
+        return fail(SNAPGPU_EIO, "%s", go_path_error("open", build_dir, e).c_str());
     }
-    {
-        // link() for every non-directory, contiguous ranges of the walk per thread (threads then
-        // work in different directories); a failed link is not an error, the entry is copied
-        std::vector<uint8_t> need_copy(actions.size(), 0);
-        const size_t nt = (flags & SNAPGPU_COPY_NO_LINK) ? 1 : std::max<size_t>(1, packer_threads(actions.size() / 64));
-        auto run = [&](size_t t) {
-            for (size_t i = actions.size() * t / nt; i < actions.size() * (t + 1) / nt; i++) {
-                const CopyAction &a = actions[i];
-                if (S_ISDIR(a.st.st_mode)) continue;
-                need_copy[i] = (flags & SNAPGPU_COPY_NO_LINK) || link(a.src.c_str(), a.dest.c_str()) != 0;
-            }
-        };
-        std::vector<std::thread> th;
-        for (size_t t = 1; t < nt; t++) th.emplace_back(run, t);
-        run(0);
-        for (auto &x : th) x.join();
-        for (size_t i = 0; i < actions.size(); i++)
-            if (need_copy[i]) to_copy.push_back(i);
-    }
-    const double t2 = wall_ms();
-    if (to_copy.empty()) {
-        if (getenv("SNAPGPU_TRACE"))
-            fprintf(stderr, "[snapgpu] copyToBuildDir: walk %.2f ms (%zu entries), mkdir/link %.2f ms, nothing to copy\n",
-                    t1 - t0, actions.size(), t2 - t1);
-        return 0;
-    }
-
-    std::vector<std::string> paths;
-    std::vector<int64_t> sizes;
-    for (size_t i : to_copy) {
-        paths.push_back(actions[i].src);
-        sizes.push_back(S_ISREG(actions[i].st.st_mode) ? (int64_t)actions[i].st.st_size : 0);
-    }
-    std::vector<struct stat> written(to_copy.size());
-    // Only a file whose bytes went to the build dir out of the pinned batch -- the very bytes the
-    // GPU hashed -- gets its digest remembered.  One that grew, or is larger than a batch, is
-    // hashed from one read of the source and copied from another: its digest is not cached, the
-    // writeHashes that follows reads the copy.
-    std::vector<uint8_t> same_bytes(to_copy.size(), 0);
-    FileSink sink = [&](size_t k, const uint8_t *bytes, uint64_t len) -> int {
-        const CopyAction &a = actions[to_copy[k]];
-        int out = ::open(a.dest.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_CLOEXEC, a.st.st_mode & 07777);
-        if (out < 0) return fail(SNAPGPU_EIO, "%s", go_path_error("open", a.dest, errno).c_str());
-        int err = 0;
-        if (bytes) {
-            same_bytes[k] = 1;
-            if (write_all(out, bytes, len) != 0) err = errno;
-        } else {                                   // did not pass through a batch: plain io.Copy
-            int in = ::open(a.src.c_str(), O_RDONLY | O_CLOEXEC);
-            if (in < 0) {
-                err = errno;
-                ::close(out);
-                return fail(SNAPGPU_EIO, "%s", go_path_error("open", a.src, err).c_str());
-            }
-            std::vector<uint8_t> buf(1 << 20);
-            for (;;) {
-                ssize_t r = ::read(in, buf.data(), buf.size());
-                if (r < 0 && errno == EINTR) continue;
-                if (r < 0) { err = errno; break; }
-                if (r == 0) break;
-                if (write_all(out, buf.data(), (uint64_t)r) != 0) { err = errno; break; }
-            }
-            ::close(in);
+    std::vector<uint8_t> buf(1 << 20);
+    int err = 0;
+    for (;;) {
+        const ssize_t r = ::read(in, buf.data(), buf.size());
+        if (r < 0 && errno == EINTR) continue;
+        if (r < 0) err = errno;
+        if (r <= 0) break;
+        if (write_all(out, buf.data(), (uint64_t)r) != 0) {
+            err = errno;
+            break;
         }
-        if (!err && fstat(out, &written[k]) != 0) err = errno;
-        if (::close(out) != 0 && !err) err = errno;
-        if (err) return fail(SNAPGPU_EIO, "%s", go_path_error("write", a.dest, err).c_str());
-        return 0;
-    };
-    std::vector<uint8_t> digests;
-    if ((rc = hash_files(paths, digests, &sizes, &sink))) return rc;
-    const double t3 = wall_ms();
-    for (size_t k = 0; k < to_copy.size(); k++)
-        if (same_bytes[k]) cache_put(written[k], &digests[64 * k]);
-    if (getenv("SNAPGPU_TRACE"))
-        fprintf(stderr, "[snapgpu] copyToBuildDir: walk %.2f ms (%zu entries), mkdir/link %.2f ms, copy+hash %.2f ms (%zu files), cache %.2f ms\n",
-                t1 - t0, actions.size(), t2 - t1, t3 - t2, to_copy.size(), wall_ms() - t3);
+    }
+    ::close(in);
+    if (::close(out) != 0 && !err) err = errno;
+    if (err) return fail(SNAPGPU_EIO, "%s", go_path_error("write", build_dir, err).c_str());
     return 0;
 }
 
@@ -2119,13 +1686,13 @@ extern "C" {
 
 int snapgpu_sha512sum_file(const char *infile, char hexdigest[129]) {
     if (!infile || !hexdigest) return fail(SNAPGPU_EINVAL, "null argument");
-    std::vector<uint8_t> dg;
-    int rc = hash_files({std::string(infile)}, dg);
+    uint8_t dg[64];
+    int rc = hash_one_file(infile, dg);
     if (rc) {
         hexdigest[0] = 0;                                    // Go returns "" with the error
         return rc;
     }
-    std::string h = hex_lower(dg.data(), 64);
+    std::string h = hex_lower(dg, 64);
     memcpy(hexdigest, h.c_str(), 129);
     return 0;
 }

@@ -376,12 +376,13 @@ def test_tree_larger_than_host_staging(gpu, oracle, tmp_path):
 
 
 def test_archive_rides_along_in_slices(gpu, tmp_path):
-    """writeHashes hashes data.tar.gz (archive-sha512, snappy/build.go:222) in slices carried by the
-    tree's batches, the rest streamed at the end: every archive size around the slice boundaries gives
-    hashlib's digest, for a tree of several batches, of one batch, and with no regular file at all."""
+    """writeHashes hashes data.tar.gz (archive-sha512, snappy/build.go:222) as a chain of 2 MiB pieces that
+    starts before the walk and runs beside the tree's batches (round 1 carried it in slices inside them,
+    hence the name): every archive size around the piece boundaries gives hashlib's digest, for a tree of
+    several batches, of one batch, and with no regular file at all."""
     from snappy_b200 import build
     rng = np.random.default_rng(33)
-    gpu.set_option("staging_bytes", 1 << 20)            # 1 MiB batches, 128 KiB slices
+    gpu.set_option("staging_bytes", 1 << 20)            # small staging for the chain's calls
     big = tmp_path / "big"
     big.mkdir()
     for i in range(60):
@@ -392,7 +393,8 @@ def test_archive_rides_along_in_slices(gpu, tmp_path):
     empty = tmp_path / "empty"
     (empty / "sub").mkdir(parents=True)
     K = 128 << 10
-    sizes = [0, 1, 127, 128, K - 1, K, K + 1, 2 * K, 3 * K + 77, 5 * K, 9 * K + 128, (1 << 20) + 5, 3_000_001]
+    P = 2 << 20                                         # the chain streamer's piece
+    sizes = [0, 1, 127, 128, K - 1, K, K + 1, 3 * K + 77, (1 << 20) + 5, P - 1, P, P + 1, P + 128, 2 * P, 2 * P + 129, 3_000_001]
     for tree in (big, small, empty):
         for n in sizes:
             tar = tmp_path / "data.tar.gz"
