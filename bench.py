@@ -477,7 +477,9 @@ def main():
         del d_data
         torch.cuda.empty_cache()
         total_files = int(os.environ.get("SNAPGPU_CFG5_TOTAL", "2000000"))
-        per = total_files // world
+        from snappy_b200 import sharding
+        shards5 = sharding.contiguous_shards(np.full(total_files - total_files % world, 65536, dtype=np.uint64), world)
+        per = shards5[rank][1] - shards5[rank][0]                # uniform sizes: equal contiguous index ranges
         need5 = per * (65536 + 64 + 36 + 8) + (4 << 30)
         fits = torch.tensor([1.0 if torch.cuda.mem_get_info(dev)[0] > need5 else 0.0], device=dev)
         if world > 1:
@@ -486,7 +488,7 @@ def main():
         if not cfg5_fits and rank == 0:
             cfg5 = {"skipped": f"a rank has less than {need5 / 1e9:.0f} GB of free HBM for its {per} files x 64 KiB"}
     if cfg5_fits:
-        lo = rank * per
+        lo = shards5[rank][0]
         l5 = np.full(per, 65536, dtype=np.uint64)
         o5, t5 = synth.layout(l5)
         d5 = torch.empty(t5, dtype=torch.uint8, device=dev)
@@ -513,12 +515,7 @@ def main():
         launches += int(st5.kernel_launches)
         # gather on the host, by index: shards are contiguous by count, so rank order is index order
         t0 = time.perf_counter()
-        if world > 1:
-            parts = [torch.empty((per, 64), dtype=torch.uint8) for _ in range(world)] if rank == 0 else None
-            dist.gather(h5, parts, dst=0, group=host_group)
-            all5 = torch.cat(parts).numpy() if rank == 0 else None
-        else:
-            all5 = h5.numpy()
+        all5 = sharding.gather_digests(h5.numpy(), shards5, rank, world, group=host_group)    # the code tests/test_dist_cpu.py runs under gloo
         gather_ms = (time.perf_counter() - t0) * 1e3
         if rank == 0:
             import hashlib
@@ -534,7 +531,7 @@ def main():
                     "roofline_frac": ALGO_INSTR_PER_BLOCK * per * 513 / (k5 * 1e-3) / 1e12 /
                                      (torch.cuda.get_device_properties(dev).multi_processor_count * INT32_LANES_PER_SM * peaks["sm_max_mhz"] * 1e-6),
                     "timed": "kernel + copy of the shard's digests to pinned host memory, CUDA events, max over ranks",
-                    "digest_gather_ms": gather_ms, "digest_gather": "torch.distributed gloo gather of host tensors to rank 0, concatenated in rank order = index order" if world > 1 else "single rank",
+                    "digest_gather_ms": gather_ms, "digest_gather": "snappy_b200.sharding.gather_digests over a gloo (host) group: rank 0 places every rank's digests at its shard's index range" if world > 1 else "single rank",
                     "spot_checked_vs_hashlib": len(picks),
                     "speedup_note": "strong scaling: compare ms_per_step with the --gpus 1 line of the same build"}
         del d5, g5, h5
