@@ -113,8 +113,6 @@ struct Pipe {
     int sm_count = 0;
     std::mutex mu;
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr, long_stream = nullptr;
-    cudaStream_t copy_stream2 = nullptr;         // batch sessions: the spans of a batch alternate between two copy
-    cudaEvent_t ev_copied2[kStageBufs] = {};     // streams, so that one span's DMA set-up hides behind the other's transfer
     cudaStream_t slot_long_stream[kStageBufs] = {};
     cudaStream_t slot_stream[kStageBufs] = {};   // batch sessions: one compute stream per staging buffer, so that the
                                                  // kernels of consecutive batches (each at least as long as the chain of
@@ -274,9 +272,6 @@ static void destroy_pipe(Pipe &D) {
     if (D.long_stream) cudaStreamDestroy(D.long_stream);
     for (auto &st : D.slot_stream)
         if (st) cudaStreamDestroy(st);
-    if (D.copy_stream2) cudaStreamDestroy(D.copy_stream2);
-    for (auto &ev : D.ev_copied2)
-        if (ev) cudaEventDestroy(ev);
     for (auto &st : D.slot_long_stream)
         if (st) cudaStreamDestroy(st);
     D.ordinal = -1;
@@ -290,8 +285,6 @@ static int init_pipe(Pipe &D, int ordinal, int sm_count) {
     SG_CUDA(cudaStreamCreateWithFlags(&D.compute_stream, cudaStreamNonBlocking));
     SG_CUDA(cudaStreamCreateWithFlags(&D.long_stream, cudaStreamNonBlocking));
     for (auto &st : D.slot_stream) SG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    SG_CUDA(cudaStreamCreateWithFlags(&D.copy_stream2, cudaStreamNonBlocking));
-    for (auto &ev : D.ev_copied2) SG_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto &st : D.slot_long_stream) SG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     for (auto &s : D.slots) {
         SG_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
@@ -1225,7 +1218,6 @@ static int session_retire(BatchSession *s, BatchSession::Lane &L, int b, std::ve
     Pipe &P = *L.lease->pipe;
     if (!S.copy_reported) {
         cudaError_t e = wait ? cudaEventSynchronize(P.ev_copied[b]) : cudaEventQuery(P.ev_copied[b]);
-        if (e == cudaSuccess) e = wait ? cudaEventSynchronize(P.ev_copied2[b]) : cudaEventQuery(P.ev_copied2[b]);
         if (e == cudaErrorNotReady) return 0;
         if (e != cudaSuccess) return fail(SNAPGPU_ECUDA, "host-to-device copy failed: %s", cudaGetErrorString(e));
         S.copy_reported = true;
@@ -1354,13 +1346,11 @@ int session_submit(BatchSession *s, const HostSpan *spans, size_t nspans, const 
     for (size_t k = 0; k < nspans; k++)
         if (spans[k].bytes)
             SG_CUDA(cudaMemcpyAsync(P.d_stage[b] + s->span_base[k], spans[k].ptr, spans[k].bytes, cudaMemcpyHostToDevice,
-                                    (k & 1) ? P.copy_stream2 : P.copy_stream));
+                                    P.copy_stream));
     R.h2d_bytes += total;
     SG_CUDA(cudaEventRecord(P.ev_copied[b], P.copy_stream));
-    SG_CUDA(cudaEventRecord(P.ev_copied2[b], P.copy_stream2));
     cudaStream_t cs = P.slot_stream[b];
     SG_CUDA(cudaStreamWaitEvent(cs, P.ev_copied[b], 0));
-    SG_CUDA(cudaStreamWaitEvent(cs, P.ev_copied2[b], 0));
     const uint64_t *base = s->span_base.data();
     auto get = [segs, base](size_t i) { return SegDesc{base[segs[i].span] + segs[i].off, segs[i].len, 0, (u32)i, 0}; };
     int rc = launch_sha512(P, cs, P.d_stage[b], get, nsegs, P.d_out[b], P.slot_long_stream[b]);

@@ -112,7 +112,10 @@ private:
 // pinned chunks
 // ------------------------------------------------------------------------------------------
 
-constexpr size_t kSmallChunk = (size_t)2 << 20;      // files up to kSmallMax are packed into these
+// 4 MiB: a span of that size copies at 52.5 GB/s, one of 2 MiB at 49.9, of 1 MiB at 45.5 (64 MiB: 55.3;
+// profiles/r02_h2d_pieces.jsonl -- where sixteen threads streaming through DRAM, as the packers do,
+// cost the copy engine another 27 %, whatever the span size and however many copy streams)
+constexpr size_t kSmallChunk = (size_t)4 << 20;      // files up to kSmallMax are packed into these
 constexpr size_t kSmallMax = (size_t)256 << 10;
 constexpr size_t kLargeChunk = (size_t)32 << 20;     // files up to kMidMax, a few per chunk
 constexpr size_t kMidMax = (size_t)16 << 20;         // longer files are chains of their own (ChainStreamer)
@@ -208,7 +211,7 @@ private:
 };
 
 inline ChunkPool &small_chunks() {
-    static ChunkPool *p = new ChunkPool(kSmallChunk, 384, 16, 0);  // 32 MiB, doubling up to 768 MiB pinned
+    static ChunkPool *p = new ChunkPool(kSmallChunk, 192, 8, 0);   // 32 MiB, doubling up to 768 MiB pinned
     return *p;
 }
 inline ChunkPool &large_chunks() {
