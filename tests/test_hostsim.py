@@ -182,3 +182,36 @@ def test_verify_reports(sim, oracle, tmp_path):
     (tree / "new").write_bytes(b"n")
     got = run(sim["asan"], "verify", tree, doc).stdout.decode().splitlines()
     assert sorted(got) == sorted(oracle.verify_hashes(str(tree), str(doc)))
+
+
+def test_compare_path_and_one_file_entry_points(sim, oracle, golden_dir, tmp_path):
+    """DirUpdated (helpers/cmp.go:97-114) and Sha512sum of one file through the same sanitizer build:
+    the cases of helpers/cmp_test.go:84-133 plus sizes across the 16 KiB chunk and the pinned staging."""
+    import json
+    rng = np.random.default_rng(9)
+    a, b = tmp_path / "a", tmp_path / "b"
+    a.mkdir()
+    b.mkdir()
+    for i, n in enumerate([0, 1, 16383, 16384, 16385, 100_000, 3_000_000]):
+        body = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        (a / f"same{i}").write_bytes(body)
+        (b / f"same{i}").write_bytes(body)
+        if n:
+            other = bytearray(body)
+            other[n // 2] ^= 1
+            (a / f"diff{i}").write_bytes(body)
+            (b / f"diff{i}").write_bytes(bytes(other))
+    (a / "only-in-a").write_bytes(b"x")
+    (b / "only-in-b").write_bytes(b"y")
+    (a / "size").write_bytes(b"12")
+    (b / "size").write_bytes(b"123")
+    (a / "subdir").mkdir()
+    (b / "subdir").mkdir()
+    got = run(sim["asan"], "dir_updated", a, b, "pfx_").stdout.decode().splitlines()
+    assert sorted(got) == sorted(oracle.dir_updated(str(a), str(b), "pfx_"))
+    for k in json.loads((golden_dir / "sha512_kats.json").read_text()):
+        f = tmp_path / "kat"
+        f.write_bytes(k["message"].encode())
+        assert run(sim["asan"], "sha512sum", f).stdout.decode().strip() == k["sha512"]
+    p = run(sim["asan"], "sha512sum", tmp_path / "missing", ok=False)
+    assert p.returncode == 3 and b"No such file or directory" in p.stdout
