@@ -34,7 +34,7 @@ errors = []
 
 
 def make_tree(root: Path, rng):
-    root.mkdir()
+    root.mkdir(parents=True)
     dirs = [root]
     for i in range(int(rng.integers(0, 25))):
         d = dirs[int(rng.integers(len(dirs)))] / f"d{i:02d}"
