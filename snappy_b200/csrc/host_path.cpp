@@ -1400,21 +1400,44 @@ int read_archive_sha512(const std::string &yaml_path, std::string *hex) {
     return 0;
 }
 
+// ioutil.WriteFile(path, content, 0644) (build.go:269).  A large document (a 100 000-file tree makes
+// 20 MB of YAML) is written by the pool, each worker its own range through its own descriptor.
 int write_file_0644(const std::string &path, const char *content, size_t size) {
     int fd = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0644);
     if (fd < 0) return fail(SNAPGPU_EIO, "%s", go_path_error("open", path, errno).c_str());
-    size_t done = 0;
-    while (done < size) {
-        ssize_t w = ::write(fd, content + done, size - done);
-        if (w < 0) {
-            if (errno == EINTR) continue;
-            int e = errno;
-            ::close(fd);
-            return fail(SNAPGPU_EIO, "%s", go_path_error("write", path, e).c_str());
+    auto write_range = [&](int wfd, size_t lo, size_t hi) -> int {
+        while (lo < hi) {
+            const ssize_t w = ::pwrite(wfd, content + lo, hi - lo, (off_t)lo);
+            if (w < 0) {
+                if (errno == EINTR) continue;
+                return errno;
+            }
+            lo += (size_t)w;
         }
-        done += (size_t)w;
+        return 0;
+    };
+    int err = 0;
+    const size_t kPiece = (size_t)2 << 20;
+    IoPool &pool = IoPool::instance();
+    const unsigned nw = (unsigned)std::min<size_t>(pool.size(), size / kPiece);
+    if (nw < 2) {
+        err = write_range(fd, 0, size);
+    } else {
+        std::vector<int> errs(nw, 0);
+        pool.run(nw, [&](unsigned t) {
+            const int wfd = ::open(path.c_str(), O_WRONLY | O_CLOEXEC);        // a pool thread has its own descriptor table
+            if (wfd < 0) {
+                errs[t] = errno;
+                return;
+            }
+            errs[t] = write_range(wfd, size * t / nw, size * (t + 1) / nw);
+            ::close(wfd);
+        });
+        for (int e : errs)
+            if (e && !err) err = e;
     }
-    ::close(fd);
+    if (::close(fd) != 0 && !err) err = errno;
+    if (err) return fail(SNAPGPU_EIO, "%s", go_path_error("write", path, err).c_str());
     return 0;
 }
 
