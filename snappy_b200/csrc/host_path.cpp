@@ -9,10 +9,10 @@
 //   snappy::yamlFileMode    snappy/hashes.go:33-57
 //   policy::AppArmorDelta   policy/policy.go:155-167
 //
-// The Go loops hash / compare one file at a time; here the walk only collects paths, the
-// contents are packed into pinned staging memory at 16-byte aligned offsets, and every
-// regular file of the tree goes through one batched GPU call (several when the tree is
-// larger than the staging buffer).  All arithmetic happens on the GPU: there is no CPU
+// The Go loops hash / compare one file at a time.  Here a tree is scanned, read, copied to the GPU,
+// hashed and written up as overlapping stages of one pipeline (tree_hasher.hpp: writeHashes,
+// verification and copyToBuildDir all run on it); the compare path packs both sides of every
+// candidate pair and makes one batched call.  All arithmetic happens on the GPU: there is no CPU
 // SHA-512 or memcmp in this file.
 //
 // The YAML writer restates what gopkg.in/yaml.v2 @ 49c95bdc (dependencies.tsv:7) emits for
