@@ -29,3 +29,7 @@ python tools/ncu_long_target.py 4 > ${o}_pair_plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:sha512_pair -c 1 -o ${o}_pair -f \
     python tools/ncu_long_target.py 4 > ${o}_ncu_pair.log 2>&1; echo "ncu pair exit $?"
 python tools/shape_probe.py > ${o}_shape_probe.jsonl 2> ${o}_shape_probe.err; echo "shape probe exit $?"
+python tools/tree_stress.py 60 1 > ${o}_tree_stress.json 2> ${o}_tree_stress.err; echo "tree stress exit $?"; cat ${o}_tree_stress.json
+SNAPGPU_TRACE=1 python tools/tree_bench.py ${o}_tree_bench.jsonl cfg2 > ${o}_tree_bench.log 2> ${o}_tree_bench_trace.log; echo "tree bench exit $?"
+python tools/tree_cfg3.py 20000 64 16 > ${o}_tree_cfg3_shape.json 2> ${o}_tree_cfg3_shape.err; echo "tree cfg3 exit $?"
+python tools/h2d_piece_probe.py > ${o}_h2d_pieces.jsonl 2> ${o}_h2d_pieces.err; echo "h2d pieces exit $?"
