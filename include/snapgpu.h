@@ -48,7 +48,8 @@ const char *snapgpu_version(void);
  * "cmp_ctas_per_sm", "time_kernels", "feeders" (host threads per device that bounce pageable
  * input into pinned memory, 0 = auto), "long_kernel" (the long-file bin: 0 off, 1 one lane per
  * file, 2 a lane pair per file = default), "pair_form" (how the two lanes of a pair exchange round results:
- * 0 shared-memory mailboxes = default, 1 warp shuffle; sha512_pair.cuh). */
+ * 0 shared-memory mailboxes = default, 1 warp shuffle; sha512_pair.cuh), "pair_files_per_cta" (0 = default: long
+ * files spread over the SMs, one per CTA while they last; 1..16 = exactly this many per CTA). */
 int snapgpu_set_option(const char *key, long long value);
 
 /* C-owned pinned host memory for the Go side to pack file contents into

@@ -91,22 +91,30 @@ __device__ __forceinline__ u64 pair_exchange(u64 x) {      // with the other lan
 // kShuffle = false (option pair_form 0, the default): through shared-memory mailboxes read by the
 //   loads that fetch W+K (see the file header).  A store of iteration i is loaded by the partner
 //   in iteration i+1, so the pair must execute the straight-line round code together.  That is
-//   arranged, not assumed: every group of 16 rounds (and the prologue, and the two tail rounds)
-//   starts with __syncwarp() -- a convergence point; the slow path of its BRA.DIV re-converges a
-//   diverged warp -- and contains no branch up to the next one, and converged lanes do not part
-//   in branch-free code: ptxas relies on the same fact when it checks convergence ONCE for the 32
-//   shfl.sync of a group of the shuffle form below.  tests/test_sass.py pins the shape (one
-//   BRA.DIV and no other branch inside the round loop, every mailbox store ahead of the load of
-//   the next round in program order).  1.86 us per block.
+//   arranged, not assumed: the prologue and every region of rounds start with __syncwarp() -- a
+//   convergence point; the slow path of its BRA.DIV re-converges a diverged warp -- and contain
+//   no branch up to the next one, and converged lanes do not part in branch-free code: ptxas
+//   relies on the same fact when it checks convergence ONCE for the 32 shfl.sync of a group of
+//   the shuffle form below.  tests/test_sass.py pins the shape (no branch inside a region, every
+//   mailbox store ahead of the load of the next round in program order).
+//   A convergence point costs ~25 clocks of the chain, so regions are as long as the instruction
+//   cache allows (profiles/r02_pair_regions.jsonl):
+//     kRegions = 2: two regions of 41 rounds (15 KB loop body, fits the L0 instruction cache):
+//                   1.90 us per block whatever the producer does;
+//     kRegions = 1: prologue and all 82 rounds are one region (30 KB): 1.83 us per block while
+//                   the producer warp is mostly idle (1 file per CTA; 1.88 with 2), but it streams
+//                   from the shared L1 instruction cache and loses to a busy producer (2.6 us with
+//                   12+ files per CTA).  The host therefore spreads long files over CTAs -- one per
+//                   CTA up to the SM count -- and picks kRegions = 1 for 1..2 files per CTA.
 // kShuffle = true (pair_form 1): a warp shuffle (__shfl_xor_sync) carries the exchange, so the
 //   synchronisation is in the instruction itself.  Role 1 loads a zero where role 0 loads W+K,
 //   and both form PD = S2*mul + kw + r (tests/test_pair_schedule.py::compress_pair_shuffle).
 //   2.04 us per block -- two SHFL and two more IMAD per round cost more than the LDS/STS they
 //   replace (profiles/r02_pair_forms.jsonl) -- so it is the cross-check, not the default.
-template <bool kAligned16, bool kShuffle>
+template <bool kAligned16, bool kShuffle, int kRegions>
 __global__ void __launch_bounds__(kLongThreads, 1)
 sha512_pair_kernel(const uint8_t *__restrict__ data, const SegDesc *__restrict__ descs, u32 nsegs,
-                   uint8_t *__restrict__ digests) {
+                   uint8_t *__restrict__ digests, u32 files_per_cta) {
     extern __shared__ __align__(16) uint8_t pair_smem[];
     u64 *ring = reinterpret_cast<u64 *>(pair_smem);
     u64 *mail = reinterpret_cast<u64 *>(pair_smem + kPairRingBytes);
@@ -117,8 +125,8 @@ sha512_pair_kernel(const uint8_t *__restrict__ data, const SegDesc *__restrict__
 
     const u32 lane = threadIdx.x & 31;
     const u32 warp = threadIdx.x >> 5;
-    const u32 first = blockIdx.x * kPairFilesPerCta;
-    const u32 count = min((u32)kPairFilesPerCta, nsegs - first);
+    const u32 first = blockIdx.x * files_per_cta;         // files_per_cta <= kPairFilesPerCta, chosen by the host
+    const u32 count = min(files_per_cta, nsegs - first);
 
     if (threadIdx.x == 0) {
         st_volatile_shared(produced, 0);
@@ -241,26 +249,34 @@ sha512_pair_kernel(const uint8_t *__restrict__ data, const SegDesc *__restrict__
         D = dn;                                                                                  \
         S3 = S2; S2 = S1; S1 = S0; S0 = e;                                                       \
     }
+            // 82 iterations in kRegions branch-free regions (1 or 2), each behind a convergence point; role 0
+            // is done after iteration 79, role 1 needs two more
+            u64 e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+#define SNAPGPU_PAIR_ITER4(k, d, o, I)                                                           \
+    SNAPGPU_PAIR_ITER(k, d, o, I) SNAPGPU_PAIR_ITER(k, d, o, (I) + 1) SNAPGPU_PAIR_ITER(k, d, o, (I) + 2) SNAPGPU_PAIR_ITER(k, d, o, (I) + 3)
+#define SNAPGPU_PAIR_ITER36(k, d, o, I)                                                          \
+    SNAPGPU_PAIR_ITER4(k, d, o, I) SNAPGPU_PAIR_ITER4(k, d, o, (I) + 4) SNAPGPU_PAIR_ITER4(k, d, o, (I) + 8)                 \
+    SNAPGPU_PAIR_ITER4(k, d, o, (I) + 12) SNAPGPU_PAIR_ITER4(k, d, o, (I) + 16) SNAPGPU_PAIR_ITER4(k, d, o, (I) + 20)        \
+    SNAPGPU_PAIR_ITER4(k, d, o, (I) + 24) SNAPGPU_PAIR_ITER4(k, d, o, (I) + 28) SNAPGPU_PAIR_ITER4(k, d, o, (I) + 32)
+            if (kRegions == 1) {
+                // no convergence point of its own: nothing but straight-line code since the prologue's
+                SNAPGPU_PAIR_ITER36(kin, din, out, 0) SNAPGPU_PAIR_ITER36(kin, din, out, 36)
+                SNAPGPU_PAIR_ITER4(kin, din, out, 72) SNAPGPU_PAIR_ITER4(kin, din, out, 76)
+                e0 = S0; e1 = S1; e2 = S2; e3 = S3;
+                SNAPGPU_PAIR_ITER(kin, din, out, 80) SNAPGPU_PAIR_ITER(kin, din, out, 81)
+            } else {
 #pragma unroll 1
-            for (int grp = 0; grp < 5; grp++) {
-                volatile u64 *const k = kin + 16 * grp, *const d = din + 16 * grp, *const o = out + 16 * grp;
-                __syncwarp();                              // convergence point: the 16 rounds below are branch-free
-                SNAPGPU_PAIR_ITER(k, d, o, 0)  SNAPGPU_PAIR_ITER(k, d, o, 1)
-                SNAPGPU_PAIR_ITER(k, d, o, 2)  SNAPGPU_PAIR_ITER(k, d, o, 3)
-                SNAPGPU_PAIR_ITER(k, d, o, 4)  SNAPGPU_PAIR_ITER(k, d, o, 5)
-                SNAPGPU_PAIR_ITER(k, d, o, 6)  SNAPGPU_PAIR_ITER(k, d, o, 7)
-                SNAPGPU_PAIR_ITER(k, d, o, 8)  SNAPGPU_PAIR_ITER(k, d, o, 9)
-                SNAPGPU_PAIR_ITER(k, d, o, 10) SNAPGPU_PAIR_ITER(k, d, o, 11)
-                SNAPGPU_PAIR_ITER(k, d, o, 12) SNAPGPU_PAIR_ITER(k, d, o, 13)
-                SNAPGPU_PAIR_ITER(k, d, o, 14) SNAPGPU_PAIR_ITER(k, d, o, 15)
+                for (int half = 0; half < 2; half++) {
+                    volatile u64 *const k = kin + 41 * half, *const d = din + 41 * half, *const o = out + 41 * half;
+                    __syncwarp();                          // convergence point: the 41 rounds below are branch-free
+                    SNAPGPU_PAIR_ITER36(k, d, o, 0)
+                    SNAPGPU_PAIR_ITER(k, d, o, 36) SNAPGPU_PAIR_ITER(k, d, o, 37) SNAPGPU_PAIR_ITER(k, d, o, 38)
+                    e0 = S0; e1 = S1; e2 = S2; e3 = S3;    // the second half's is iteration 79
+                    SNAPGPU_PAIR_ITER(k, d, o, 39) SNAPGPU_PAIR_ITER(k, d, o, 40)
+                }
             }
-            // role 0 is done after iteration 79; role 1 needs two more
-            const u64 e0 = S0, e1 = S1, e2 = S2, e3 = S3;
-            {
-                volatile u64 *const k = kin + 80, *const d = din + 80, *const o = out + 80;
-                __syncwarp();
-                SNAPGPU_PAIR_ITER(k, d, o, 0)  SNAPGPU_PAIR_ITER(k, d, o, 1)
-            }
+#undef SNAPGPU_PAIR_ITER36
+#undef SNAPGPU_PAIR_ITER4
 #undef SNAPGPU_PAIR_ITER
             if (b < my_blocks) {
                 st[0] += role ? S0 : e0;

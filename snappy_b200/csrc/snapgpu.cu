@@ -204,6 +204,7 @@ struct Options {
     std::atomic<long long> long_kernel{2};      // 0 off, 1 one lane per file, 2 a lane pair per file
     std::atomic<long long> two_ended{1};        // several CTAs per SM: slow warps claim from the short end of the plan
     std::atomic<long long> pair_form{0};        // lane-pair kernel: 0 lanes exchange through mailboxes, 1 by shuffle
+    std::atomic<long long> pair_files_per_cta{0};   // lane-pair kernel: 0 = spread over the SMs, 1..16 = exactly this many
 };
 
 // devs is written only by snapgpu_init / snapgpu_shutdown, under mu AND devs_mu held exclusively;
@@ -302,11 +303,13 @@ static int init_pipe(Pipe &D, int ordinal, int sm_count) {
     return 0;
 }
 
-typedef void (*PairKernel)(const uint8_t *, const SegDesc *, u32, uint8_t *);
-// the lane-pair kernel by alignment and exchange form (sha512_pair.cuh): 0 mailboxes (default), 1 shuffle
-static PairKernel pair_kernel_for(bool aligned, int form) {
-    if (form == 1) return aligned ? sha512_pair_kernel<true, true> : sha512_pair_kernel<false, true>;
-    return aligned ? sha512_pair_kernel<true, false> : sha512_pair_kernel<false, false>;
+typedef void (*PairKernel)(const uint8_t *, const SegDesc *, u32, uint8_t *, u32);
+// the lane-pair kernel by alignment, exchange form (0 mailboxes -- the default, 1 shuffle) and, for the mailbox form,
+// the number of branch-free regions a block's rounds are cut into (sha512_pair.cuh)
+static PairKernel pair_kernel_for(bool aligned, int form, int regions) {
+    if (form == 1) return aligned ? sha512_pair_kernel<true, true, 2> : sha512_pair_kernel<false, true, 2>;
+    if (regions == 1) return aligned ? sha512_pair_kernel<true, false, 1> : sha512_pair_kernel<false, false, 1>;
+    return aligned ? sha512_pair_kernel<true, false, 2> : sha512_pair_kernel<false, false, 2>;
 }
 
 static void destroy_device(Device &dev) {
@@ -329,10 +332,11 @@ static int init_device(Device &dev, int ordinal) {
                     prop.major, prop.minor);
     SG_CUDA(cudaFuncSetAttribute(sha512_long_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytes));
     SG_CUDA(cudaFuncSetAttribute(sha512_long_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytes));
-    for (int form = 0; form < 2; form++) {
-        SG_CUDA(cudaFuncSetAttribute(pair_kernel_for(true, form), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes));
-        SG_CUDA(cudaFuncSetAttribute(pair_kernel_for(false, form), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes));
-    }
+    for (int form = 0; form < 2; form++)
+        for (int regions = 1; regions <= 2; regions++) {
+            SG_CUDA(cudaFuncSetAttribute(pair_kernel_for(true, form, regions), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes));
+            SG_CUDA(cudaFuncSetAttribute(pair_kernel_for(false, form, regions), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes));
+        }
     for (auto &p : dev.pipes) {
         p.reset(new Pipe());
         int rc = init_pipe(*p, ordinal, dev.sm_count);
@@ -668,9 +672,16 @@ static int launch_sha512(Pipe &D, cudaStream_t stream, const uint8_t *d_data, Ge
         SG_CUDA(cudaEventRecord(slot->fork, stream));
         SG_CUDA(cudaStreamWaitEvent(long_stream, slot->fork, 0));
         if (R.opt.long_kernel.load() >= 2) {                // one chain per lane pair (sha512_pair.cuh)
-            const u32 long_grid = (u32)((n_long + kPairFilesPerCta - 1) / kPairFilesPerCta);
-            pair_kernel_for(aligned, (int)R.opt.pair_form.load())<<<long_grid, kLongThreads, kPairSmemBytes, long_stream>>>(
-                d_data, plan.long_descs, (u32)n_long, d_digests);
+            // spread the chains over the SMs: the fewer files a CTA's producer warp serves, the longer the
+            // branch-free region its consumer can afford (kRegions in sha512_pair.cuh)
+            u32 per_cta = (u32)((n_long + (size_t)D.sm_count - 1) / (size_t)D.sm_count);
+            const u32 forced = (u32)R.opt.pair_files_per_cta.load();
+            if (forced) per_cta = forced;
+            per_cta = std::min<u32>(std::max<u32>(per_cta, 1), kPairFilesPerCta);
+            const u32 long_grid = (u32)((n_long + per_cta - 1) / per_cta);
+            pair_kernel_for(aligned, (int)R.opt.pair_form.load(), per_cta <= 2 ? 1 : 2)
+                <<<long_grid, kLongThreads, kPairSmemBytes, long_stream>>>(d_data, plan.long_descs, (u32)n_long, d_digests,
+                                                                           per_cta);
         } else {                                            // one chain per lane (sha512_long.cuh)
             const u32 long_grid = (u32)((n_long + kLongFilesPerCta - 1) / kLongFilesPerCta);
             if (aligned)
@@ -1607,6 +1618,9 @@ int snapgpu_set_option(const char *key, long long value) {
     } else if (k == "pair_form") {
         if (value < 0 || value > 1) return fail(SNAPGPU_EINVAL, "pair_form: 0 shared-memory mailboxes, 1 shuffle exchange");
         o.pair_form = value;
+    } else if (k == "pair_files_per_cta") {
+        if (value < 0 || value > kPairFilesPerCta) return fail(SNAPGPU_EINVAL, "pair_files_per_cta: 0 auto, 1..16");
+        o.pair_files_per_cta = value;
     } else if (k == "long_kernel") {
         if (value < 0 || value > 2) return fail(SNAPGPU_EINVAL, "long_kernel: 0 off, 1 one lane per file, 2 lane pair per file");
         o.long_kernel = value;

@@ -20,6 +20,7 @@ def default_options(gpu):
     gpu.set_option("sha_warps_per_sm", 0)
     gpu.set_option("long_kernel", 2)
     gpu.set_option("pair_form", 0)
+    gpu.set_option("pair_files_per_cta", 0)
     gpu.set_option("two_ended", 1)
     yield
 
@@ -243,16 +244,19 @@ def test_long_file_chain(gpu):
     assert dg[1].tobytes() == hashlib.sha512(synth.file_bytes(1, 100)).digest()
 
 
-@pytest.mark.parametrize("mode,pair_form", [(1, 0), (2, 0), (2, 1)])
-def test_long_file_kernel(gpu, oracle, mode, pair_form):
+@pytest.mark.parametrize("mode,pair_form,per_cta", [(1, 0, 0), (2, 0, 0), (2, 0, 16), (2, 0, 5), (2, 0, 2), (2, 1, 16)])
+def test_long_file_kernel(gpu, oracle, mode, pair_form, per_cta):
     """The long-file bin: files whose chain would dominate a launch leave the batched kernel when a
     launch has at most 256 of them -- mode 1 one lane per file (sha512_long.cuh), mode 2 a lane pair
     per file (sha512_pair.cuh), its lanes exchanging through shared-memory mailboxes (pair_form 0, the
-    default) or by warp shuffle (pair_form 1).  Same digests with the bin switched off, and all equal the
-    oracle."""
+    default) or by warp shuffle (pair_form 1).  The pair form spreads its files over the SMs (per_cta 0: one
+    file per CTA while the SMs last, and then the rounds of a block are one branch-free region; 3+ files per
+    CTA: two regions); per_cta forces the CTA shape the comments below name.  Same digests with the bin
+    switched off, and all equal the oracle."""
     from snappy_b200 import helpers
     gpu.set_option("long_kernel", mode)
     gpu.set_option("pair_form", pair_form)
+    gpu.set_option("pair_files_per_cta", per_cta)
     rng = np.random.default_rng(21)
     MiB = 1 << 20
     cases = [

@@ -97,52 +97,80 @@ def test_probe_kernels_issue_what_they_claim(sass, kind, opcode, least):
     assert count(c, opcode) >= least, c.most_common(6)
 
 
-def test_pair_kernel_round_loop(native):
-    """sha512_pair_kernel, mailbox form (the default): the 16-round loop of the consumer has ~17 ALU
-    instructions per round (28 in the one-lane consumer) and talks through shared memory only.  The
-    exchange is safe because the loop body is ONE convergence check (the BRA.DIV of __syncwarp) followed
-    by branch-free code in which the volatile accesses keep their order -- load, load, store per round, so
-    every mailbox store sits ahead of the partner's load in the next round.  No spills."""
+def _pair_stretches(native, mangled_prefix):
+    """(instructions, branch-free stretches) of one pair kernel: a stretch is a maximal run without a control
+    instruction (BSSY only declares a reconvergence point and does not end one), kept with the control
+    instruction in front of it and the one that ends it."""
     text = subprocess.run(["cuobjdump", "-sass", str(native.LIB_PATH)], capture_output=True, text=True, check=True).stdout
-    body = [p for p in text.split("Function : ") if p.startswith("_ZN7snapgpu18sha512_pair_kernelILb1ELb0E")]
+    body = [p for p in text.split("Function : ") if p.startswith(mangled_prefix)]
     assert len(body) == 1
     insts = []
     for line in body[0].splitlines():
         m = re.match(r"\s+/\*([0-9a-f]{4,6})\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)(.*?);", line)
         if m:
             insts.append((int(m.group(1), 16), m.group(2), m.group(3)))
-    assert not any(op.startswith(("LDL", "STL")) for _, op, _ in insts)
-    # loops = backward branches; the round loop is the one whose body holds 16 STS.64 and 32 LDS.64
-    loops = []
-    for addr, op, rest in insts:
-        if op.startswith("BRA") and not op.startswith("BRA.DIV"):
-            m = re.search(r"0x([0-9a-f]+)", rest)
-            if m and int(m.group(1), 16) < addr:
-                loops.append((int(m.group(1), 16), addr))
-    alu = re.compile(r"^(IADD3|LOP3|SHF|PRMT|SEL|ISETP|VIADD|LEA|MOV|IMNMX|VIMNMX)")
-    found = False
-    for lo, hi in loops:
-        ops = [op for a, op, _ in insts if lo <= a <= hi]
-        if (sum(op.startswith("STS.64") for op in ops) == 16 and sum(op.startswith("LDS.64") for op in ops) == 32
-                and len(ops) < 500):
-            found = True
-            assert sum(op.startswith("SHF.R.W") for op in ops) == 16 * 6
-            assert not any(op.startswith(("SHFL", "WARPSYNC", "BAR", "BSSY", "BSYNC", "CALL", "RET", "EXIT")) for op in ops)
-            branches = [op for op in ops if op.startswith(("BRA", "BRX", "JMP"))]
-            assert sorted(branches) == ["BRA", "BRA.DIV"], branches          # the back edge and one convergence check
-            assert ops.index("BRA.DIV") < next(i for i, op in enumerate(ops) if op.startswith(("LDS", "STS")))
-            mem = ["L" if op.startswith("LDS") else "S" for op in ops if op.startswith(("LDS.64", "STS.64"))]
-            assert "".join(mem) == "LLS" * 16, "".join(mem)
-            n_alu = sum(bool(alu.match(op)) for op in ops)
-            assert n_alu <= 16 * 17.5, n_alu
-    assert found
+    assert not any(op.startswith(("LDL", "STL")) for _, op, _ in insts)          # no spills
+    control = ("BRA", "BRX", "JMP", "WARPSYNC", "BAR", "BSYNC", "CALL", "RET", "EXIT", "SHFL", "NANOSLEEP")
+    stretches, before, run = [], None, []
+    for inst in insts:
+        if inst[1].startswith(control):
+            stretches.append((before, run, inst))
+            before, run = inst, []
+        else:
+            run.append(inst)
+    return insts, stretches
+
+
+_PAIR_ALU = re.compile(r"^(IADD3|LOP3|SHF|PRMT|SEL|ISETP|VIADD|LEA|MOV|IMNMX|VIMNMX)")
+
+
+def _mem_string(run):
+    return "".join("L" if op.startswith("LDS") else "S" for _, op, _ in run if op.startswith(("LDS.64", "STS.64")))
+
+
+def test_pair_kernel_round_loop(native):
+    """sha512_pair_kernel, mailbox form, two regions per block (3+ files per CTA): the consumer's loop body
+    is ONE convergence check (the BRA.DIV of __syncwarp) followed by 41 rounds of branch-free code in which
+    the volatile accesses keep their order -- load, load, store per round, so every mailbox store sits
+    ahead of the partner's load in the next round -- and the back edge.  ~17 ALU instructions per round
+    (28 in the one-lane consumer), no shuffles, no spills."""
+    _, stretches = _pair_stretches(native, "_ZN7snapgpu18sha512_pair_kernelILb1ELb0ELi2E")
+    found = 0
+    for before, run, after in stretches:
+        if _mem_string(run) != "LLS" * 41:
+            continue
+        found += 1
+        assert before is not None and before[1] == "BRA.DIV", before         # entered through the convergence point
+        assert after[1] == "BRA" and int(re.search(r"0x([0-9a-f]+)", after[2]).group(1), 16) <= before[0], after
+        ops = [op for _, op, _ in run]
+        assert sum(op.startswith("SHF.R.W") for op in ops) == 41 * 6
+        assert sum(bool(_PAIR_ALU.match(op)) for op in ops) <= 41 * 17.5
+    assert found == 1
+
+
+def test_pair_kernel_single_region(native):
+    """One or two files per CTA: prologue and all 82 rounds of a block are ONE branch-free stretch behind the
+    prologue's convergence point."""
+    _, stretches = _pair_stretches(native, "_ZN7snapgpu18sha512_pair_kernelILb1ELb0ELi1E")
+    found = 0
+    for before, run, _ in stretches:
+        mem = _mem_string(run)
+        if not mem.endswith("LLS" * 82):
+            continue
+        found += 1
+        assert before is not None and before[1] == "BRA.DIV", before
+        assert len(mem) == 3 * 82 + 5, mem[:12]                              # the prologue: kin[0], two seeds, din[0], a seed
+        ops = [op for _, op, _ in run]
+        assert sum(op.startswith("SHF.R.W") for op in ops) >= 82 * 6
+        assert sum(bool(_PAIR_ALU.match(op)) for op in ops) <= 82 * 17.5 + 60
+    assert found == 1
 
 
 def test_pair_kernel_shuffle_form(native):
     """The cross-check form (pair_form 1): the lanes exchange by SHFL.BFLY, two per round, and the round
     loop stores nothing to shared memory."""
     text = subprocess.run(["cuobjdump", "-sass", str(native.LIB_PATH)], capture_output=True, text=True, check=True).stdout
-    body = [p for p in text.split("Function : ") if p.startswith("_ZN7snapgpu18sha512_pair_kernelILb1ELb1E")]
+    body = [p for p in text.split("Function : ") if p.startswith("_ZN7snapgpu18sha512_pair_kernelILb1ELb1ELi2E")]
     assert len(body) == 1
     ops = re.findall(r"/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", body[0])
     assert ops.count("SHFL.BFLY") >= 2 * 18 and not any(op.startswith(("LDL", "STL")) for op in ops)
