@@ -48,7 +48,8 @@ const char *snapgpu_version(void);
  * "cmp_ctas_per_sm", "time_kernels", "feeders" (host threads per device that bounce pageable
  * input into pinned memory, 0 = auto), "long_kernel" (the long-file bin: 0 off, 1 one lane per
  * file, 2 a lane pair per file = default), "pair_form" (how the two lanes of a pair exchange round results:
- * 0 shared-memory mailboxes = default, 1 warp shuffle; sha512_pair.cuh), "pair_files_per_cta" (0 = default: long
+ * 0 shared-memory mailboxes = default, 1 warp shuffle; sha512_pair.cuh), "long_min_blocks" (smallest file, in
+ * 128-byte blocks, the long-file bin considers; 0 = default: 256 for the lane-pair form), "pair_files_per_cta" (0 = default: long
  * files spread over the SMs, one per CTA while they last; 1..16 = exactly this many per CTA). */
 int snapgpu_set_option(const char *key, long long value);
 
@@ -223,6 +224,7 @@ typedef struct snapgpu_stats {
     uint64_t sha512_kernel_timed;
     double cmp_kernel_ms_sum;
     uint64_t cmp_kernel_timed;
+    uint64_t sha512_long_launches;  /* launches of the long-file bin's kernel (counted in kernel_launches too) */
 } snapgpu_stats;
 int snapgpu_get_stats(snapgpu_stats *out);
 void snapgpu_reset_stats(void);

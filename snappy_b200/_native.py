@@ -36,6 +36,7 @@ class Stats(ctypes.Structure):
         ("sha512_kernel_timed", ctypes.c_uint64),
         ("cmp_kernel_ms_sum", ctypes.c_double),
         ("cmp_kernel_timed", ctypes.c_uint64),
+        ("sha512_long_launches", ctypes.c_uint64),
     ]
 
 

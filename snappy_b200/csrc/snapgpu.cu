@@ -204,6 +204,8 @@ struct Options {
     std::atomic<long long> long_kernel{2};      // 0 off, 1 one lane per file, 2 a lane pair per file
     std::atomic<long long> two_ended{1};        // several CTAs per SM: slow warps claim from the short end of the plan
     std::atomic<long long> pair_form{0};        // lane-pair kernel: 0 lanes exchange through mailboxes, 1 by shuffle
+    std::atomic<long long> taper{1};            // host-buffer pipeline: small last chunk (see taper_cap)
+    std::atomic<long long> long_min_blocks{0};  // long-file bin: candidates have at least this many blocks (0 = by form)
     std::atomic<long long> pair_files_per_cta{0};   // lane-pair kernel: 0 = spread over the SMs, 1..16 = exactly this many
 };
 
@@ -468,13 +470,21 @@ static ShaKernel sha_kernel_for(int variant, bool aligned) {
 // Host half of the launch plan: the `n` descriptors produced by get(i) are streamed into
 // pinned memory in the caller's order and checked; the ordering by length is done on the
 // device (plan_kernels.cuh).  Multi-million-file shards are written by several host threads.
-// The long-file bin takes the files whose chain would dominate the launch: at least kLongMinBlocks
-// blocks (128 KiB) AND at least kLongDominance times the launch's blocks per lane -- if there are
-// no more than one CTA per SM of the lane-pair kernel can take (16 files each: 2368 on a B200; 256
-// for the one-lane form).  Up to there every chain runs at 1.86 us per block instead of 3.86 while
-// the batched kernel would need the same single wave; beyond it the batched kernel keeps
-// everything -- it has the higher throughput.
-constexpr uint64_t kLongMinBlocks = 1024;
+// The long-file bin takes the files whose chain would dominate the launch: at least `long_min_blocks`
+// blocks AND at least kLongDominance times the launch's blocks per lane AND (lane-pair form) at least
+// kPairBalance of the longest file -- if there are no more of them than one CTA per SM of the lane-pair
+// kernel can take (16 files each: 2368 on a B200; 256 for the one-lane form).  Up to there every chain
+// runs at 1.8-1.9 us per block instead of 3.8 while the batched kernel would need the same single wave;
+// beyond it the batched kernel keeps everything -- it has the higher throughput.
+//   long_min_blocks: 256 (32 KiB) for the lane-pair form -- a launch with nothing longer is over in
+// under a millisecond whatever hashes it; what this buys is the chain-bound launch of a small batch (the
+// last chunk of a host-buffer call, a tree batch, a small request): with 64 KiB files in it 1.95 ms in
+// the batched kernel, 0.97 ms with the top files on lane pairs.  The one-lane form gains nothing over a
+// lone warp of the batched kernel below 128 KiB and keeps 1024.
+//   kPairBalance: the bin's chains run 2.1x faster than those left behind, so files shorter than
+// 31/64 of the longest would finish before it in the batched kernel anyway.
+constexpr uint64_t kLongMinBlocksPair = 256, kLongMinBlocksLane = 1024;
+constexpr uint64_t kPairBalanceNum = 31, kPairBalanceDen = 64;
 constexpr uint64_t kLongDominance = 4;
 constexpr size_t kLongMaxFiles = 2400;          // descriptor room in a plan slot
 constexpr size_t kLongMaxCandidates = 4096;
@@ -484,8 +494,9 @@ struct PlanInfo {
     bool aligned = true;
     int bad = 0;            // 1: too large, 2: non-final segment not a multiple of 128
     size_t bad_index = 0;
-    uint64_t max_short_blocks = 0;      // longest item below kLongMinBlocks
-    size_t n_long = 0;                  // items of >= kLongMinBlocks blocks
+    uint64_t min_long_blocks = kLongMinBlocksLane;   // in: what counts as a candidate for the long-file bin
+    uint64_t max_short_blocks = 0;      // longest item below min_long_blocks
+    size_t n_long = 0;                  // items of >= min_long_blocks blocks
     std::vector<u32> long_idx;          // their indices (the first kLongMaxCandidates)
 };
 
@@ -494,6 +505,7 @@ static void write_descriptors(Get get, size_t n, SegDesc *descs, PlanInfo *info)
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     const size_t nthreads = n < (1u << 19) ? 1 : std::min<size_t>({(size_t)hw, (size_t)8, n >> 18});
     std::vector<PlanInfo> part(nthreads);
+    const uint64_t min_long = info->min_long_blocks;
     auto body = [&](size_t t) {
         PlanInfo &pi = part[t];
         const size_t lo = n * t / nthreads, hi = n * (t + 1) / nthreads;
@@ -506,7 +518,7 @@ static void write_descriptors(Get get, size_t n, SegDesc *descs, PlanInfo *info)
             const uint64_t nb = seg_blocks(d.len, d.flags);
             pi.total_blocks += nb;
             pi.max_blocks = std::max(pi.max_blocks, nb);
-            if (nb >= kLongMinBlocks) {
+            if (nb >= min_long) {
                 if (pi.long_idx.size() < kLongMaxCandidates) pi.long_idx.push_back((u32)i);
                 pi.n_long++;
             } else {
@@ -583,6 +595,12 @@ static int launch_sha512(Pipe &D, cudaStream_t stream, const uint8_t *d_data, Ge
     int rc = acquire_slot(D, plan_bytes(n, kPlanTopMax + 1), &slot);
     if (rc) return rc;
     PlanInfo info;
+    const long long long_mode = R.opt.long_kernel.load();
+    const bool pair_bin = long_mode >= 2;
+    {
+        const long long forced = R.opt.long_min_blocks.load();
+        info.min_long_blocks = forced > 0 ? (uint64_t)forced : pair_bin ? kLongMinBlocksPair : kLongMinBlocksLane;
+    }
     if (trace_on()) fprintf(stderr, "[snapgpu] plan slot acquired after %.3f ms\n", now_ms() - t_plan);
     write_descriptors(get, n, static_cast<SegDesc *>(slot->h_buf), &info);
     if (trace_on()) fprintf(stderr, "[snapgpu] %zu descriptors written in %.3f ms\n", n, now_ms() - t_plan);
@@ -599,14 +617,13 @@ static int launch_sha512(Pipe &D, cudaStream_t stream, const uint8_t *d_data, Ge
     // the higher throughput, the long kernel only the shorter chain.
     SegDesc *h_descs = static_cast<SegDesc *>(slot->h_buf);
     size_t n_long = 0;
-    if (info.n_long >= 1 && info.n_long <= kLongMaxCandidates && R.opt.long_kernel.load()) {
+    if (info.n_long >= 1 && info.n_long <= kLongMaxCandidates && long_mode) {
         const uint64_t lanes = (uint64_t)D.sm_count * kShaThreads;
-        const uint64_t threshold = std::max<uint64_t>(kLongMinBlocks, kLongDominance * (total_blocks / lanes));
+        uint64_t threshold = std::max<uint64_t>(info.min_long_blocks, kLongDominance * (total_blocks / lanes));
+        if (pair_bin) threshold = std::max(threshold, max_blocks * kPairBalanceNum / kPairBalanceDen);
         size_t dominant = 0;
         for (u32 i : info.long_idx) dominant += seg_blocks(h_descs[i].len, h_descs[i].flags) >= threshold;
-        const size_t room = R.opt.long_kernel.load() >= 2
-                                ? std::min<size_t>(kLongMaxFiles, (size_t)D.sm_count * kPairFilesPerCta)
-                                : 256;
+        const size_t room = pair_bin ? std::min<size_t>(kLongMaxFiles, (size_t)D.sm_count * kPairFilesPerCta) : 256;
         if (dominant >= 1 && dominant <= room) {
             SegDesc *h_long = h_descs + n;
             uint64_t max_rest = info.max_short_blocks;
@@ -671,7 +688,7 @@ static int launch_sha512(Pipe &D, cudaStream_t stream, const uint8_t *d_data, Ge
         // everything `stream` has been asked to do so far (the data, a chaining value) comes first
         SG_CUDA(cudaEventRecord(slot->fork, stream));
         SG_CUDA(cudaStreamWaitEvent(long_stream, slot->fork, 0));
-        if (R.opt.long_kernel.load() >= 2) {                // one chain per lane pair (sha512_pair.cuh)
+        if (pair_bin) {                                     // one chain per lane pair (sha512_pair.cuh)
             // spread the chains over the SMs: the fewer files a CTA's producer warp serves, the longer the
             // branch-free region its consumer can afford (kRegions in sha512_pair.cuh)
             u32 per_cta = (u32)((n_long + (size_t)D.sm_count - 1) / (size_t)D.sm_count);
@@ -1034,6 +1051,23 @@ static size_t ramp_cap(size_t chunk_index, size_t cap_max) {
     return std::min(want, cap_max);
 }
 
+// ... and tapers it: nothing overlaps the hashing of the LAST chunk, and a launch costs at least the serial
+// chain of its longest file however few files it has (with 64 KiB files: ~2 ms in the batched kernel, ~1 ms
+// once the long-file bin takes them, which it does for chunks up to ~256 MiB).  So the rest of a shard does
+// not go out as one large chunk: the last one is 64 MiB -- small enough for the bin and a short copy-back of
+// digests, long enough in the copying (1.2 ms) for the launch before it to finish underneath (chunks alternate
+// between two compute streams, so the last launch does not queue behind that one either).
+constexpr uint64_t kTailChunk = 64u << 20;
+static size_t taper_cap(size_t want, const ItemList &shard, size_t next_item) {
+    if (next_item >= shard.size() || !rt().opt.taper.load()) return want;
+    const WorkItem last = shard.at(shard.size() - 1);
+    const uint64_t pos = shard.at(next_item).off, end = last.off + last.len;
+    if (end <= pos) return want;                          // not laid out in order: no estimate
+    const uint64_t left = end - pos;
+    if (left <= want && left >= 3 * kTailChunk) return (size_t)(left - kTailChunk);
+    return want;
+}
+
 // Runs one device's shard of a host-buffer SHA-512 batch.  digests: caller's n*64 array.
 // The staging buffers a shard needs: the configured size, or less when the whole shard is smaller
 // (a concurrent caller hashing a few MiB on a second pipe should not allocate two 1 GiB buffers).
@@ -1084,8 +1118,11 @@ static int sha512_shard(Device &dev, const uint8_t *data, const ItemList &shard,
     };
 
     Chunk c;
-    for (size_t ci = 0; stream.next(ramp_cap(ci, cap), cap, &c); ci++) {
+    for (size_t ci = 0; stream.next(taper_cap(ramp_cap(ci, cap), shard, stream.k), cap, &c); ci++) {
         const int b = (int)(ci & 1);
+        // one compute stream per staging buffer: launches of small chunks are bound by the chain of their longest
+        // file, not by throughput, so the last chunk's should not queue behind the one before it
+        const cudaStream_t cs = D.slot_stream[b];
         const double t_chunk = now_ms();
         if ((rc = scatter(b))) return rc;        // buffer b (stage, out) is free again
         const double t_free = now_ms();
@@ -1100,21 +1137,21 @@ static int sha512_shard(Device &dev, const uint8_t *data, const ItemList &shard,
             if ((rc = scatter(b ^ 1))) return rc;
             for (size_t i = 0; i < c.count; i++)
                 memcpy(D.h_out[b] + 64 * i, digests + 64 * plan.item(c, i).user_index, 64);
-            SG_CUDA(cudaMemcpyAsync(D.d_out[b], D.h_out[b], c.count * 64, cudaMemcpyHostToDevice, D.compute_stream));
+            SG_CUDA(cudaMemcpyAsync(D.d_out[b], D.h_out[b], c.count * 64, cudaMemcpyHostToDevice, cs));
             R.h2d_bytes += c.count * 64;
         }
-        SG_CUDA(cudaStreamWaitEvent(D.compute_stream, D.ev_copied[b], 0));
+        SG_CUDA(cudaStreamWaitEvent(cs, D.ev_copied[b], 0));
         {
             const uint64_t rebase = phase - c.span_begin;       // host offset -> staging offset
             auto get = [&plan, &c, rebase](size_t i) {
                 const WorkItem w = plan.item(c, i);
                 return SegDesc{w.off + rebase, w.len, w.prefix, (u32)i, w.flags};
             };
-            if ((rc = launch_sha512(D, D.compute_stream, D.d_stage[b], get, c.count, D.d_out[b]))) return rc;
+            if ((rc = launch_sha512(D, cs, D.d_stage[b], get, c.count, D.d_out[b], D.slot_long_stream[b]))) return rc;
         }
-        SG_CUDA(cudaMemcpyAsync(D.h_out[b], D.d_out[b], c.count * 64, cudaMemcpyDeviceToHost, D.compute_stream));
+        SG_CUDA(cudaMemcpyAsync(D.h_out[b], D.d_out[b], c.count * 64, cudaMemcpyDeviceToHost, cs));
         R.d2h_bytes += c.count * 64;
-        SG_CUDA(cudaEventRecord(D.ev_done[b], D.compute_stream));
+        SG_CUDA(cudaEventRecord(D.ev_done[b], cs));
         scatter_pending[b] = (int)ci;   // scatter(b) syncs on ev_done[b] before buffer b is reused
         if (trace_on())
             fprintf(stderr, "[snapgpu] chunk %zu: %zu items, span %.1f MiB, waited %.2f ms for the buffer, enqueue %.2f ms\n",
@@ -1618,6 +1655,11 @@ int snapgpu_set_option(const char *key, long long value) {
     } else if (k == "pair_form") {
         if (value < 0 || value > 1) return fail(SNAPGPU_EINVAL, "pair_form: 0 shared-memory mailboxes, 1 shuffle exchange");
         o.pair_form = value;
+    } else if (k == "taper") {
+        o.taper = value ? 1 : 0;
+    } else if (k == "long_min_blocks") {
+        if (value < 0) return fail(SNAPGPU_EINVAL, "long_min_blocks: 0 = default, else the smallest file (in 128-byte blocks) the long-file bin takes");
+        o.long_min_blocks = value;
     } else if (k == "pair_files_per_cta") {
         if (value < 0 || value > kPairFilesPerCta) return fail(SNAPGPU_EINVAL, "pair_files_per_cta: 0 auto, 1..16");
         o.pair_files_per_cta = value;
@@ -1777,6 +1819,7 @@ int snapgpu_get_stats(snapgpu_stats *out) {
     out->kernel_launches = R.kernel_launches;
     out->sha512_launches = R.sha_launches;
     out->cmp_launches = R.cmp_launches;
+    out->sha512_long_launches = R.sha_long_launches;
     out->h2d_bytes = R.h2d_bytes;
     out->d2h_bytes = R.d2h_bytes;
     double sha_sum = 0, cmp_sum = 0;

@@ -21,6 +21,7 @@ def default_options(gpu):
     gpu.set_option("long_kernel", 2)
     gpu.set_option("pair_form", 0)
     gpu.set_option("pair_files_per_cta", 0)
+    gpu.set_option("long_min_blocks", 0)
     gpu.set_option("two_ended", 1)
     yield
 
@@ -242,6 +243,31 @@ def test_long_file_chain(gpu):
     dg = device.sha512_batch_device(d, off, lengths).cpu().numpy()
     assert dg[0].tobytes() == hashlib.sha512(synth.file_bytes(0, 64 << 20)).digest()
     assert dg[1].tobytes() == hashlib.sha512(synth.file_bytes(1, 100)).digest()
+
+
+def test_chain_bound_small_batch_uses_the_pair_bin(gpu, oracle):
+    """A small batch whose launch is bound by the chain of its longest files (64 KiB files among a few
+    thousand small ones: the last chunk of a host-buffer call, a tree batch): the files of at least 32 KiB
+    that are within 31/64 of the longest go to the lane-pair kernel, whose chain is 2.1x shorter; option
+    long_min_blocks 1024 restores round 1's rule (nothing below 128 KiB).  Same digests either way."""
+    from snappy_b200 import helpers, synth
+    rng = np.random.default_rng(77)
+    lengths = synth.lognormal_sizes(100_000)[:3000]
+    data, off, ln = pack(lengths, rng)
+    want = oracle.sha512_batch(data, off, ln, 8)
+    for min_blocks, binned in ((0, True), (1024, False), (300, True)):
+        gpu.set_option("long_min_blocks", min_blocks)
+        gpu.reset_stats()
+        got = helpers.sha512_batch(data, off, ln)
+        st = gpu.stats()
+        assert np.array_equal(got, want), min_blocks
+        assert (st.sha512_long_launches >= 1) == binned, (min_blocks, st.sha512_long_launches)
+    gpu.set_option("long_min_blocks", 0)
+    # nothing as long as 32 KiB: no bin
+    data, off, ln = pack(np.minimum(lengths, 30000), rng)
+    gpu.reset_stats()
+    assert np.array_equal(helpers.sha512_batch(data, off, ln), oracle.sha512_batch(data, off, ln, 8))
+    assert gpu.stats().sha512_long_launches == 0
 
 
 @pytest.mark.parametrize("mode,pair_form,per_cta", [(1, 0, 0), (2, 0, 0), (2, 0, 16), (2, 0, 5), (2, 0, 2), (2, 1, 16)])
