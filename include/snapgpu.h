@@ -49,8 +49,9 @@ const char *snapgpu_version(void);
  * input into pinned memory, 0 = auto), "long_kernel" (the long-file bin: 0 off, 1 one lane per
  * file, 2 a lane pair per file = default), "pair_form" (how the two lanes of a pair exchange round results:
  * 0 shared-memory mailboxes = default, 1 warp shuffle; sha512_pair.cuh), "long_min_blocks" (smallest file, in
- * 128-byte blocks, the long-file bin considers; 0 = default: 256 for the lane-pair form), "pair_files_per_cta" (0 = default: long
- * files spread over the SMs, one per CTA while they last; 1..16 = exactly this many per CTA). */
+ * 128-byte blocks, the long-file bin considers; 0 = default: 256 for the lane-pair form), "pair_files_per_cta" (0 = default: one
+ * long file per CTA while a quarter of the SMs last, then 2, then 16; 1..16 = exactly this many per CTA), "taper"
+ * (1 = default: a host-buffer call ends on a 64 MiB chunk). */
 int snapgpu_set_option(const char *key, long long value);
 
 /* C-owned pinned host memory for the Go side to pack file contents into

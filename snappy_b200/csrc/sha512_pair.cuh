@@ -41,7 +41,13 @@ constexpr int kPairRingPad = 8;                      // the last slot's W+K pref
 constexpr size_t kPairRingBytes = (size_t)(kLongRingWords + kPairRingPad) * 8;
 constexpr size_t kPairMailBytes = (size_t)kPairFilesPerCta * 2 * kPairMailWords * 8;
 constexpr size_t kPairZeroBytes = (size_t)kPairMailWords * 8;
-constexpr size_t kPairSmemBytes = kPairRingBytes + kPairMailBytes + 2 * kPairZeroBytes + 16;
+constexpr size_t kPairUsedBytes = kPairRingBytes + kPairMailBytes + 2 * kPairZeroBytes + 16;
+// A CTA of this kernel keeps its SM to itself: a batched-kernel CTA on the same SM would put a second warp on the
+// consumer's sub-partition and halve the chain's share of the ALU pipe (measured: 1.40 -> 1.58 ms for a 10 000-file
+// batch once the two were allowed to share).  The request is rounded up so that what is left of the SM's 228 KB
+// cannot hold the smallest batched-kernel CTA (33 KB + 1 KB reserved).
+constexpr size_t kPairSmemBytes = kPairUsedBytes > (200u << 10) ? kPairUsedBytes : (200u << 10);
+static_assert(kPairSmemBytes + 1024 <= 227u * 1024, "dynamic + static shared memory of one CTA must fit an SM");
 
 // rotr64 by a per-lane amount below 32
 __device__ __forceinline__ u64 rotr64_var(u64 x, u32 r) {
@@ -104,8 +110,8 @@ __device__ __forceinline__ u64 pair_exchange(u64 x) {      // with the other lan
 //     kRegions = 1: prologue and all 82 rounds are one region (30 KB): 1.83 us per block while
 //                   the producer warp is mostly idle (1 file per CTA; 1.88 with 2), but it streams
 //                   from the shared L1 instruction cache and loses to a busy producer (2.6 us with
-//                   12+ files per CTA).  The host therefore spreads long files over CTAs -- one per
-//                   CTA up to the SM count -- and picks kRegions = 1 for 1..2 files per CTA.
+//                   12+ files per CTA).  The host therefore gives a chain its own CTA while a quarter
+//                   of the SMs last, two per CTA up to twice that, and picks kRegions = 1 for those.
 // kShuffle = true (pair_form 1): a warp shuffle (__shfl_xor_sync) carries the exchange, so the
 //   synchronisation is in the instruction itself.  Role 1 loads a zero where role 0 loads W+K,
 //   and both form PD = S2*mul + kw + r (tests/test_pair_schedule.py::compress_pair_shuffle).

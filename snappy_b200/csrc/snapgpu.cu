@@ -432,7 +432,6 @@ static bool trace_on() {
     return on;
 }
 
-typedef void (*ShaKernel)(const uint8_t *, const SegDesc *, const u32 *, u32, uint8_t *, u32 *, u32, u32);
 
 constexpr int kShaCtasPerSmMax = 3;   // 168 registers per thread: no spills with the one-block-ahead prefetch
 constexpr int kShaVariants = 6;
@@ -450,6 +449,7 @@ constexpr int kShaVariants = 6;
 //            between 0 and 5 fell in between, profiles/r01_sweep_fma_add_variants.txt): IMAD.WIDE
 //            issues at half the ALU rate and holds up the ALU instructions issued next to it (a 1:1 mix
 //            of LOP3 and IMAD.WIDE runs at 0.75 + 0.75 per clock per SM, pipe_microbench.cuh).
+typedef void (*ShaKernel)(const uint8_t *, const SegDesc *, const u32 *, u32, uint8_t *, u32 *, u32, u32);
 static ShaKernel sha_kernel_for(int variant, bool aligned) {
     if (!aligned) {
         // any byte alignment: the staged kernel reading from each file's own phase; variant 2
@@ -689,9 +689,13 @@ static int launch_sha512(Pipe &D, cudaStream_t stream, const uint8_t *d_data, Ge
         SG_CUDA(cudaEventRecord(slot->fork, stream));
         SG_CUDA(cudaStreamWaitEvent(long_stream, slot->fork, 0));
         if (pair_bin) {                                     // one chain per lane pair (sha512_pair.cuh)
-            // spread the chains over the SMs: the fewer files a CTA's producer warp serves, the longer the
-            // branch-free region its consumer can afford (kRegions in sha512_pair.cuh)
-            u32 per_cta = (u32)((n_long + (size_t)D.sm_count - 1) / (size_t)D.sm_count);
+            // A CTA of this kernel has its SM to itself (sha512_pair.cuh: kPairSmemBytes), so its consumer warp
+            // shares the ALU pipe with nobody -- and the batched kernel has that many SMs less.  Up to a quarter
+            // of the SMs go to the bin: one file per CTA while that lasts (then the rounds of a block are one
+            // branch-free region, 1.81 us per block), two (1.88), and from there 16 per CTA (two regions, 1.90
+            // whatever the count) on as many CTAs as it takes.
+            const u32 budget = std::max<u32>(1, (u32)D.sm_count / 4);
+            u32 per_cta = n_long <= budget ? 1 : n_long <= 2 * (size_t)budget ? 2 : (u32)kPairFilesPerCta;
             const u32 forced = (u32)R.opt.pair_files_per_cta.load();
             if (forced) per_cta = forced;
             per_cta = std::min<u32>(std::max<u32>(per_cta, 1), kPairFilesPerCta);

@@ -275,9 +275,9 @@ def test_long_file_kernel(gpu, oracle, mode, pair_form, per_cta):
     """The long-file bin: files whose chain would dominate a launch leave the batched kernel when a
     launch has at most 256 of them -- mode 1 one lane per file (sha512_long.cuh), mode 2 a lane pair
     per file (sha512_pair.cuh), its lanes exchanging through shared-memory mailboxes (pair_form 0, the
-    default) or by warp shuffle (pair_form 1).  The pair form spreads its files over the SMs (per_cta 0: one
-    file per CTA while the SMs last, and then the rounds of a block are one branch-free region; 3+ files per
-    CTA: two regions); per_cta forces the CTA shape the comments below name.  Same digests with the bin
+    default) or by warp shuffle (pair_form 1).  The pair form gives a chain its own CTA while a quarter of the
+    SMs last (per_cta 0: then the rounds of a block are one branch-free region), two files per CTA up to
+    half the SMs' worth, 16 beyond (two regions); per_cta forces the CTA shape the comments below name.  Same digests with the bin
     switched off, and all equal the oracle."""
     from snappy_b200 import helpers
     gpu.set_option("long_kernel", mode)

@@ -48,7 +48,7 @@ for rounds in range(2):
         print(json.dumps({"what": "config 2 batch, pinned host buffer, one call", "long_min_blocks": min_blocks,
                           "ms_best": ts[0] * 1e3, "ms_median": ts[4] * 1e3, "gb_per_s_best": nbytes / ts[0] / 1e9}), flush=True)
         # small batches, device resident: the first k files of config 2 (kernel time from the library's events)
-        for k in (1000, 3000, 10000):
+        for k in (1000, 3000, 10000, 21000, 70000, 100000):
             o2, total = synth.layout(lengths[:k])
             d = torch.empty(total, dtype=torch.uint8, device="cuda:0")
             device.synth_fill_device(d, o2, lengths[:k])
