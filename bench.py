@@ -445,7 +445,7 @@ def main():
         e2e = {"value": e2e_gbs, "unit": "GB/s", "ms_per_step": dt * 1e3,
                "files_per_s": world * len(lengths) / dt,
                "h2d_bytes_per_step": int(st2.h2d_bytes // e2e_steps), "d2h_bytes_per_step": int(st2.d2h_bytes // e2e_steps),
-               "bound": "PCIe host-to-device copy (pinned host memory; chunks of 64 MiB, 256 MiB, then up to 1 GiB with a 64 MiB last one, double buffered)",
+               "bound": "PCIe host-to-device copy (pinned host memory; chunks of 64 MiB, 256 MiB, then up to 1 GiB, ending on 128 MiB and 64 MiB, double buffered)",
                "timing": "host wall clock around the synchronous C-ABI call (digests are in host memory on return), max over ranks",
                "h2d_gbs_per_gpu": st2.h2d_bytes / e2e_steps / dt / 1e9,
                "h2d_peak_gbs": h2d_peak, "h2d_peak_gbs_per_gpu": h2d_peak / world, "frac": e2e_gbs / h2d_peak,

@@ -1058,18 +1058,23 @@ static size_t ramp_cap(size_t chunk_index, size_t cap_max) {
 // ... and tapers it: nothing overlaps the hashing of the LAST chunk, and a launch costs at least the serial
 // chain of its longest file however few files it has (with 64 KiB files: ~2 ms in the batched kernel, ~1 ms
 // once the long-file bin takes them, which it does for chunks up to ~256 MiB).  So the rest of a shard does
-// not go out as one large chunk: the last one is 64 MiB -- small enough for the bin and a short copy-back of
-// digests, long enough in the copying (1.2 ms) for the launch before it to finish underneath (chunks alternate
-// between two compute streams, so the last launch does not queue behind that one either).
-constexpr uint64_t kTailChunk = 64u << 20;
+// not go out as one large chunk.  The last one is 64 MiB: small enough for the bin and a short copy-back of
+// digests.  The one before it is 128 MiB: its launch (1.15 ms) is over before the last chunk has been copied
+// (1.2 ms) -- the bin's CTAs want SMs to themselves and would otherwise wait for the batched kernel of a
+// large chunk to leave them (measured: 1.6 ms instead of 1.0 for the last launch) -- and its own copy (2.4 ms)
+// covers the ~2 ms launch of the large chunk before it.  Chunks alternate between two compute streams, so a
+// launch never queues behind the previous one either.
+constexpr uint64_t kTailLast = 64u << 20, kTailBefore = 128u << 20;
 static size_t taper_cap(size_t want, const ItemList &shard, size_t next_item) {
     if (next_item >= shard.size() || !rt().opt.taper.load()) return want;
     const WorkItem last = shard.at(shard.size() - 1);
     const uint64_t pos = shard.at(next_item).off, end = last.off + last.len;
     if (end <= pos) return want;                          // not laid out in order: no estimate
     const uint64_t left = end - pos;
-    if (left <= want && left >= 3 * kTailChunk) return (size_t)(left - kTailChunk);
-    return want;
+    if (left <= kTailLast + kTailLast / 2) return want;                                   // the last chunk
+    if (left <= kTailLast + kTailBefore + kTailBefore / 2) return (size_t)std::min<uint64_t>(want, left - kTailLast);
+    const uint64_t body = left - (kTailLast + kTailBefore);
+    return body <= want ? (size_t)body : want;
 }
 
 // Runs one device's shard of a host-buffer SHA-512 batch.  digests: caller's n*64 array.
@@ -1121,6 +1126,15 @@ static int sha512_shard(Device &dev, const uint8_t *data, const ItemList &shard,
         return 0;
     };
 
+    // trace only: when each chunk's copy began and ended on the copy stream, relative to the first
+    std::vector<cudaEvent_t> tr;
+    auto mark = [&]() {
+        if (!trace_on()) return;
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        cudaEventRecord(e, D.copy_stream);
+        tr.push_back(e);
+    };
     Chunk c;
     for (size_t ci = 0; stream.next(taper_cap(ramp_cap(ci, cap), shard, stream.k), cap, &c); ci++) {
         const int b = (int)(ci & 1);
@@ -1131,10 +1145,12 @@ static int sha512_shard(Device &dev, const uint8_t *data, const ItemList &shard,
         if ((rc = scatter(b))) return rc;        // buffer b (stage, out) is free again
         const double t_free = now_ms();
         const size_t span = (size_t)(c.span_end - c.span_begin);
+        mark();
         if (span) {
             if ((rc = h2d_span(D, D.d_stage[b] + phase, data + c.span_begin, span, pinned))) return rc;
             R.h2d_bytes += span;
         }
+        mark();
         SG_CUDA(cudaEventRecord(D.ev_copied[b], D.copy_stream));
         if (c.needs_state_in) {
             // chaining values come from the previous chunk: finish it first
@@ -1163,7 +1179,21 @@ static int sha512_shard(Device &dev, const uint8_t *data, const ItemList &shard,
     }
     if ((rc = scatter(0))) return rc;
     if ((rc = scatter(1))) return rc;
-    if (trace_on()) fprintf(stderr, "[snapgpu] dev %d: shard done in %.2f ms\n", D.ordinal, now_ms() - t_begin);
+    if (trace_on()) {
+        const double t_end = now_ms();
+        std::string line;
+        for (size_t i = 0; i + 1 < tr.size(); i += 2) {
+            float t0 = 0, t1 = 0;
+            cudaEventElapsedTime(&t0, tr[0], tr[i]);
+            cudaEventElapsedTime(&t1, tr[0], tr[i + 1]);
+            char buf[64];
+            snprintf(buf, sizeof buf, " [%.2f-%.2f]", t0, t1);
+            line += buf;
+        }
+        for (cudaEvent_t e : tr) cudaEventDestroy(e);
+        fprintf(stderr, "[snapgpu] dev %d: shard done in %.2f ms; copies on the copy stream (ms from the first):%s\n", D.ordinal,
+                t_end - t_begin, line.c_str());
+    }
     return 0;
 }
 
