@@ -128,6 +128,9 @@ struct Pipe {
     size_t out_cap = 0;       // bytes
     int out_n = 0;
     cudaEvent_t ev_copied[kStageBufs] = {}, ev_done[kStageBufs] = {};
+    // SNAPGPU_TRACE only: device timestamps of a session batch (copy begin / end, kernel begin, all done) and their base
+    cudaEvent_t tr_ev[kStageBufs][4] = {}, tr_base = nullptr;
+    double tr_base_host = 0;
     // bounce buffers for callers whose host buffer is ordinary pageable memory (allocated on first use)
     uint8_t *bounce[kFeeders][2] = {};
     cudaEvent_t bounce_free[kFeeders][2] = {};
@@ -253,8 +256,11 @@ static void destroy_pipe(Pipe &D) {
         if (D.d_out[b]) cudaFree(D.d_out[b]);
         if (D.h_out[b]) cudaFreeHost(D.h_out[b]);
         if (D.ev_copied[b]) cudaEventDestroy(D.ev_copied[b]);
+        for (auto &e : D.tr_ev[b])
+            if (e) { cudaEventDestroy(e); e = nullptr; }
         if (D.ev_done[b]) cudaEventDestroy(D.ev_done[b]);
     }
+    if (D.tr_base) { cudaEventDestroy(D.tr_base); D.tr_base = nullptr; }
     for (auto &t : D.sha_t) { if (t.beg) cudaEventDestroy(t.beg); if (t.end) cudaEventDestroy(t.end); }
     for (auto &t : D.cmp_t) { if (t.beg) cudaEventDestroy(t.beg); if (t.end) cudaEventDestroy(t.end); }
     for (int f = 0; f < kFeeders; f++) {
@@ -1313,7 +1319,16 @@ static int session_retire(BatchSession *s, BatchSession::Lane &L, int b, std::ve
     for (size_t i = 0; i < S.dst.size(); i++) memcpy(S.dst[i], src + 64 * i, 64);
     S.busy = false;
     s->in_flight--;
-    if (trace_on()) fprintf(stderr, "[snapgpu] session: batch %llu done, seen at %.2f ms\n", (unsigned long long)S.ticket, now_ms() - s->t_open);
+    if (trace_on()) {
+        float t[4] = {0, 0, 0, 0};
+        if (P.tr_base) {
+            cudaEventSynchronize(P.tr_ev[b][3]);
+            for (int k = 0; k < 4; k++) cudaEventElapsedTime(&t[k], P.tr_base, P.tr_ev[b][k]);
+        }
+        const double o = P.tr_base_host;
+        fprintf(stderr, "[snapgpu] session: batch %llu done, seen at %.2f ms; on the device: copy %.2f-%.2f, kernels end %.2f, digests back %.2f\n",
+                (unsigned long long)S.ticket, now_ms() - s->t_open, t[0] + o, t[1] + o, t[2] + o, t[3] + o);
+    }
     return 0;
 }
 
@@ -1425,21 +1440,37 @@ int session_submit(BatchSession *s, const HostSpan *spans, size_t nspans, const 
             fprintf(stderr, "[snapgpu] session: staging grown to %d x %zu MiB (+ %zu KiB of digests) in %.2f ms\n", kStageBufs,
                     P.stage_cap >> 20, P.out_cap >> 10, now_ms() - tg);
     }
+    const bool tr = trace_on();
+    if (tr) {
+        if (!P.tr_base) {
+            SG_CUDA(cudaEventCreate(&P.tr_base));
+            for (auto &row : P.tr_ev)
+                for (auto &e : row) SG_CUDA(cudaEventCreate(&e));
+        }
+        if (s->in_flight == 0 && s->next_ticket == 1) {
+            SG_CUDA(cudaEventRecord(P.tr_base, P.copy_stream));
+            P.tr_base_host = now_ms() - s->t_open;
+        }
+        SG_CUDA(cudaEventRecord(P.tr_ev[b][0], P.copy_stream));
+    }
     for (size_t k = 0; k < nspans; k++)
         if (spans[k].bytes)
             SG_CUDA(cudaMemcpyAsync(P.d_stage[b] + s->span_base[k], spans[k].ptr, spans[k].bytes, cudaMemcpyHostToDevice,
                                     P.copy_stream));
     R.h2d_bytes += total;
     SG_CUDA(cudaEventRecord(P.ev_copied[b], P.copy_stream));
+    if (tr) SG_CUDA(cudaEventRecord(P.tr_ev[b][1], P.copy_stream));
     cudaStream_t cs = P.slot_stream[b];
     SG_CUDA(cudaStreamWaitEvent(cs, P.ev_copied[b], 0));
     const uint64_t *base = s->span_base.data();
     auto get = [segs, base](size_t i) { return SegDesc{base[segs[i].span] + segs[i].off, segs[i].len, 0, (u32)i, 0}; };
     int rc = launch_sha512(P, cs, P.d_stage[b], get, nsegs, P.d_out[b], P.slot_long_stream[b]);
     if (rc) return rc;
+    if (tr) SG_CUDA(cudaEventRecord(P.tr_ev[b][2], cs));
     SG_CUDA(cudaMemcpyAsync(P.h_out[b], P.d_out[b], nsegs * 64, cudaMemcpyDeviceToHost, cs));
     R.d2h_bytes += nsegs * 64;
     SG_CUDA(cudaEventRecord(P.ev_done[b], cs));
+    if (tr) SG_CUDA(cudaEventRecord(P.tr_ev[b][3], cs));
     BatchSession::Slot &S = lane->slot[b];
     S.busy = true;
     S.copy_reported = false;
