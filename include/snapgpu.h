@@ -51,7 +51,8 @@ const char *snapgpu_version(void);
  * 0 shared-memory mailboxes = default, 1 warp shuffle; sha512_pair.cuh), "long_min_blocks" (smallest file, in
  * 128-byte blocks, the long-file bin considers; 0 = default: 256 for the lane-pair form), "pair_files_per_cta" (0 = default: one
  * long file per CTA while a quarter of the SMs last, then 2, then 16; 1..16 = exactly this many per CTA), "taper"
- * (1 = default: a host-buffer call ends on a 64 MiB chunk). */
+ * (1 = default: a host-buffer call ends on a 128 MiB and a 64 MiB chunk), "two_ended" (claims from both ends of the
+ * length-sorted plan: 0 never, 1 = default: when the longest file is at least three times the mean, 2 always). */
 int snapgpu_set_option(const char *key, long long value);
 
 /* C-owned pinned host memory for the Go side to pack file contents into

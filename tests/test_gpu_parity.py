@@ -957,7 +957,7 @@ def test_two_ended_claims_cover_every_unit_once(gpu, oracle):
     d = torch.from_numpy(data).cuda()
     for warps in (2, 3):
         gpu.set_option("sha_warps_per_sm", warps)
-        for mode in (1, 0):
+        for mode in (2, 1, 0):                    # always / when the lengths are spread wide (they are here) / never
             gpu.set_option("two_ended", mode)
             got = device.sha512_batch_device(d, off, ln).cpu().numpy()
             assert np.array_equal(got, want), (warps, mode)

@@ -24,6 +24,11 @@ ncu --set full --clock-control none --import-source on -k regex:cmp_pairs -s 4 -
 SNAPGPU_TRACE=1 python tools/tree_trace.py 4 2> ${o}_tree_trace.log; echo "tree trace exit $?"; grep "writeHashes:" ${o}_tree_trace.log | tail -2
 tools/tree_probe.sh ${o}_tree_probe.txt; echo "tree probe exit $?"
 python tools/pair_form_probe.py 4 > ${o}_pair_forms.jsonl 2> ${o}_pair_forms.err; echo "pair forms exit $?"; grep '"files": 1,' ${o}_pair_forms.jsonl | cut -c1-120
+python tools/pair_form_probe.py 4 0 1,16,37,38,74,75,148,400 > ${o}_pair_regions.jsonl 2> ${o}_pair_regions.err
+python tools/pair_form_probe.py 4 0 1,16,64 16 >> ${o}_pair_regions.jsonl 2>> ${o}_pair_regions.err; echo "pair regions exit $?"
+python tools/long_bin_probe.py > ${o}_long_bin_probe.jsonl 2> ${o}_long_bin_probe.err; echo "long bin probe exit $?"
+python tools/tree_tail_probe.py 30 > ${o}_tree_tail_probe.jsonl 2> ${o}_tree_tail_probe.err; echo "tree tail probe exit $?"; cat ${o}_tree_tail_probe.jsonl
+SNAPGPU_TRACE=1 python tools/e2e_trace.py > ${o}_e2e_trace.txt 2> ${o}_e2e_trace.log; echo "e2e trace exit $?"; grep "shard done" ${o}_e2e_trace.log | tail -1
 python tools/stress.py 60 2 > ${o}_stress.json 2> ${o}_stress.err; echo "stress exit $?"; tail -1 ${o}_stress.json
 python tools/ncu_long_target.py 4 > ${o}_pair_plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:sha512_pair -c 1 -o ${o}_pair -f \

@@ -42,9 +42,9 @@ for name, lengths in cases.items():
     blocks = synth.blocks(lengths)
     row = {"lengths": name, "files": len(lengths), "max_over_mean_blocks": round(float(blocks.max() / blocks.mean()), 2),
            "depth": round(float(blocks.sum() / (148 * 128 * blocks.max())), 2)}
-    for bal in (1, 0):                     # two-ended claims on (the default) and off
+    for bal in (1, 2, 0):                  # two-ended claims: by the spread of the lengths (the default), always, never
         N.set_option("two_ended", bal)
-        for r in ((0, 1, 2, 3) if bal else (0, 2, 3)):
+        for r in ((0, 1, 2, 3) if bal == 1 else (0, 2, 3)):
             N.set_option("sha_warps_per_sm", r)
             dg = torch.empty((len(lengths), 64), dtype=torch.uint8, device="cuda:0")
             for _ in range(2):
@@ -56,7 +56,7 @@ for name, lengths in cases.items():
             torch.cuda.synchronize()
             s = N.stats()
             ms = s.sha512_kernel_ms_sum / s.sha512_kernel_timed
-            key = ("auto" if r == 0 else f"R{r}") + ("" if bal else " one-ended")
+            key = ("auto" if r == 0 else f"R{r}") + {1: "", 2: " two-ended always", 0: " one-ended"}[bal]
             row[key] = round(int(blocks.sum()) * 3568 / (ms * 1e-3) / PEAK, 4)
             print("   ", name, key, row[key], file=sys.stderr, flush=True)
     print(json.dumps(row), flush=True)

@@ -73,7 +73,7 @@ while time.time() < t_end:
     opts = {"sha_variant": int(rng.integers(0, 6)), "sha_warps_per_sm": int(rng.integers(0, 4)),
             "long_kernel": int(rng.integers(0, 3)), "pair_form": int(rng.integers(0, 2)),
             "pair_files_per_cta": int(rng.choice([0, 0, 1, 2, 3, 7, 16])),
-            "long_min_blocks": int(rng.choice([0, 0, 16, 64, 1024])), "two_ended": int(rng.integers(0, 2)),
+            "long_min_blocks": int(rng.choice([0, 0, 16, 64, 1024])), "two_ended": int(rng.integers(0, 3)),
             "staging_bytes": int(rng.choice([1, 3, 16, 64, 1024])) * MiB}
     for k, v in opts.items():
         N.set_option(k, v)
