@@ -1,6 +1,7 @@
 // io_probe -- per-file cost of scan + open/fstat/read/close on a tree, by thread count and strategy
 // (mode 0 lstat+open by path, 1 fstatat+openat, 2 openat+fstat+O_NOATIME, 3 openat only), with
-// UNSHARE=1 giving every thread a private descriptor table and NOREAD=1 skipping the read.
+// UNSHARE=1 giving every thread a private descriptor table, NOREAD=1 skipping the read and DEFER=n closing n
+// descriptors with one close_range call (only meaningful with UNSHARE=1).
 //   g++ -O2 -std=c++17 -o io_probe io_probe.cpp -lpthread;  io_probe TREE THREADS MODE
 // probe: per-file cost of open/read/close on tmpfs with several strategies
 #include <dirent.h>
@@ -47,6 +48,8 @@ int main(int argc, char **argv) {
                 for (long p = 0; p < n;) { auto *e = (linux_dirent64*)(dbuf.data()+p); p += e->d_reclen; if (e->d_name[0]=='.' && (!e->d_name[1] || (e->d_name[1]=='.'&&!e->d_name[2]))) continue; names.emplace_back(e->d_name, e->d_type);} }
             std::sort(names.begin(), names.end());
             size_t chunk = 0, chunk_end = 0;
+            const int defer = getenv("DEFER") ? atoi(getenv("DEFER")) : 0;
+            int lo_fd = -1, hi_fd = -1, held = 0;
             for (auto &nm : names) {
                 struct stat st;
                 int fd;
@@ -69,9 +72,14 @@ int main(int argc, char **argv) {
                 ssize_t r = getenv("NOREAD") ? st.st_size : read(fd, buf + chunk, st.st_size + 1);
                 if (mode == 3) need = (r + 15) & ~15ull;
                 chunk += need;
-                close(fd);
+                if (!defer) close(fd);
+                else {
+                    if (!held) lo_fd = hi_fd = fd; else { lo_fd = std::min(lo_fd, fd); hi_fd = std::max(hi_fd, fd); }
+                    if (++held == defer) { syscall(SYS_close_range, (unsigned)lo_fd, (unsigned)hi_fd, 0); held = 0; }
+                }
                 nf++; nb += r;
             }
+            if (held) syscall(SYS_close_range, (unsigned)lo_fd, (unsigned)hi_fd, 0);
             close(dfd);
         }
         files += nf; bytes += nb;
