@@ -178,6 +178,12 @@ int snapgpu_apparmor_delta(const char *old_path, const char *new_path, const cha
  * partial, as in the reference.  flags: SNAPGPU_COPY_NO_LINK = never hard-link. */
 #define SNAPGPU_COPY_NO_LINK 1
 int snapgpu_copy_to_build_dir(const char *source_dir, const char *build_dir, int flags);
+
+/* Optional warm-up: does ahead of time what the first snapgpu_write_hashes of a process otherwise waits for (pinning
+ * the file packer's chunk pool, 256 MiB; staging, digest and plan buffers; the first launch of each kernel).  A build
+ * calls it from a goroutine as soon as it starts: by the time the tree has been copied and
+ * the archive compressed, writeHashes runs warm (config 2: 42 ms instead of 80-250).  Replaces nothing in the reference. */
+int snapgpu_warm(void);
 int snapgpu_should_exclude(const char *base_name);          /* shouldExclude, 1 = excluded */
 void snapgpu_digest_cache_clear(void);
 void snapgpu_digest_cache_stats(size_t *entries, uint64_t *hits);

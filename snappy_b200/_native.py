@@ -96,6 +96,7 @@ SIGNATURES = {
     "snapgpu_hasher_sum": (_i, [_vp, _vp]),
     "snapgpu_hasher_free": (None, [_vp]),
     "snapgpu_copy_to_build_dir": (_i, [_cp, _cp, _i]),
+    "snapgpu_warm": (_i, []),
     "snapgpu_should_exclude": (_i, [_cp]),
     "snapgpu_digest_cache_clear": (None, []),
     "snapgpu_digest_cache_stats": (None, [_psz, ctypes.POINTER(ctypes.c_uint64)]),

@@ -37,6 +37,12 @@ def copyToBuildDir(sourceDir: str, buildDir: str, no_link: bool = False) -> None
     _raise(N.lib().snapgpu_copy_to_build_dir(N.fs(sourceDir), N.fs(buildDir), 1 if no_link else 0))
 
 
+def warm() -> None:
+    """snapgpu_warm: pin the packer's chunk pool, allocate the pipeline's buffers and launch every kernel once,
+    ahead of the first writeHashes of the process (no counterpart in the reference)."""
+    _raise(N.lib().snapgpu_warm())
+
+
 def shouldExclude(basename: str) -> bool:
     """shouldExclude (/root/reference/snappy/build.go:52-83)."""
     return bool(N.lib().snapgpu_should_exclude(N.fs(basename)))

@@ -1936,6 +1936,49 @@ int snapgpu_copy_to_build_dir(const char *source_dir, const char *build_dir, int
     return copy_to_build_dir(source_dir, build_dir, flags);
 }
 
+// Everything the first writeHashes of a process would otherwise wait for, done ahead of it: the pinned chunk pool at
+// the size a large tree settles at, the session's staging and digest buffers, the plan slots, and one launch of each
+// kernel on the path (CUDA loads a kernel's code at its first launch).  Cold, writeHashes on the config 2 tree takes
+// 80-250 ms instead of 42; after this call -- made from a thread of its own while the build is still copying and
+// compressing -- the first call is a warm one.  Safe to call at any time, from any thread.
+int snapgpu_warm(void) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    IoPool::instance();                              // the packer's threads (created on first use)
+    ChunkPool &pool = small_chunks();
+    if (!pool.reserve(64)) return fail(SNAPGPU_ECUDA, "no pinned memory for the file packer: %s", snapgpu_last_error());
+    Chunk *c = nullptr;
+    for (int tries = 0; tries < 1000 && !(c = pool.try_get()); tries++) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+    if (!c) return fail(SNAPGPU_ECUDA, "no free chunk to warm up with");
+    // three messages of zeros: one block, a few blocks, and 40 KiB (the long-file bin's kernel)
+    const uint64_t lens[3] = {100, 5000, 40 << 10};
+    memset(c->base, 0, c->cap);
+    std::vector<SpanSeg> segs;
+    uint64_t off = 0;
+    for (uint64_t len : lens) {
+        segs.push_back(SpanSeg{0, off, len});
+        off += (len + 1 + 15) & ~(uint64_t)15;
+    }
+    HostSpan span{c->base, (size_t)off};
+    uint8_t digests[3][64];
+    uint8_t *dst[3] = {digests[0], digests[1], digests[2]};
+    BatchSession *session = nullptr;
+    rc = session_open(&session, kTreeBatchBytes);
+    uint64_t ticket = 0;
+    std::vector<uint64_t> copied;
+    if (!rc) rc = session_submit(session, &span, 1, segs.data(), dst, segs.size(), &ticket, &copied);
+    // while the session holds its pipe: the lone-chain path of the archive, which runs on the next one
+    if (!rc) {
+        uint8_t chain[64];
+        const HostSeg seg{0, 3u << 20, 0, 0};
+        rc = sha512_host_segments(c->base, &seg, 1, chain);
+    }
+    if (!rc) rc = session_poll(session, &copied, true);
+    if (session) session_close(session);
+    pool.put(c);
+    return rc;
+}
+
 int snapgpu_should_exclude(const char *base_name_) { return base_name_ && should_exclude(base_name_) ? 1 : 0; }
 
 void snapgpu_digest_cache_clear(void) {

@@ -18,6 +18,8 @@
 #include <shared_mutex>
 #include <thread>
 #include <time.h>
+#include <sys/mman.h>
+#include <map>
 
 #include "cmp_kernels.cuh"
 #include "pipe_microbench.cuh"
@@ -225,6 +227,79 @@ struct Runtime {
         d2h_bytes{0};
 };
 
+// Pinned host memory.  cudaHostAlloc pins page by page: 0.45 ms per MiB on this pool's boxes (114 ms for 256 MiB,
+// tools/pin_probe.cu), which is what the first large tree of a process used to wait for.  From 2 MiB up the memory is
+// instead an anonymous mapping on transparent huge pages (madvise; 512x fewer pages to pin), faulted in by a few
+// threads at once and then registered: 256 MiB in ~10 ms, same copy rate (55 GB/s).  Anything that fails on the way
+// falls back to cudaHostAlloc.  SNAPGPU_PIN=hostalloc forces the old path (for A/B runs).
+namespace {
+struct PinnedMapping {
+    void *map_base;
+    size_t map_len;
+};
+std::mutex g_pinned_mu;
+std::map<void *, PinnedMapping> g_pinned_maps;       // registered mappings by user pointer
+
+void *pinned_huge_alloc(size_t bytes) {
+    constexpr size_t kHuge = (size_t)2 << 20;
+    const size_t len = (bytes + kHuge - 1) & ~(kHuge - 1), map_len = len + kHuge;
+    void *m = mmap(nullptr, map_len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (m == MAP_FAILED) return nullptr;
+    uint8_t *a = reinterpret_cast<uint8_t *>(((uintptr_t)m + kHuge - 1) & ~(uintptr_t)(kHuge - 1));
+#ifdef MADV_HUGEPAGE
+    madvise(a, len, MADV_HUGEPAGE);                  // refused or unsupported: 4 KiB pages, still correct
+#endif
+#ifdef MADV_DONTFORK
+    madvise(a, len, MADV_DONTFORK);                  // a child (tar, gzip ...) neither copies nor shares DMA memory
+#endif
+    // fault the pages in (zeroing them is the cost) on several threads; one touch per 4 KiB page covers both page sizes
+    const size_t nthreads = std::max<size_t>(1, std::min<size_t>({(size_t)8, len / ((size_t)16 << 20),
+                                                                  (size_t)std::max(1u, std::thread::hardware_concurrency())}));
+    auto touch = [a, len, nthreads](size_t t) {
+        const size_t lo = len / nthreads * t, hi = t + 1 == nthreads ? len : len / nthreads * (t + 1);
+        for (size_t o = lo; o < hi; o += 4096) reinterpret_cast<volatile uint8_t *>(a)[o] = 0;
+    };
+    std::vector<std::thread> th;
+    for (size_t t = 1; t < nthreads; t++) th.emplace_back(touch, t);
+    touch(0);
+    for (auto &x : th) x.join();
+    if (cudaHostRegister(a, len, cudaHostRegisterPortable) != cudaSuccess) {
+        cudaGetLastError();
+        munmap(m, map_len);
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
+    g_pinned_maps[a] = PinnedMapping{m, map_len};
+    return a;
+}
+
+// pinned memory for the runtime's own buffers (plan slots, digest buffers, bounce buffers)
+cudaError_t host_pinned_alloc(void **out, size_t bytes) {
+    static const bool force_hostalloc = [] { const char *e = getenv("SNAPGPU_PIN"); return e && !strcmp(e, "hostalloc"); }();
+    if (bytes >= ((size_t)2 << 20) && !force_hostalloc && (*out = pinned_huge_alloc(bytes))) return cudaSuccess;
+    return cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+}
+void host_pinned_free(void *p) {
+    if (!p) return;
+    PinnedMapping pm{nullptr, 0};
+    {
+        std::lock_guard<std::mutex> lk(g_pinned_mu);
+        auto it = g_pinned_maps.find(p);
+        if (it != g_pinned_maps.end()) {
+            pm = it->second;
+            g_pinned_maps.erase(it);
+        }
+    }
+    if (pm.map_base) {
+        cudaHostUnregister(p);
+        munmap(pm.map_base, pm.map_len);
+    } else {
+        cudaFreeHost(p);
+    }
+}
+}  // namespace
+
+
 static Runtime &rt() {
     static Runtime r;
     return r;
@@ -243,7 +318,7 @@ static void destroy_pipe(Pipe &D) {
     cudaSetDevice(D.ordinal);
     cudaDeviceSynchronize();
     for (auto &s : D.slots) {
-        if (s.h_buf) cudaFreeHost(s.h_buf);
+        if (s.h_buf) host_pinned_free(s.h_buf);
         if (s.d_buf) cudaFree(s.d_buf);
         if (s.d_counter) cudaFree(s.d_counter);
         if (s.done) cudaEventDestroy(s.done);
@@ -254,7 +329,7 @@ static void destroy_pipe(Pipe &D) {
     for (int b = 0; b < kStageBufs; b++) {
         if (D.d_stage[b]) cudaFree(D.d_stage[b]);
         if (D.d_out[b]) cudaFree(D.d_out[b]);
-        if (D.h_out[b]) cudaFreeHost(D.h_out[b]);
+        if (D.h_out[b]) host_pinned_free(D.h_out[b]);
         if (D.ev_copied[b]) cudaEventDestroy(D.ev_copied[b]);
         for (auto &e : D.tr_ev[b])
             if (e) { cudaEventDestroy(e); e = nullptr; }
@@ -265,7 +340,7 @@ static void destroy_pipe(Pipe &D) {
     for (auto &t : D.cmp_t) { if (t.beg) cudaEventDestroy(t.beg); if (t.end) cudaEventDestroy(t.end); }
     for (int f = 0; f < kFeeders; f++) {
         for (int k = 0; k < 2; k++) {
-            if (D.bounce[f][k]) cudaFreeHost(D.bounce[f][k]);
+            if (D.bounce[f][k]) host_pinned_free(D.bounce[f][k]);
             if (D.bounce_free[f][k]) cudaEventDestroy(D.bounce_free[f][k]);
             D.bounce[f][k] = nullptr;
             D.bounce_free[f][k] = nullptr;
@@ -384,11 +459,11 @@ static int acquire_slot(Pipe &D, size_t bytes, PlanSlot **out) {
                 SG_CUDA(cudaEventSynchronize(g.done));
                 g.in_flight = false;
             }
-            if (g.h_buf) cudaFreeHost(g.h_buf);
+            if (g.h_buf) host_pinned_free(g.h_buf);
             if (g.d_buf) cudaFree(g.d_buf);
             g.h_buf = g.d_buf = nullptr;
             g.cap = 0;
-            SG_CUDA(cudaHostAlloc(&g.h_buf, want, cudaHostAllocPortable));
+            SG_CUDA(host_pinned_alloc(&g.h_buf, want));
             SG_CUDA(cudaMalloc(&g.d_buf, want));
             memset(g.h_buf, 0, want);          // touch the pages now, not inside a timed launch
             g.cap = want;
@@ -844,7 +919,7 @@ static int ensure_staging(Pipe &D, size_t stage_bytes, size_t out_bytes, int nbu
     if (D.out_cap < out_bytes) {
         for (int b = 0; b < kStageBufs; b++) {
             if (D.d_out[b]) cudaFree(D.d_out[b]);
-            if (D.h_out[b]) cudaFreeHost(D.h_out[b]);
+            if (D.h_out[b]) host_pinned_free(D.h_out[b]);
             D.d_out[b] = D.h_out[b] = nullptr;
         }
         D.out_n = 0;
@@ -852,7 +927,7 @@ static int ensure_staging(Pipe &D, size_t stage_bytes, size_t out_bytes, int nbu
     }
     for (; D.out_n < nbuf; D.out_n++) {
         SG_CUDA(cudaMalloc(&D.d_out[D.out_n], D.out_cap));
-        SG_CUDA(cudaHostAlloc(&D.h_out[D.out_n], D.out_cap, cudaHostAllocPortable));
+        SG_CUDA(host_pinned_alloc(reinterpret_cast<void **>(&D.h_out[D.out_n]), D.out_cap));
     }
     return 0;
 }
@@ -892,7 +967,7 @@ static int h2d_span(Pipe &D, uint8_t *dst, const uint8_t *src, size_t bytes, boo
         SG_CUDA(cudaStreamCreateWithFlags(&D.feeder_stream[f], cudaStreamNonBlocking));
         SG_CUDA(cudaEventCreateWithFlags(&D.feeder_done[f], cudaEventDisableTiming));
         for (int k = 0; k < 2; k++) {
-            SG_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&D.bounce[f][k]), kBounceBytes, cudaHostAllocPortable));
+            SG_CUDA(host_pinned_alloc(reinterpret_cast<void **>(&D.bounce[f][k]), kBounceBytes));
             SG_CUDA(cudaEventCreateWithFlags(&D.bounce_free[f][k], cudaEventDisableTiming));
         }
     }
@@ -1752,17 +1827,15 @@ void *snapgpu_alloc_pinned(size_t bytes) {
         return nullptr;
     }
     cudaSetDevice(rt().devs[0]->ordinal);
-    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
+    cudaError_t e = host_pinned_alloc(&p, bytes);
     if (e != cudaSuccess) {
-        set_error("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        set_error("pinning %zu bytes of host memory failed: %s", bytes, cudaGetErrorString(e));
         return nullptr;
     }
     return p;
 }
 
-void snapgpu_free_pinned(void *p) {
-    if (p) cudaFreeHost(p);
-}
+void snapgpu_free_pinned(void *p) { host_pinned_free(p); }
 
 void snapgpu_free(void *p) { free(p); }
 

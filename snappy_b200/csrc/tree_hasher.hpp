@@ -169,37 +169,83 @@ public:
         std::lock_guard<std::mutex> lk(mu_);
         free_.push_back(c);
     }
-    // driver side (may call CUDA): returns how many chunks were added, -1 when workers wait and
-    // there is not a single chunk to recycle for them (pinned memory cannot be had at all).
-    // Pinning is slow (~0.4 ms per MiB) and holds up every other CUDA call of the process while
-    // it lasts, so the pool grows in slabs that double it (at least `first_slab` chunks): a
-    // handful of allocations during the first large tree of a process, none afterwards.
+    // driver side: starts growing the pool when workers wait for chunks; returns -1 when they wait, there is not a
+    // single chunk to recycle for them and pinned memory cannot be had at all, else 0.  The pool grows in slabs that
+    // double it (at least `first_slab` chunks): a handful of allocations during the first large tree of a process,
+    // none afterwards.  The allocation itself runs on a thread of its own (pinning 256 MiB takes 10-50 ms, 115 ms
+    // through cudaHostAlloc): the driver keeps submitting and recycling meanwhile, and the workers, which poll the
+    // pool every 150 us while they wait, pick the new chunks up as they appear.  The pool outlives every tree
+    // (process-lifetime singleton), so a slab that arrives after its tree has finished is simply there for the next.
     int serve_allocations() {
         size_t want = 0;
         {
             std::lock_guard<std::mutex> lk(mu_);
-            if (waiters_ > free_.size() && all_.size() < max_)
-                want = std::min(std::max(first_slab_, all_.size()), max_ - all_.size());
+            if (failed_ && all_.empty() && waiters_ > 0) return -1;
+            if (!growing_ && !failed_ && waiters_ > free_.size() && all_.size() < max_) {
+                // doubling, but no slab larger than 128 MiB: registering a slab holds up the process's other CUDA calls
+                // for a few milliseconds per 64 MiB, and a smaller slab is in the workers' hands sooner
+                const size_t slab_cap = std::max<size_t>(first_slab_, ((size_t)128 << 20) / bytes_);
+                want = std::min({std::max(first_slab_, all_.size()), slab_cap, max_ - all_.size()});
+                growing_ = want != 0;
+            }
         }
         if (!want) return 0;
-        uint8_t *p = nullptr;
-        for (; want; want /= 2)                  // a smaller slab if the large one cannot be pinned
-            if ((p = static_cast<uint8_t *>(snapgpu_alloc_pinned(want * bytes_)))) break;
-        std::lock_guard<std::mutex> lk(mu_);
-        if (!p) return all_.empty() ? -1 : 0;   // the workers keep waiting for recycled chunks
-        for (size_t k = 0; k < want; k++) {
-            Chunk *c = new Chunk();
-            c->base = p + k * bytes_;
-            c->cap = bytes_;
-            c->cls = cls_;
-            all_.push_back(c);
-            free_.push_back(c);
-        }
-        return (int)want;
+        std::thread([this, want]() mutable {
+            uint8_t *p = nullptr;
+            for (; want; want /= 2)              // a smaller slab if the large one cannot be pinned
+                if ((p = static_cast<uint8_t *>(snapgpu_alloc_pinned(want * bytes_)))) break;
+            if (getenv("SNAPGPU_TRACE"))
+                fprintf(stderr, "[snapgpu] chunk pool %d: +%zu chunks of %zu MiB (%s)\n", cls_, p ? want : (size_t)0, bytes_ >> 20,
+                        p ? "pinned" : "no pinned memory");
+            std::lock_guard<std::mutex> lk(mu_);
+            growing_ = false;
+            failed_ = p == nullptr;              // no more growing; the workers keep waiting for recycled chunks
+            for (size_t k = 0; p && k < want; k++) {
+                Chunk *c = new Chunk();
+                c->base = p + k * bytes_;
+                c->cap = bytes_;
+                c->cls = cls_;
+                all_.push_back(c);
+                free_.push_back(c);
+            }
+        }).detach();
+        return 0;
     }
     size_t allocated() {
         std::lock_guard<std::mutex> lk(mu_);
         return all_.size();
+    }
+    // Grow the pool to at least n chunks now, on the calling thread (snapgpu_warm: ahead of the first tree).
+    bool reserve(size_t n) {
+        for (;;) {
+            size_t want;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (all_.size() >= std::min(n, max_)) return true;
+                if (failed_) return false;
+                if (growing_) want = 0;              // a tree is growing it at this moment: let that slab land first
+                else {
+                    want = std::min(std::min(n, max_) - all_.size(), std::max<size_t>(first_slab_, ((size_t)128 << 20) / bytes_));
+                    growing_ = true;
+                }
+            }
+            if (!want) {
+                std::this_thread::sleep_for(std::chrono::milliseconds(1));
+                continue;
+            }
+            uint8_t *p = static_cast<uint8_t *>(snapgpu_alloc_pinned(want * bytes_));
+            std::lock_guard<std::mutex> lk(mu_);
+            growing_ = false;
+            failed_ = p == nullptr;
+            for (size_t k = 0; p && k < want; k++) {
+                Chunk *c = new Chunk();
+                c->base = p + k * bytes_;
+                c->cap = bytes_;
+                c->cls = cls_;
+                all_.push_back(c);
+                free_.push_back(c);
+            }
+        }
     }
 
 private:
@@ -208,14 +254,15 @@ private:
     std::mutex mu_;
     std::vector<Chunk *> all_, free_;
     size_t waiters_ = 0;
+    bool growing_ = false, failed_ = false;
 };
 
 inline ChunkPool &small_chunks() {
-    static ChunkPool *p = new ChunkPool(kSmallChunk, 192, 8, 0);   // 32 MiB, doubling up to 768 MiB pinned
+    static ChunkPool *p = new ChunkPool(kSmallChunk, 192, 8, 0);   // 32 MiB, then slabs of up to 128 MiB, up to 768 MiB pinned
     return *p;
 }
 inline ChunkPool &large_chunks() {
-    static ChunkPool *p = new ChunkPool(kLargeChunk, 24, 2, 1);    // 64 MiB, doubling up to 768 MiB pinned
+    static ChunkPool *p = new ChunkPool(kLargeChunk, 24, 2, 1);    // 64 MiB, then slabs of 128 MiB, up to 768 MiB pinned
     return *p;
 }
 
@@ -805,10 +852,13 @@ private:
             // ready or in flight), wake the driver, wait for a new or a recycled chunk
             flush_chunk(W, cls ^ 1);
             bool asked = false;
+            // a chunk whose copy has just finished is usually back within a few hundred microseconds; only a worker
+            // that has waited longer asks for the pool to grow -- and much longer once the pool holds a quarter of a
+            // gigabyte: from there a wait is a hiccup of the pipeline, not a pool that is too small, and pinning
+            // another slab in the middle of a warm call costs that call more than the wait (measured: +37 ms)
+            const int patience = pool.allocated() * (cls ? kLargeChunk : kSmallChunk) >= ((size_t)256 << 20) ? 40 : 2;
             for (int spins = 0; !(c = pool.try_get()); spins++) {
-                // a chunk whose copy has just finished is usually back within a few hundred
-                // microseconds; only a worker that has waited longer asks for the pool to grow
-                if (spins == 2 && !asked) {
+                if (spins == patience && !asked) {
                     pool.begin_wait();
                     asked = true;
                 }

@@ -943,6 +943,24 @@ def test_archive_hashed_while_written_then_write_hashes_with_the_digest(gpu, ora
     assert build.hashes_yaml(str(tree), str(tar)) == want
 
 
+def test_warm_up_then_write_hashes(gpu, oracle, tmp_path):
+    """snapgpu_warm (no counterpart in the reference: it only moves one-off allocation and kernel-load cost ahead
+    of the first writeHashes) leaves results alone: the document of a tree hashed right after it is the oracle's,
+    and it can be called again at any time."""
+    from snappy_b200 import build
+    build.warm()
+    tree = tmp_path / "t"
+    (tree / "bin").mkdir(parents=True)
+    rng = np.random.default_rng(5)
+    for i, n in enumerate([0, 1, 111, 112, 4096, 40_000, 70_000, 300_000]):
+        (tree / "bin" / f"f{i}").write_bytes(rng.integers(0, 256, n, dtype=np.uint8).tobytes())
+    tar = tmp_path / "data.tar.gz"
+    tar.write_bytes(rng.integers(0, 256, 50_000, dtype=np.uint8).tobytes())
+    assert build.hashes_yaml(str(tree), str(tar)) == oracle.write_hashes(str(tree), str(tar))
+    build.warm()
+    assert build.hashes_yaml(str(tree), str(tar)) == oracle.write_hashes(str(tree), str(tar))
+
+
 def test_two_ended_claims_cover_every_unit_once(gpu, oracle):
     """Launches with several CTAs per SM claim units from both ends of the length-sorted plan (slow warps
     from the short end, sha512_kernels.cuh): on 400,000 files -- enough units for the mode to switch on at
