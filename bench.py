@@ -608,6 +608,20 @@ def main():
             tar2 = root / "cfg2_data.tar.gz"
             tar2.write_bytes(b"")
             e2e_tree["cfg2"] = one_tree("cfg2", t2, tar2, tree_paths(t2, len(lengths)), lengths, file_bytes)
+            # What a `snappy build` pays is the FIRST call of a process: the same tree in a fresh process, cold and
+            # after snapgpu_warm() (tools/cold_start_probe.py; the child binds device 0 of this rank's view).
+            try:
+                first = {}
+                for mode in ("cold", "warm"):
+                    out = subprocess.run([sys.executable, str(ROOT / "tools" / "cold_start_probe.py"), "child", mode, str(t2),
+                                          str(tar2)], capture_output=True, text=True, timeout=300, check=True).stdout
+                    r = json.loads(out.strip().splitlines()[-1])
+                    first[mode] = {k: round(r[k], 2) for k in ("snapgpu_warm_ms", "first_write_hashes_ms", "second_write_hashes_ms")}
+                first["what"] = ("config 2 tree, one fresh process per row: its first and second snapgpu_hashes_yaml; 'warm' "
+                                 "calls snapgpu_warm() first (what a build does from a goroutine while it copies and compresses)")
+                e2e_tree["cfg2_first_call_of_a_process"] = first
+            except Exception as exc:                                 # a measurement beside the line, never its failure
+                e2e_tree["cfg2_first_call_of_a_process"] = {"error": repr(exc)[:200]}
             shutil.rmtree(t2)
             # config 1: 1,000 x 4 KiB, with an empty archive and with a real tar | gzip of the tree
             l1 = np.full(1000, 4096, dtype=np.uint64)

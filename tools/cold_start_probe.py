@@ -14,7 +14,11 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 root = Path("/dev/shm/snapgpu_cold_tree")
 
-if len(sys.argv) > 1 and sys.argv[1] == "child":
+if len(sys.argv) > 1 and sys.argv[1] == "child":          # child MODE [TREE ARCHIVE]
+    if len(sys.argv) > 4:
+        tree_dir, archive = sys.argv[3], sys.argv[4]
+    else:
+        tree_dir, archive = str(root / "t"), str(root / "tar")
     from snappy_b200 import _native as N
     from snappy_b200 import build
     t0 = time.perf_counter()
@@ -26,10 +30,10 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         build.warm()
         t_warm = time.perf_counter() - t0
     t0 = time.perf_counter()
-    doc = build.hashes_yaml(str(root / "t"), str(root / "tar"))
+    doc = build.hashes_yaml(tree_dir, archive)
     t_first = time.perf_counter() - t0
     t0 = time.perf_counter()
-    build.hashes_yaml(str(root / "t"), str(root / "tar"))
+    build.hashes_yaml(tree_dir, archive)
     t_second = time.perf_counter() - t0
     print(json.dumps({"mode": sys.argv[2], "pin": os.environ.get("SNAPGPU_PIN", "huge pages + cudaHostRegister"),
                       "snapgpu_init_ms": t_init * 1e3, "snapgpu_warm_ms": t_warm * 1e3,
