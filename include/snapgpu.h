@@ -259,6 +259,9 @@ int snapgpu_test_filehash_yaml(const char *name, long long size, const char *sha
                                char **out, size_t *out_len);
 int snapgpu_test_shard(const uint64_t *weights, size_t n, int ndev, int *device_of);
 int snapgpu_test_split(const uint64_t *lengths, size_t n, int ndev, size_t *cut);   /* 1 = cut in place, 0 = too heavy an item */
+/* rows of (user index, offset, length, prefix, flags, chunk) as the host-buffer pipeline cuts a shard into chunks of at
+ * most `cap` bytes: is_sha 0 compare, 1 SHA-512 with one fixed chunk size, 2 SHA-512 with the pipeline's sizes (64 MiB,
+ * 256 MiB, then `cap`, ending on 128 MiB and 64 MiB) */
 long long snapgpu_test_chunks(const uint64_t *offsets, const uint64_t *lengths, size_t n,
                               uint64_t cap, int is_sha, uint64_t *rows, size_t max_rows);
 /* the order the device-side length binning gives files of these lengths (needs a GPU) */

@@ -2074,7 +2074,14 @@ long long snapgpu_test_chunks(const uint64_t *offsets, const uint64_t *lengths, 
     std::vector<WorkItem> in(n);
     ChunkPlan plan;
     for (size_t i = 0; i < n; i++) in[i] = WorkItem{i, offsets[i], lengths[i], 0, 0};
-    build_chunks(in, (size_t)cap, is_sha != 0, plan);
+    if (is_sha == 2) {                       // as sha512_shard cuts a shard: chunk sizes ramp up and taper off
+        const ItemList list(in);
+        ChunkStream cs(list, true, plan);
+        Chunk c;
+        for (size_t ci = 0; cs.next(taper_cap(ramp_cap(ci, (size_t)cap), list, cs.k), (size_t)cap, &c); ci++) {}
+    } else {
+        build_chunks(in, (size_t)cap, is_sha != 0, plan);
+    }
     const std::vector<Chunk> &chunks = plan.chunks;
     size_t row = 0;
     for (size_t c = 0; c < chunks.size(); c++)

@@ -211,6 +211,58 @@ def test_chunker_covers_every_byte_once(native):
             assert end - begin <= cap
 
 
+def test_pipeline_chunks_ramp_up_and_taper_off(native):
+    """The chunks sha512_shard cuts a shard into (csrc/snapgpu.cu: ramp_cap, taper_cap): 64 MiB, 256 MiB, then the
+    staging size -- and the end of the shard as 128 MiB and 64 MiB, because nothing overlaps the hashing of the
+    last chunk.  Every file in exactly one chunk, in order; short shards and unordered lists are cut sanely too."""
+    MiB = 1 << 20
+
+    def chunks_of(lengths, cap, offsets=None):
+        lengths = np.asarray(lengths, dtype=np.uint64)
+        if offsets is None:
+            offsets = np.zeros(len(lengths), dtype=np.uint64)
+            pos = 0
+            for i, l in enumerate(lengths):
+                offsets[i] = pos
+                pos += (int(l) + 15) // 16 * 16
+        rows = np.zeros((len(lengths) + 64, 6), dtype=np.uint64)
+        n = native.lib().snapgpu_test_chunks(offsets.ctypes.data, lengths.ctypes.data, len(lengths), cap, 2,
+                                             rows.ctypes.data, len(rows))
+        assert n == len(lengths)                           # nothing here is larger than a chunk: no pieces
+        rows = rows[:n]
+        assert rows[:, 0].tolist() == list(range(len(lengths)))
+        assert (np.diff(rows[:, 5].astype(np.int64)) >= 0).all()
+        spans = []
+        for c in np.unique(rows[:, 5]):
+            r = rows[rows[:, 5] == c]
+            spans.append(int((r[:, 1] + r[:, 2]).max()) - int(r[:, 1].min()))
+        return spans
+
+    rng = np.random.default_rng(3)
+    lengths = rng.integers(1024, 65537, 36_000)            # ~1.2 GB, the size of config 2
+    total = int(((lengths + 15) // 16 * 16).sum())
+    spans = chunks_of(lengths, 1024 * MiB)
+    assert len(spans) == 5 and sum(spans) <= total
+    assert 63 * MiB < spans[0] <= 64 * MiB and 255 * MiB < spans[1] <= 256 * MiB
+    assert 127 * MiB < spans[3] <= 129 * MiB and 63 * MiB < spans[4] <= 65 * MiB
+    assert spans[2] == max(spans)
+    # a staging size below the ramp: every chunk at most that size, and still the two short ones at the end
+    spans = chunks_of(lengths, 200 * MiB)
+    assert max(spans) <= 200 * MiB and 63 * MiB < spans[-1] <= 65 * MiB and 127 * MiB < spans[-2] <= 129 * MiB
+    # shards shorter than the taper: one chunk, or the first 64 MiB and a last chunk of at most 96 MiB
+    assert len(chunks_of(lengths[:1000], 1024 * MiB)) == 1
+    spans = chunks_of(lengths[:4500], 1024 * MiB)           # ~150 MB
+    assert len(spans) == 2 and spans[0] <= 64 * MiB and spans[1] <= 96 * MiB
+    # files listed back to front: no estimate of what is left, the plain ramp
+    lens = rng.integers(1024, 65537, 3000).astype(np.uint64)
+    offs = np.zeros(len(lens), dtype=np.uint64)
+    pos = 0
+    for i in range(len(lens) - 1, -1, -1):
+        offs[i] = pos
+        pos += (int(lens[i]) + 15) // 16 * 16
+    assert sum(1 for _ in chunks_of(lens, 1024 * MiB, offs)) >= 1
+
+
 # ---- copyToBuildDir (snappy/build.go:362-418): host logic that needs no GPU ---------------------
 
 EXCLUDE_CASES = ["foo.snap", "foo.click", ".foo.swp", "..swp", ".swp", "foo~", "~", ",,x", ",x", ".#lock", ".~tmp",
