@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 
 #include "../../include/snapgpu.h"
 
@@ -87,6 +88,24 @@ int main(int argc, char **argv) {
             }
         }
         fwrite(first.data(), 1, first.size(), stdout);
+    } else if (cmd == "warm" && argc == 4) {
+        // snapgpu_warm from a second thread while the first already hashes the tree (a build's goroutine may lose the race)
+        int warm_rc = 0;
+        std::thread warmer([&] { warm_rc = snapgpu_warm(); });
+        rc = snapgpu_hashes_yaml(argv[2], argv[3], &out, &len);
+        warmer.join();
+        if (rc) return die(rc);
+        if (warm_rc) return die(warm_rc);
+        std::string first(out, len);
+        snapgpu_free(out);
+        if ((rc = snapgpu_warm())) return die(rc);
+        if ((rc = snapgpu_hashes_yaml(argv[2], argv[3], &out, &len))) return die(rc);
+        if (first != std::string(out, len)) {
+            printf("ERR 0 the document after the warm-up differs\n");
+            return 3;
+        }
+        fwrite(out, 1, len, stdout);
+        snapgpu_free(out);
     } else if (cmd == "write_hashes" && argc == 4) {
         if ((rc = snapgpu_write_hashes(argv[2], argv[3]))) return die(rc);
     } else if (cmd == "verify" && (argc == 4 || argc == 5)) {

@@ -959,6 +959,21 @@ def test_warm_up_then_write_hashes(gpu, oracle, tmp_path):
     assert build.hashes_yaml(str(tree), str(tar)) == oracle.write_hashes(str(tree), str(tar))
     build.warm()
     assert build.hashes_yaml(str(tree), str(tar)) == oracle.write_hashes(str(tree), str(tar))
+    # ... and from a second thread while writeHashes is already running (a build's goroutine may lose the race)
+    import threading
+    errors = []
+
+    def warm():
+        try:
+            build.warm()
+        except Exception as exc:                              # noqa: BLE001
+            errors.append(exc)
+
+    t = threading.Thread(target=warm)
+    t.start()
+    doc = build.hashes_yaml(str(tree), str(tar))
+    t.join()
+    assert not errors and doc == oracle.write_hashes(str(tree), str(tar))
 
 
 def test_two_ended_claims_cover_every_unit_once(gpu, oracle):

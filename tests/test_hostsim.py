@@ -102,6 +102,19 @@ def test_mixed_tree_matches_the_oracle(sim, oracle, tmp_path, flavour):
         assert got == want
 
 
+@pytest.mark.parametrize("flavour", ["asan", "tsan"])
+def test_warm_up_beside_a_running_write_hashes(sim, oracle, tmp_path, flavour):
+    """snapgpu_warm from a second thread while the first is already inside writeHashes (both grow the chunk pool,
+    both open a session), and again afterwards: same document, nothing for the sanitizers to report."""
+    rng = np.random.default_rng(17)
+    tree = tmp_path / "tree"
+    make_mixed_tree(tree, rng)
+    tar = tmp_path / "data.tar.gz"
+    tar.write_bytes(rng.integers(0, 256, size=(1 << 20) + 5, dtype=np.uint8).tobytes())
+    env = {"SNAPGPU_SHARED_FDS": "1"} if flavour == "tsan" else {}
+    assert run(sim[flavour], "warm", tree, tar, env=env).stdout == oracle.write_hashes(str(tree), str(tar))
+
+
 def test_empty_tree_and_missing_root(sim, oracle, tmp_path):
     tar = tmp_path / "t"
     tar.write_bytes(b"x")
