@@ -75,6 +75,18 @@ for cfg in configs:
            "yaml_bytes": len(doc), "yaml_identical_to_oracle": doc == want,
            "packer_threads": int(os.environ.get("SNAPGPU_PACK_THREADS", "0")) or min(16, os.cpu_count() or 1)}
     assert doc == want, "hashes.yaml differs from the oracle"
+    # verification: the document just made, written beside the tree, checked against the tree
+    yaml_path = base / (cfg + "_hashes.yaml")
+    yaml_path.write_bytes(doc)
+    build.verifyHashes(str(root), str(yaml_path), tar)
+    verify_best = 1e9
+    for _ in range(3):
+        t0 = time.perf_counter()
+        report = build.verifyHashes(str(root), str(yaml_path), tar)
+        verify_best = min(verify_best, time.perf_counter() - t0)
+    assert report == [], report[:3]
+    row["gpu_verify_hashes_ms"] = verify_best * 1e3
+    yaml_path.unlink()
     # build staging: copyToBuildDir with the copy path forced, then writeHashes
     stage = base / (cfg + "_stage")
     fused_best = 1e9
