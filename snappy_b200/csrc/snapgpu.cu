@@ -579,6 +579,11 @@ struct PlanInfo {
     uint64_t max_short_blocks = 0;      // longest item below min_long_blocks
     size_t n_long = 0;                  // items of >= min_long_blocks blocks
     std::vector<u32> long_idx;          // their indices (the first kLongMaxCandidates)
+    // second tier, for a launch with too many candidates of the first (50 000 files of which 4 000 are longer than
+    // 32 KiB, and four of 1 GiB): the items of at least kLongMinBlocksLane blocks alone
+    uint64_t max_mid_blocks = 0;        // longest item of the first tier only
+    size_t n_very = 0;
+    std::vector<u32> very_idx;
 };
 
 template <typename Get>
@@ -602,6 +607,12 @@ static void write_descriptors(Get get, size_t n, SegDesc *descs, PlanInfo *info)
             if (nb >= min_long) {
                 if (pi.long_idx.size() < kLongMaxCandidates) pi.long_idx.push_back((u32)i);
                 pi.n_long++;
+                if (nb >= kLongMinBlocksLane) {
+                    if (pi.very_idx.size() < kLongMaxCandidates) pi.very_idx.push_back((u32)i);
+                    pi.n_very++;
+                } else {
+                    pi.max_mid_blocks = std::max(pi.max_mid_blocks, nb);
+                }
             } else {
                 pi.max_short_blocks = std::max(pi.max_short_blocks, nb);
             }
@@ -624,6 +635,10 @@ static void write_descriptors(Get get, size_t n, SegDesc *descs, PlanInfo *info)
         info->max_short_blocks = std::max(info->max_short_blocks, pi.max_short_blocks);
         for (u32 i : pi.long_idx)
             if (info->long_idx.size() < kLongMaxCandidates) info->long_idx.push_back(i);
+        info->n_very += pi.n_very;
+        info->max_mid_blocks = std::max(info->max_mid_blocks, pi.max_mid_blocks);
+        for (u32 i : pi.very_idx)
+            if (info->very_idx.size() < kLongMaxCandidates) info->very_idx.push_back(i);
     }
 }
 
@@ -698,17 +713,28 @@ static int launch_sha512(Pipe &D, cudaStream_t stream, const uint8_t *d_data, Ge
     // the higher throughput, the long kernel only the shorter chain.
     SegDesc *h_descs = static_cast<SegDesc *>(slot->h_buf);
     size_t n_long = 0;
-    if (info.n_long >= 1 && info.n_long <= kLongMaxCandidates && long_mode) {
+    const std::vector<u32> *candidates = nullptr;
+    uint64_t floor_blocks = 0, rest_blocks = 0;           // smallest candidate; longest item that is not one
+    if (long_mode && info.n_long >= 1 && info.n_long <= kLongMaxCandidates) {
+        candidates = &info.long_idx;
+        floor_blocks = info.min_long_blocks;
+        rest_blocks = info.max_short_blocks;
+    } else if (long_mode && info.n_very >= 1 && info.n_very <= kLongMaxCandidates) {
+        candidates = &info.very_idx;
+        floor_blocks = std::max(info.min_long_blocks, kLongMinBlocksLane);
+        rest_blocks = std::max(info.max_short_blocks, info.max_mid_blocks);
+    }
+    if (candidates) {
         const uint64_t lanes = (uint64_t)D.sm_count * kShaThreads;
-        uint64_t threshold = std::max<uint64_t>(info.min_long_blocks, kLongDominance * (total_blocks / lanes));
+        uint64_t threshold = std::max<uint64_t>(floor_blocks, kLongDominance * (total_blocks / lanes));
         if (pair_bin) threshold = std::max(threshold, max_blocks * kPairBalanceNum / kPairBalanceDen);
         size_t dominant = 0;
-        for (u32 i : info.long_idx) dominant += seg_blocks(h_descs[i].len, h_descs[i].flags) >= threshold;
+        for (u32 i : *candidates) dominant += seg_blocks(h_descs[i].len, h_descs[i].flags) >= threshold;
         const size_t room = pair_bin ? std::min<size_t>(kLongMaxFiles, (size_t)D.sm_count * kPairFilesPerCta) : 256;
         if (dominant >= 1 && dominant <= room) {
             SegDesc *h_long = h_descs + n;
-            uint64_t max_rest = info.max_short_blocks;
-            for (u32 i : info.long_idx) {
+            uint64_t max_rest = rest_blocks;
+            for (u32 i : *candidates) {
                 SegDesc &d = h_descs[i];
                 const uint64_t nb = seg_blocks(d.len, d.flags);
                 if (nb < threshold) {

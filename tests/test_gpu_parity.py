@@ -745,6 +745,9 @@ def test_config3_shape_at_reduced_size(gpu):
     device.synth_fill_device(d, off, lengths)
     gpu.reset_stats()
     dg = device.sha512_batch_device(d, off, lengths).cpu().numpy()
+    # the four long files leave the batched kernel although the launch has thousands of files above the bin's lower
+    # bound (32 KiB): with too many candidates of that size the bin falls back to the files of 128 KiB and more
+    assert gpu.stats().sha512_long_launches == 1
     _spot_check(dg, lengths, [50_000, 50_001, 50_002, 50_003, 0, 49_999, 123, 31_337])
     gpu.set_option("long_kernel", 0)
     small = device.sha512_batch_device(d, off[:50_000], lengths[:50_000]).cpu().numpy()
