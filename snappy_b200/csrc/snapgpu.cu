@@ -231,7 +231,8 @@ struct Runtime {
 // tools/pin_probe.cu), which is what the first large tree of a process used to wait for.  From 2 MiB up the memory is
 // instead an anonymous mapping on transparent huge pages (madvise; 512x fewer pages to pin), faulted in by a few
 // threads at once and then registered: 256 MiB in ~10 ms, same copy rate (55 GB/s).  Anything that fails on the way
-// falls back to cudaHostAlloc.  SNAPGPU_PIN=hostalloc forces the old path (for A/B runs).
+// falls back to cudaHostAlloc.  SNAPGPU_PIN=hostalloc forces the old path, SNAPGPU_PIN=nohuge the mapping without huge
+// pages (for A/B runs: warm, the three are indistinguishable; cold, they are 115 / 10-50 / 65 ms per 256 MiB).
 namespace {
 struct PinnedMapping {
     void *map_base;
@@ -247,7 +248,8 @@ void *pinned_huge_alloc(size_t bytes) {
     if (m == MAP_FAILED) return nullptr;
     uint8_t *a = reinterpret_cast<uint8_t *>(((uintptr_t)m + kHuge - 1) & ~(uintptr_t)(kHuge - 1));
 #ifdef MADV_HUGEPAGE
-    madvise(a, len, MADV_HUGEPAGE);                  // refused or unsupported: 4 KiB pages, still correct
+    static const bool no_huge = [] { const char *e = getenv("SNAPGPU_PIN"); return e && !strcmp(e, "nohuge"); }();
+    if (!no_huge) madvise(a, len, MADV_HUGEPAGE);    // refused or unsupported: 4 KiB pages, still correct
 #endif
 #ifdef MADV_DONTFORK
     madvise(a, len, MADV_DONTFORK);                  // a child (tar, gzip ...) neither copies nor shares DMA memory
