@@ -264,6 +264,10 @@ int snapgpu_test_split(const uint64_t *lengths, size_t n, int ndev, size_t *cut)
  * 256 MiB, then `cap`, ending on 128 MiB and 64 MiB) */
 long long snapgpu_test_chunks(const uint64_t *offsets, const uint64_t *lengths, size_t n,
                               uint64_t cap, int is_sha, uint64_t *rows, size_t max_rows);
+/* which files the long-file bin takes out of a launch of files of these lengths on a device of sm_count SMs (long_mode,
+ * min_blocks: options long_kernel and long_min_blocks), and how many files a lane-pair CTA gets; host logic, no GPU */
+int snapgpu_test_long_bin(const uint64_t *lengths, size_t n, int sm_count, int long_mode, long long min_blocks,
+                          uint8_t *in_bin, uint32_t *per_cta);
 /* the order the device-side length binning gives files of these lengths (needs a GPU) */
 int snapgpu_test_plan_order(const uint64_t *lengths, size_t n, uint32_t *order);
 

@@ -111,6 +111,7 @@ SIGNATURES = {
     "snapgpu_test_shard": (_i, [_vp, _sz, _i, _vp]),
     "snapgpu_test_split": (_i, [_vp, _sz, _i, _vp]),
     "snapgpu_test_chunks": (ctypes.c_longlong, [_vp, _vp, _sz, _u64, _i, _vp, _sz]),
+    "snapgpu_test_long_bin": (_i, [_vp, _sz, _i, _i, ctypes.c_longlong, _vp, _vp]),
 }
 
 

@@ -677,6 +677,68 @@ static int enqueue_length_binning(Pipe &D, cudaStream_t stream, const DevicePlan
 }
 
 // Enqueue the hashing of `n` segments (get(i) -> SegDesc) of `d_data` on `stream`.
+// Which files of a launch go to the long-file bin (rule above): marks them kSegSkip in descs[0..n), appends their
+// descriptors at descs[n..), longest first, takes their blocks out of *total_blocks and sets *max_blocks to the longest
+// file left to the batched kernel.  Returns how many.  Pure host logic (tests/test_host_logic.py drives it through
+// snapgpu_test_long_bin).
+static size_t select_long_bin(const PlanInfo &info, SegDesc *h_descs, size_t n, int sm_count, long long long_mode,
+                              uint64_t *total_blocks_io, uint64_t *max_blocks_io) {
+    const bool pair_bin = long_mode >= 2;
+    uint64_t &total_blocks = *total_blocks_io, &max_blocks = *max_blocks_io;
+    size_t n_long = 0;
+    const std::vector<u32> *candidates = nullptr;
+    uint64_t floor_blocks = 0, rest_blocks = 0;           // smallest candidate; longest item that is not one
+    if (long_mode && info.n_long >= 1 && info.n_long <= kLongMaxCandidates) {
+        candidates = &info.long_idx;
+        floor_blocks = info.min_long_blocks;
+        rest_blocks = info.max_short_blocks;
+    } else if (long_mode && info.n_very >= 1 && info.n_very <= kLongMaxCandidates) {
+        candidates = &info.very_idx;
+        floor_blocks = std::max(info.min_long_blocks, kLongMinBlocksLane);
+        rest_blocks = std::max(info.max_short_blocks, info.max_mid_blocks);
+    }
+    if (candidates) {
+        const uint64_t lanes = (uint64_t)sm_count * kShaThreads;
+        uint64_t threshold = std::max<uint64_t>(floor_blocks, kLongDominance * (total_blocks / lanes));
+        if (pair_bin) threshold = std::max(threshold, max_blocks * kPairBalanceNum / kPairBalanceDen);
+        size_t dominant = 0;
+        for (u32 i : *candidates) dominant += seg_blocks(h_descs[i].len, h_descs[i].flags) >= threshold;
+        const size_t room = pair_bin ? std::min<size_t>(kLongMaxFiles, (size_t)sm_count * kPairFilesPerCta) : 256;
+        if (dominant >= 1 && dominant <= room) {
+            SegDesc *h_long = h_descs + n;
+            uint64_t max_rest = rest_blocks;
+            for (u32 i : *candidates) {
+                SegDesc &d = h_descs[i];
+                const uint64_t nb = seg_blocks(d.len, d.flags);
+                if (nb < threshold) {
+                    max_rest = std::max(max_rest, nb);
+                    continue;
+                }
+                h_long[n_long++] = d;
+                total_blocks -= nb;
+                d.flags |= kSegSkip;
+            }
+            std::sort(h_long, h_long + n_long, [](const SegDesc &a, const SegDesc &b) {
+                return seg_blocks(a.len, a.flags) > seg_blocks(b.len, b.flags);
+            });
+            max_blocks = max_rest;
+        }
+    }
+    return n_long;
+}
+
+// Files per CTA of the lane-pair kernel for n_long files (forced: option pair_files_per_cta, 0 = this rule).  A CTA of
+// that kernel has its SM to itself (sha512_pair.cuh: kPairSmemBytes), so its consumer warp shares the ALU pipe with
+// nobody -- and the batched kernel has that many SMs less.  Up to a quarter of the SMs go to the bin: one file per CTA
+// while that lasts (then the rounds of a block are one branch-free region, 1.81 us per block), two (1.88), and from
+// there 16 per CTA (two regions, 1.90 whatever the count) on as many CTAs as it takes.
+static u32 pair_cta_shape(size_t n_long, int sm_count, u32 forced) {
+    const u32 budget = std::max<u32>(1, (u32)sm_count / 4);
+    u32 per_cta = n_long <= budget ? 1 : n_long <= 2 * (size_t)budget ? 2 : (u32)kPairFilesPerCta;
+    if (forced) per_cta = forced;
+    return std::min<u32>(std::max<u32>(per_cta, 1), kPairFilesPerCta);
+}
+
 // Caller holds D.mu.  The plan goes up on the copy stream so that it overlaps whatever the
 // caller's stream is still running.
 template <typename Get>
@@ -714,45 +776,7 @@ static int launch_sha512(Pipe &D, cudaStream_t stream, const uint8_t *d_data, Ge
     // beside it on its own stream.  With many long files the batched kernel keeps them: it has
     // the higher throughput, the long kernel only the shorter chain.
     SegDesc *h_descs = static_cast<SegDesc *>(slot->h_buf);
-    size_t n_long = 0;
-    const std::vector<u32> *candidates = nullptr;
-    uint64_t floor_blocks = 0, rest_blocks = 0;           // smallest candidate; longest item that is not one
-    if (long_mode && info.n_long >= 1 && info.n_long <= kLongMaxCandidates) {
-        candidates = &info.long_idx;
-        floor_blocks = info.min_long_blocks;
-        rest_blocks = info.max_short_blocks;
-    } else if (long_mode && info.n_very >= 1 && info.n_very <= kLongMaxCandidates) {
-        candidates = &info.very_idx;
-        floor_blocks = std::max(info.min_long_blocks, kLongMinBlocksLane);
-        rest_blocks = std::max(info.max_short_blocks, info.max_mid_blocks);
-    }
-    if (candidates) {
-        const uint64_t lanes = (uint64_t)D.sm_count * kShaThreads;
-        uint64_t threshold = std::max<uint64_t>(floor_blocks, kLongDominance * (total_blocks / lanes));
-        if (pair_bin) threshold = std::max(threshold, max_blocks * kPairBalanceNum / kPairBalanceDen);
-        size_t dominant = 0;
-        for (u32 i : *candidates) dominant += seg_blocks(h_descs[i].len, h_descs[i].flags) >= threshold;
-        const size_t room = pair_bin ? std::min<size_t>(kLongMaxFiles, (size_t)D.sm_count * kPairFilesPerCta) : 256;
-        if (dominant >= 1 && dominant <= room) {
-            SegDesc *h_long = h_descs + n;
-            uint64_t max_rest = rest_blocks;
-            for (u32 i : *candidates) {
-                SegDesc &d = h_descs[i];
-                const uint64_t nb = seg_blocks(d.len, d.flags);
-                if (nb < threshold) {
-                    max_rest = std::max(max_rest, nb);
-                    continue;
-                }
-                h_long[n_long++] = d;
-                total_blocks -= nb;
-                d.flags |= kSegSkip;
-            }
-            std::sort(h_long, h_long + n_long, [](const SegDesc &a, const SegDesc &b) {
-                return seg_blocks(a.len, a.flags) > seg_blocks(b.len, b.flags);
-            });
-            max_blocks = max_rest;
-        }
-    }
+    const size_t n_long = select_long_bin(info, h_descs, n, D.sm_count, long_mode, &total_blocks, &max_blocks);
     const size_t n_main = n - n_long;
 
     // upload and binning run on the copy stream, i.e. beside whatever the caller's stream is
@@ -798,16 +822,7 @@ static int launch_sha512(Pipe &D, cudaStream_t stream, const uint8_t *d_data, Ge
         SG_CUDA(cudaEventRecord(slot->fork, stream));
         SG_CUDA(cudaStreamWaitEvent(long_stream, slot->fork, 0));
         if (pair_bin) {                                     // one chain per lane pair (sha512_pair.cuh)
-            // A CTA of this kernel has its SM to itself (sha512_pair.cuh: kPairSmemBytes), so its consumer warp
-            // shares the ALU pipe with nobody -- and the batched kernel has that many SMs less.  Up to a quarter
-            // of the SMs go to the bin: one file per CTA while that lasts (then the rounds of a block are one
-            // branch-free region, 1.81 us per block), two (1.88), and from there 16 per CTA (two regions, 1.90
-            // whatever the count) on as many CTAs as it takes.
-            const u32 budget = std::max<u32>(1, (u32)D.sm_count / 4);
-            u32 per_cta = n_long <= budget ? 1 : n_long <= 2 * (size_t)budget ? 2 : (u32)kPairFilesPerCta;
-            const u32 forced = (u32)R.opt.pair_files_per_cta.load();
-            if (forced) per_cta = forced;
-            per_cta = std::min<u32>(std::max<u32>(per_cta, 1), kPairFilesPerCta);
+            const u32 per_cta = pair_cta_shape(n_long, D.sm_count, (u32)R.opt.pair_files_per_cta.load());
             const u32 long_grid = (u32)((n_long + per_cta - 1) / per_cta);
             pair_kernel_for(aligned, (int)R.opt.pair_form.load(), per_cta <= 2 ? 1 : 2)
                 <<<long_grid, kLongThreads, kPairSmemBytes, long_stream>>>(d_data, plan.long_descs, (u32)n_long, d_digests,
@@ -2065,6 +2080,24 @@ int snapgpu_test_plan_order(const uint64_t *lengths, size_t n, uint32_t *order) 
     if ((rc = enqueue_length_binning(*D, s, plan, n, info.max_blocks))) return rc;
     SG_CUDA(cudaMemcpyAsync(order, plan.order, n * sizeof(u32), cudaMemcpyDeviceToHost, s));
     SG_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+// The long-file bin's choice for files of these lengths on a device of sm_count SMs (long_mode as option
+// long_kernel, min_blocks as option long_min_blocks): in_bin[i] = 1 for the files that leave the batched kernel,
+// *per_cta = files per CTA of the lane-pair kernel (0 when nothing is binned).  Host logic only, no GPU.
+int snapgpu_test_long_bin(const uint64_t *lengths, size_t n, int sm_count, int long_mode, long long min_blocks,
+                          uint8_t *in_bin, uint32_t *per_cta) {
+    if (!lengths || !in_bin || !per_cta || sm_count < 1 || n > 0xfffffff0ull) return fail(SNAPGPU_EINVAL, "bad argument");
+    std::vector<SegDesc> descs(n + kLongMaxFiles);
+    PlanInfo info;
+    info.min_long_blocks = min_blocks > 0 ? (uint64_t)min_blocks : long_mode >= 2 ? kLongMinBlocksPair : kLongMinBlocksLane;
+    write_descriptors([lengths](size_t i) { return SegDesc{0, std::min<uint64_t>(lengths[i], kMaxSegBytes - 1), 0, (u32)i, 0}; },
+                      n, descs.data(), &info);
+    uint64_t total_blocks = info.total_blocks, max_blocks = info.max_blocks;
+    const size_t n_long = long_mode ? select_long_bin(info, descs.data(), n, sm_count, long_mode, &total_blocks, &max_blocks) : 0;
+    for (size_t i = 0; i < n; i++) in_bin[i] = (descs[i].flags & kSegSkip) ? 1 : 0;
+    *per_cta = n_long && long_mode >= 2 ? pair_cta_shape(n_long, sm_count, 0) : 0;
     return 0;
 }
 

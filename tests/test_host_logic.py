@@ -263,6 +263,56 @@ def test_pipeline_chunks_ramp_up_and_taper_off(native):
     assert sum(1 for _ in chunks_of(lens, 1024 * MiB, offs)) >= 1
 
 
+def test_long_file_bin_policy(native):
+    """Which files of a launch leave the batched kernel for the long-file bin (csrc/snapgpu.cu: select_long_bin,
+    pair_cta_shape) -- the files whose serial chain would set the launch's makespan:
+    lane-pair form: at least 256 blocks (32 KiB), at least four times the launch's blocks per lane and within 31/64 of
+    the longest file; with more than 4,096 files above the lower bound only those of 128 KiB and more are looked at;
+    at most one CTA per SM of 16 files; one file per CTA up to a quarter of the SMs, two up to half, 16 beyond."""
+    from snappy_b200 import synth
+
+    def bin_of(lengths, sm=148, mode=2, min_blocks=0):
+        lengths = np.ascontiguousarray(lengths, dtype=np.uint64)
+        flags = np.zeros(len(lengths), dtype=np.uint8)
+        per_cta = ctypes.c_uint32(0)
+        native.check(native.lib().snapgpu_test_long_bin(lengths.ctypes.data, len(lengths), sm, mode, min_blocks,
+                                                        flags.ctypes.data, ctypes.addressof(per_cta)))
+        return flags.astype(bool), per_cta.value
+
+    cfg2 = synth.lognormal_sizes(100_000)
+    blocks = synth.blocks(cfg2)
+    # config 3 as one batch: thousands of files above 32 KiB, four of 1 GiB -> exactly those four, one per CTA
+    flags, per_cta = bin_of(np.concatenate([cfg2[:50_000], np.full(4, 1 << 30, dtype=np.uint64)]))
+    assert np.nonzero(flags)[0].tolist() == [50_000, 50_001, 50_002, 50_003] and per_cta == 1
+    # a small chain-bound batch: the files of 256+ blocks that are within 31/64 of the longest
+    flags, per_cta = bin_of(cfg2[:3000])
+    b = blocks[:3000]
+    want = b >= max(256, int(b.max()) * 31 // 64)
+    assert np.array_equal(flags, want) and 100 < flags.sum() < 600 and per_cta == 16
+    # a launch that is bound by throughput keeps everything in the batched kernel
+    assert not bin_of(cfg2)[0].any()
+    assert not bin_of(np.concatenate([np.full(2000, 65536), np.full(400_000, 4096)]))[0].any()
+    # nothing as long as 32 KiB: nothing to gain
+    assert not bin_of(np.minimum(cfg2[:3000], 30_000))[0].any()
+    # the one-lane form gains nothing below 128 KiB; long_min_blocks overrides either bound
+    assert not bin_of(cfg2[:3000], mode=1)[0].any()
+    assert bin_of(cfg2[:3000], min_blocks=1024)[0].sum() == 0 and bin_of(cfg2[:3000], min_blocks=400)[0].sum() > 0
+    assert not bin_of(cfg2[:3000], mode=0)[0].any()
+    # room: one CTA per SM of 16 files
+    assert bin_of(np.full(2368, 130 * 1024))[0].all() and not bin_of(np.full(2369, 130 * 1024))[0].any()
+    assert bin_of(np.full(32, 130 * 1024), sm=2)[0].all() and not bin_of(np.full(33, 130 * 1024), sm=2)[0].any()
+    # placement: one file per CTA up to a quarter of the SMs, two up to half, then 16
+    for n, shape in ((1, 1), (37, 1), (38, 2), (74, 2), (75, 16), (2000, 16)):
+        assert bin_of(np.full(n, 1 << 20))[1] == shape, n
+    # the few dominant files of a mixed launch, whatever their order in the list
+    mixed = np.concatenate([np.full(5, 4 << 20), cfg2[:20_000], [7 << 20]]).astype(np.uint64)
+    flags, per_cta = bin_of(mixed)
+    assert np.nonzero(flags)[0].tolist() == [0, 1, 2, 3, 4, 20_005] and per_cta == 1
+    # ... but not the ones that would finish in the batched kernel before the longest does on its lane pair (3 < 7 * 31/64)
+    mixed[:5] = 3 << 20
+    assert np.nonzero(bin_of(mixed)[0])[0].tolist() == [20_005]
+
+
 # ---- copyToBuildDir (snappy/build.go:362-418): host logic that needs no GPU ---------------------
 
 EXCLUDE_CASES = ["foo.snap", "foo.click", ".foo.swp", "..swp", ".swp", "foo~", "~", ",,x", ",x", ".#lock", ".~tmp",
