@@ -174,3 +174,28 @@ def test_pair_kernel_shuffle_form(native):
     assert len(body) == 1
     ops = re.findall(r"/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", body[0])
     assert ops.count("SHFL.BFLY") >= 2 * 18 and not any(op.startswith(("LDL", "STL")) for op in ops)
+
+
+def test_pair_cta_keeps_its_sm_to_itself(native):
+    """A lane-pair CTA asks for 200 KB of dynamic shared memory (csrc/sha512_pair.cuh: kPairSmemBytes) so that no
+    batched-kernel CTA fits beside it on the SM -- a second warp on the consumer's sub-partition would halve the
+    chain's share of the ALU pipe.  Checked against the shared memory the built kernels really use."""
+    text = subprocess.run(["cuobjdump", "-res-usage", str(native.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    usage = {}
+    name = None
+    for line in text.splitlines():
+        m = re.search(r"Function (\S+):", line)
+        if m:
+            name = m.group(1)
+        m = re.search(r"SHARED:(\d+)", line)
+        if m and name:
+            usage[name] = int(m.group(1))
+    # the shipped batched kernel (variants 0, 1, 5: cp.async staging through shared memory); the register-prefetch
+    # variants 2-4 are comparison builds and use no shared memory
+    batched = [v for k, v in usage.items() if "sha512_segments_kernel_v2" in k]
+    pair_static = [v for k, v in usage.items() if "sha512_pair_kernel" in k]
+    assert batched and pair_static
+    sm_bytes, reserved = 228 * 1024, 1024                     # per SM; reserved per resident CTA
+    pair_cta = 200 * 1024 + max(pair_static) + reserved
+    assert pair_cta <= sm_bytes                               # the pair CTA itself fits
+    assert pair_cta + min(batched) + reserved > sm_bytes      # ... and leaves no room for the smallest batched CTA
