@@ -38,3 +38,6 @@ python tools/tree_stress.py 60 1 > ${o}_tree_stress.json 2> ${o}_tree_stress.err
 SNAPGPU_TRACE=1 python tools/tree_bench.py ${o}_tree_bench.jsonl cfg2 > ${o}_tree_bench.log 2> ${o}_tree_bench_trace.log; echo "tree bench exit $?"
 python tools/tree_cfg3.py 20000 64 16 > ${o}_tree_cfg3_shape.json 2> ${o}_tree_cfg3_shape.err; echo "tree cfg3 exit $?"
 python tools/h2d_piece_probe.py > ${o}_h2d_pieces.jsonl 2> ${o}_h2d_pieces.err; echo "h2d pieces exit $?"
+python tools/cold_start_probe.py 3 > ${o}_cold_start.jsonl 2> ${o}_cold_start.err; echo "cold start exit $?"
+[ -x tools/pin_probe ] || nvcc -O2 -gencode arch=compute_100a,code=sm_100a -o tools/pin_probe tools/pin_probe.cu 2>/dev/null
+tools/pin_probe 256 2>&1 | grep -v "^  " > ${o}_pin_probe.txt; echo "pin probe exit $?"
